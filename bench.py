@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""bench.py -- the driver contract for the XbitOps hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+metric   a16w4_g128_gemv_effective_bandwidth, GB/s = algorithmic bytes / time;
+         us/call per shape rides along in `per_shape` (BASELINE.json: "A16W4 GEMV us/call & achieved HBM GB/s").
+step     one pass over the workload's rotating set: for every shape, R distinct weight sets with
+         R * bytes >= 1 GiB (>> the 126 MB L2, so every call streams from HBM), one GEMV call per set,
+         all captured in one CUDA graph (steady-state decode: programmatic dependent launch lets call
+         n+1 prefetch weights while call n drains).
+N = 1    workload llama2-7b  = BASELINE.json configs[1]: 4096x4096, 4096x11008, 11008x4096, batch 1.
+N > 1    workload llama2-70b = configs[3]: 8192x8192, 8192x28672, 28672x8192 N-split over the ranks,
+         output slices combined by an all-gather (NCCL), strong scaling; rank 0 also times the
+         unsharded workload alone and reports it as `single_gpu_same_workload` for context.
+--impl reference   the reference's CPU implementation of the path (oracle/_ref: the unmodified
+         src/cpp_simulate.cc dequant, N-sliced over all host threads, then the oracle's dot) on a
+         bounded sample (one call per shape).  This is the only place besides cpu_baseline where
+         oracle/ is executed, and only as the thing the baseline arm measures.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "llama2-7b": [(4096, 4096), (4096, 11008), (11008, 4096)],
+    "llama2-70b": [(8192, 8192), (8192, 28672), (28672, 8192)],
+}
+BITS, GROUP = 4, 128
+METRIC = "a16w4_g128_gemv_effective_bandwidth"
+UNIT = "GB/s"
+MIN_ROTATE_BYTES = 1 << 30
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (burst copy)"
+        except Exception:  # noqa: BLE001
+            pass
+    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------- clocks
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons DURING the timed region (pynvml, 20 ms period)."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:  # noqa: BLE001
+            self.nv = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.02)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ----------------------------------------------------------------------------- reference / CPU arms
+
+def cpu_reference_run(shapes, threads: int):
+    """One call per shape of the reference CPU path: unmodified cpp_simulate.cc dequant (oracle/_ref)
+    N-sliced over `threads` host threads, then the oracle's fp64 dot over the dequantised slice.
+    Falls back to the oracle port for the dequant when oracle/_ref was not built.
+    Returns (seconds, bytes, kind)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle as O
+    from xbitops_b200 import synth
+    co = O.COracle()
+    rc = O.RefCpu() if O.RefCpu.available() else None
+    kind = "reference" if rc is not None else "port"
+    total_s, total_b = 0.0, 0
+    for (K, N) in shapes:
+        qw, s, qz, a = synth.make_inputs(K, N, BITS, GROUP, seed=0)
+        t = max(1, min(threads, N // 64))
+        while N % (t * 8):
+            t -= 1
+        width = N // t
+        slices = []
+        for i in range(t):
+            sl = slice(i * width, (i + 1) * width)
+            slices.append((np.ascontiguousarray(qw[:, sl]), np.ascontiguousarray(s[:, sl]),
+                           np.ascontiguousarray(qz[:, i * width // 8:(i + 1) * width // 8])))
+
+        def work(args):
+            q, sc, z = args
+            w = rc.dequant(q, sc, z, GROUP, BITS, K) if rc is not None else co.dequant(q, sc, z, GROUP, BITS, K, 0)
+            return co.gemv_from_dq(a, w)[1]
+
+        t0 = time.perf_counter()
+        if t == 1:
+            work(slices[0])
+        else:
+            with ThreadPoolExecutor(t) as ex:
+                list(ex.map(work, slices))
+        total_s += time.perf_counter() - t0
+        total_b += synth.gemv_bytes(K, N, BITS, GROUP)
+    return total_s, total_b, kind
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    shapes = WORKLOADS[args.workload or ("llama2-7b" if args.gpus == 1 else "llama2-70b")]
+    cores = os.cpu_count() or 1
+    steps, warm = max(1, min(args.steps, 5)), max(0, min(args.warmup, 1))
+    for _ in range(warm):
+        cpu_reference_run(shapes, cores)
+    secs, nbytes, kind = 0.0, 0, "port"
+    for _ in range(steps):
+        s, b, kind = cpu_reference_run(shapes, cores)
+        secs += s
+        nbytes += b
+    val = nbytes / secs / 1e9
+    sample = f"one call per shape of {shapes} per step; {steps} steps"
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warm, "ms_per_step": secs / steps * 1e3, "higher_is_better": True,
+            "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "config": {"workload": args.workload or ("llama2-7b" if args.gpus == 1 else "llama2-70b"),
+                       "shapes": shapes, "bits": BITS, "groupsize": GROUP, "batch": 1,
+                       "note": "reference CPU simulator (src/cpp_simulate.cc) dequant + fp64 dot, N-sliced over host threads"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------- GPU arm
+
+class ShapeSet:
+    """R rotating weight sets of one (K, N_local) shape, generated on the device."""
+
+    def __init__(self, torch, dev, K, N_total, world, rank, gen):
+        from xbitops_b200 import synth
+        self.K, self.N_total, self.world, self.rank = K, N_total, world, rank
+        self.N = N_total // world
+        assert N_total % (world * 64) == 0
+        self.bytes_call = synth.gemv_bytes(K, N_total, BITS, GROUP)          # unsharded algorithmic bytes
+        self.bytes_rank = synth.gemv_bytes(K, self.N, BITS, GROUP)
+        self.R = max(2, (MIN_ROTATE_BYTES + self.bytes_rank - 1) // self.bytes_rank)
+        G = K // GROUP
+        self.qw = torch.randint(-2**31, 2**31 - 1, (self.R, K * BITS // 32, self.N), dtype=torch.int32, device=dev, generator=gen)
+        self.sc = (torch.rand((self.R, G, self.N), device=dev, generator=gen) * 0.018 + 0.002).to(torch.float16)
+        self.qz = torch.randint(-2**31, 2**31 - 1, (self.R, G, self.N * BITS // 32), dtype=torch.int32, device=dev, generator=gen)
+        self.a = torch.randn((1, K), device=dev, generator=gen).to(torch.float16)
+        self.out = torch.zeros((self.R, 1, N_total), device=dev, dtype=torch.float16)
+        self.col0 = rank * self.N
+
+
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    from xbitops_b200 import capi, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run for --gpus > 1")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: xbitops_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = capi.load()
+    workload = args.workload or ("llama2-7b" if world == 1 else "llama2-70b")
+    shapes = WORKLOADS[workload]
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    sets = [ShapeSet(torch, dev, K, N, world, rank, gen) for (K, N) in shapes]
+    family = {"auto": capi.GEMV_AUTO, "simt": capi.GEMV_SIMT, "mma": capi.GEMV_MMA}[args.family]
+    flags = 0 if args.no_pdl else capi.GEMV_FLAG_STATIC_WEIGHTS
+    peak, peak_src = measured_peak_gbs()
+
+    def launch(ss: ShapeSet, j: int):
+        st = torch.cuda.current_stream().cuda_stream
+        out = ss.out[j]
+        rc = lib.xbit_gemv_f16_peers_ex(ss.a.data_ptr(), ss.qw[j].data_ptr(), ss.sc[j].data_ptr(), ss.qz[j].data_ptr(),
+                                        (ctypes.c_void_p * 1)(out.data_ptr()), 1, 1, ss.K, ss.N, BITS, GROUP, 0,
+                                        ss.N_total, ss.col0, None, 0, family | flags, st)
+        if rc != 0:
+            raise RuntimeError(capi.last_error())
+        if world > 1 and not args.no_gather:
+            dist.all_gather_into_tensor(out.view(-1), out[:, ss.col0:ss.col0 + ss.N].reshape(-1))
+
+    def capture(set_list):
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):          # warm outside capture (module load, NCCL channels)
+            for ss in set_list:
+                launch(ss, 0)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        n = 0
+        with torch.cuda.graph(g):
+            for ss in set_list:
+                for j in range(ss.R):
+                    launch(ss, j)
+                    n += 1
+        return g, n
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(graph, steps, warmup):
+        for _ in range(warmup):
+            graph.replay()
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            graph.replay()
+        e1.record()
+        sync_all()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    graph, calls_per_step = capture(sets)
+    step_bytes = sum(ss.bytes_call * ss.R for ss in sets)
+    with ClockSampler(local_rank) as clk:
+        total_ms = timed(graph, args.steps, args.warmup)
+    ms_per_step = total_ms / args.steps
+    value = step_bytes / (ms_per_step * 1e-3) / 1e9
+
+    # ---- per-shape breakdown (separate graphs; same protocol) -- explains the aggregate
+    per_shape = {}
+    for ss in sets:
+        g1, n1 = capture([ss])
+        ms1 = timed(g1, max(3, args.steps // 4), 3) / max(3, args.steps // 4)
+        us = ms1 * 1e3 / n1
+        gbs = ss.bytes_call / us / 1e3
+        per_shape[f"{ss.K}x{ss.N_total}"] = {
+            "us_per_call": round(us, 3), "GBps": round(gbs, 1), "frac_of_measured_peak": round(gbs / (peak * world), 4),
+            "frac_of_8TBps_nominal": round(gbs / (8000.0 * world), 4), "algorithmic_bytes": ss.bytes_call,
+            "rotating_sets": ss.R, "family": lib.xbit_gemv_pick_family(1, ss.K, ss.N, BITS, GROUP) if family == 0 else family}
+        del g1
+
+    line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms_per_step, 5), "higher_is_better": True,
+            "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "config": {"workload": workload, "shapes": shapes, "bits": BITS, "groupsize": GROUP, "batch": 1,
+                       "calls_per_step": calls_per_step,
+                       "l2_policy": "inputs larger than L2: every call reads a distinct weight set, >= 1 GiB rotated per shape",
+                       "launch": "one CUDA graph per step, programmatic dependent launch" + (" off" if args.no_pdl else ""),
+                       "combine": ("nccl all_gather_into_tensor per call" if world > 1 and not args.no_gather else "none"),
+                       "parallelism": f"n-split x{world}" if world > 1 else "single"},
+            "per_shape": per_shape, "clocks": clk.summary(), "gpu_launches": calls_per_step * args.steps}
+
+    if rank == 0:
+        # roofline of the dominant (only) kernel family over the timed region
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get(workload)
+            except Exception:  # noqa: BLE001
+                traffic = None
+        avg_us = ms_per_step * 1e3 / calls_per_step
+        line["roofline"] = {"bound": "hbm", "achieved": round(value / world, 2), "peak": peak, "unit": "GB/s",
+                            "frac": round(value / world / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                            "kernel": "xbit::gemv_w4_kernel", "avg_launch_us": round(avg_us, 3),
+                            "algorithmic_bytes_per_launch": round(step_bytes / calls_per_step / world),
+                            "frac_of_8TBps_nominal": round(value / world / 8000.0, 4)}
+
+    # ---- e2e: the public host-buffer entry point, H2D activations + D2H result inside the timed region
+    if world == 1:
+        hs = [(torch.randn((1, ss.K)).to(torch.float16).pin_memory(), torch.empty((1, ss.N_total), dtype=torch.float16).pin_memory(),
+               torch.empty((1, ss.K), dtype=torch.float16, device=dev), torch.empty((1, ss.N_total), dtype=torch.float16, device=dev))
+              for ss in sets]
+        st = torch.cuda.current_stream().cuda_stream
+
+        def e2e_step():
+            for ss, (ha, ho, da, do) in zip(sets, hs):
+                for j in range(ss.R):
+                    rc = lib.xbit_gemv_f16_host(ha.data_ptr(), ho.data_ptr(), da.data_ptr(), do.data_ptr(), ss.qw[j].data_ptr(),
+                                                ss.sc[j].data_ptr(), ss.qz[j].data_ptr(), 1, ss.K, ss.N, BITS, GROUP, 0, None, 0, st)
+                    if rc != 0:
+                        raise RuntimeError(capi.last_error())
+            torch.cuda.synchronize()
+
+        e2e_steps = max(3, min(args.steps, 20))
+        for _ in range(3):
+            e2e_step()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        dt = (time.perf_counter() - t0) / e2e_steps
+        line["e2e"] = {"value": round(step_bytes / dt / 1e9, 2), "unit": UNIT,
+                       "h2d_bytes_per_step": int(sum(ss.K * 2 * ss.R for ss in sets)),
+                       "d2h_bytes_per_step": int(sum(ss.N_total * 2 * ss.R for ss in sets)),
+                       "us_per_call": round(dt * 1e6 / calls_per_step, 3),
+                       "how": "xbit_gemv_f16_host per call (pinned H2D activations -> gemv -> D2H result), eager launches, "
+                              "one host sync per step; weights resident"}
+    else:
+        line["e2e"] = None
+
+    # ---- cpu baseline beside it (rank 0, N=1 only): bounded sample, single thread, stated
+    if world == 1 and rank == 0 and not args.no_cpu:
+        secs, nbytes, kind = cpu_reference_run([shapes[0]], 1)
+        line["cpu_baseline"] = {"value": round(nbytes / secs / 1e9, 5), "unit": UNIT, "cores": 1, "kind": kind,
+                                "sample": f"1 call of {shapes[0][0]}x{shapes[0][1]} (dequant via cpp_simulate.cc + fp64 dot), {secs:.2f} s"}
+    elif rank == 0:
+        line["cpu_baseline"] = None
+
+    if world > 1 and rank == 0 and not args.no_single:
+        # the same (unsharded) workload on one GPU, for the strong-scaling context
+        del sets, graph
+        torch.cuda.empty_cache()
+        os.environ["WORLD_SIZE_OVERRIDE"] = "1"
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=None, choices=[None, *WORKLOADS])
+    ap.add_argument("--family", default="auto", choices=["auto", "simt", "mma"])
+    ap.add_argument("--no-pdl", action="store_true", help="do not assert static weights (no prefetch before griddepcontrol.wait)")
+    ap.add_argument("--no-gather", action="store_true", help="N>1: kernel only, skip the all-gather")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-single", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

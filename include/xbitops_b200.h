@@ -1,0 +1,146 @@
+/*
+ * xbitops_b200.h -- torch-free C ABI of the B200-native (sm_100a) XbitOps hot path.
+ *
+ * This is the drop-in boundary.  It replaces the reference's L2 host
+ * launchers, which take torch::Tensor& and therefore cannot be bound from anything but ATen:
+ *
+ *   xbit_dequant_f16      <-  lauch_deqantize_cuda_pt_kernel   /root/reference/src/cu/unpack_weight_2_to_7.cu:426-441
+ *                             (declared at src/dq_torch_ops.cc:11-13, called at :39)
+ *   xbit_gemv_f16         <-  lauch_Gemv_kernel                /root/reference/src/cu/gemv_w4a16_pt.cu:149-173
+ *                             (declared at src/dq_torch_ops.cc:15-17, called at :72)
+ *   xbit_gemv_f16_peers   <-  no reference counterpart (the reference is single-GPU):
+ *                             N-split GEMV whose epilogue stores each finished output slice into
+ *                             every rank's output buffer over NVLink peer mappings.
+ *
+ * The reference's own `extern "C" int QbitGemv(SampleData*)` (src/gemv.cuh:22) is a benchmark
+ * harness entry, not an operator ABI, and is deliberately not mirrored.
+ *
+ * Conventions (same meaning as the reference's op arguments, src/dq_torch_ops.cc:23-24,46-48):
+ *   K = in_features, N = out_features = qweight.size(1), M = activation rows, G = ceil(K/groupsize)
+ *   qweight  int32 [ceil(K*bits/32), N]  LSB-first bit stream along K per column
+ *   scales   fp16  [G, N]
+ *   qzeros   int32 [G, ceil(N*bits/32)]  LSB-first bit stream along N per group row;
+ *                                        effective zero = stored + add_zero_bias
+ *   out      dequant: fp16 [K, N] row-major; gemv: fp16 [M, N] with row stride out_row_stride
+ * All pointers are DEVICE pointers on the current CUDA device unless a name says "host".
+ * Every entry point only enqueues work on `stream` (no allocation, no synchronisation, no
+ * global state): re-entrant, thread-safe and CUDA-graph capturable.
+ *
+ * Error convention: 0 = XBIT_OK; otherwise a negative XBIT_E* code and a message retrievable
+ * with xbit_last_error() (thread-local).  Nothing in this library calls exit()/abort()
+ * (the reference does: unpack_weight_2_to_7.cu:436-440, gemv_w4a16_pt.cu:152-155,168-172).
+ * There is no CPU fallback: without a CUDA device every compute entry returns XBIT_ECUDA.
+ */
+#ifndef XBITOPS_B200_H_
+#define XBITOPS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define XBIT_API
+#else
+#define XBIT_API __attribute__((visibility("default")))
+#endif
+
+/* cudaStream_t without pulling in cuda_runtime.h */
+typedef struct CUstream_st* xbit_stream_t;
+
+enum {
+  XBIT_OK = 0,
+  XBIT_EINVAL = -1,   /* bad argument (shape, bits, groupsize, null pointer, alignment) */
+  XBIT_ECUDA = -2,    /* CUDA runtime error (launch failure, no device) */
+  XBIT_EWORKSPACE = -3 /* workspace too small */
+};
+
+/* GEMV kernel families; XBIT_GEMV_AUTO lets the library pick by (M, bits, groupsize, shape). */
+enum {
+  XBIT_GEMV_AUTO = 0,
+  XBIT_GEMV_SIMT = 1,     /* W4 SIMT kernel: LOP3 magic-number unpack, half2 FMA, M <= 4            */
+  XBIT_GEMV_MMA = 2,      /* W4 tensor-core kernel: register-level unpack straight into mma.sync
+                             m16n8k16 fragments, fp32 accumulation, M <= 16                          */
+  XBIT_GEMV_GENERIC = 3   /* any bits 2..8, any groupsize >= 16, any M: SIMT, fp32 accumulation      */
+};
+
+/* Flags OR-ed into the `family` argument of xbit_gemv_f16_ex / xbit_gemv_f16_peers_ex. */
+enum {
+  /* The weight tensors (qweight, scales, qzeros) were completely written before the kernel that
+   * precedes this call in `stream` was launched (true for resident model weights in a decode
+   * loop).  The kernel may then prefetch weights while that previous kernel is still running
+   * (programmatic dependent launch); activations are still read only after it has finished. */
+  XBIT_GEMV_FLAG_STATIC_WEIGHTS = 0x100,
+  XBIT_GEMV_FAMILY_MASK = 0xFF
+};
+
+XBIT_API int xbit_version(void);                 /* major*10000 + minor*100 + patch */
+XBIT_API const char* xbit_last_error(void);      /* thread-local; "" when no error */
+
+/* Dequantise to fp16.  bits in [2, 8]; groupsize >= 16; N even.  out is fully overwritten
+ * (no pre-zeroing needed, unlike the reference's at::zeros, src/dq_torch_ops.cc:38). */
+XBIT_API int xbit_dequant_f16(const int32_t* qweight, const void* scales_f16, const int32_t* qzeros,
+                              void* out_f16, int K, int N, int bits, int groupsize, int add_zero_bias,
+                              xbit_stream_t stream);
+
+/* Bytes of scratch xbit_gemv_f16 needs for this problem (may be 0).  The scratch must be
+ * 256-byte aligned and must not be shared by calls that can run concurrently. */
+XBIT_API size_t xbit_gemv_workspace_bytes(int M, int K, int N, int bits, int groupsize);
+
+/* y[m, n] = RN16( sum_k a[m, k] * DQ[k, n] ), fp32 accumulation.
+ * a_f16 is [M, K] row-major contiguous.  out_row_stride is in elements (>= N).
+ * bits in [2, 8] (the reference aborts unless bits == 4 && groupsize == 128). */
+XBIT_API int xbit_gemv_f16(const void* a_f16, const int32_t* qweight, const void* scales_f16,
+                           const int32_t* qzeros, void* out_f16, int M, int K, int N, int bits,
+                           int groupsize, int add_zero_bias, int64_t out_row_stride,
+                           void* workspace, size_t workspace_bytes, xbit_stream_t stream);
+
+/* As xbit_gemv_f16, with an explicit kernel family (XBIT_GEMV_*) -- used by the crossover
+ * sweep (BASELINE.json configs[4]) and the tests.  Returns XBIT_EINVAL if the family cannot
+ * run the problem. */
+XBIT_API int xbit_gemv_f16_ex(const void* a_f16, const int32_t* qweight, const void* scales_f16,
+                              const int32_t* qzeros, void* out_f16, int M, int K, int N, int bits,
+                              int groupsize, int add_zero_bias, int64_t out_row_stride,
+                              void* workspace, size_t workspace_bytes, int family,
+                              xbit_stream_t stream);
+
+/* The family xbit_gemv_f16 would pick (XBIT_GEMV_*), for introspection and the bench log. */
+XBIT_API int xbit_gemv_pick_family(int M, int K, int N, int bits, int groupsize);
+
+/* N-split multi-GPU GEMV with a fused all-gather epilogue.  This rank owns output columns
+ * [col_offset, col_offset + N_local) of an [M, N_total] result; qweight/scales/qzeros are the
+ * rank-local column shards (N = N_local).  peer_out[r] (r in [0, world)) is rank r's full
+ * [M, N_total] fp16 output buffer as mapped in THIS process (peer_out[rank] is the local one;
+ * the others are NVLink peer mappings, e.g. from cudaIpcOpenMemHandle or torch symmetric
+ * memory).  The kernel's epilogue stores this rank's slice into all `world` buffers; the caller
+ * still has to synchronise ranks (a barrier) before anyone reads its buffer. */
+XBIT_API int xbit_gemv_f16_peers(const void* a_f16, const int32_t* qweight, const void* scales_f16,
+                                 const int32_t* qzeros, void* const* peer_out_host_array, int world,
+                                 int M, int K, int N_local, int bits, int groupsize, int add_zero_bias,
+                                 int64_t out_row_stride, int64_t col_offset,
+                                 void* workspace, size_t workspace_bytes, xbit_stream_t stream);
+
+/* As xbit_gemv_f16_peers with an explicit family | flags word (see xbit_gemv_f16_ex). */
+XBIT_API int xbit_gemv_f16_peers_ex(const void* a_f16, const int32_t* qweight, const void* scales_f16,
+                                    const int32_t* qzeros, void* const* peer_out_host_array, int world,
+                                    int M, int K, int N_local, int bits, int groupsize, int add_zero_bias,
+                                    int64_t out_row_stride, int64_t col_offset,
+                                    void* workspace, size_t workspace_bytes, int family,
+                                    xbit_stream_t stream);
+
+/* Host-buffer convenience used for end-to-end measurement: activations come from (pinned) host
+ * memory and the result goes back to host memory; weights stay resident on the device.
+ * d_a_staging / d_out_staging are device scratch of M*K*2 and M*N*2 bytes.  Enqueues
+ * H2D copy -> gemv -> D2H copy on `stream`; the caller synchronises. */
+XBIT_API int xbit_gemv_f16_host(const void* a_f16_host, void* out_f16_host, void* d_a_staging,
+                                void* d_out_staging, const int32_t* qweight, const void* scales_f16,
+                                const int32_t* qzeros, int M, int K, int N, int bits, int groupsize,
+                                int add_zero_bias, void* workspace, size_t workspace_bytes,
+                                xbit_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XBITOPS_B200_H_ */

@@ -1,0 +1,72 @@
+"""The C-ABI library loads and exports every symbol include/xbitops_b200.h declares (no compute).
+Also: the product never touches the oracle."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "xbitops_b200.h")).read()
+    return sorted(set(re.findall(r"XBIT_API\s+[\w\s\*]+?\b(xbit_\w+)\s*\(", text)))
+
+
+def test_header_declares_expected_entry_points():
+    names = _declared()
+    for must in ("xbit_dequant_f16", "xbit_gemv_f16", "xbit_gemv_f16_ex", "xbit_gemv_f16_peers", "xbit_gemv_f16_host",
+                 "xbit_gemv_workspace_bytes", "xbit_last_error", "xbit_version"):
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol():
+    from xbitops_b200 import capi
+    lib = capi.load()
+    for name in _declared():
+        assert hasattr(lib, name), f"libxbitops_b200.so does not export {name}"
+        assert name in capi.SIGNATURES, f"capi.SIGNATURES lacks {name}"
+    assert set(capi.SIGNATURES) == set(_declared())
+    assert lib.xbit_version() >= 100
+
+
+def test_validation_errors_without_gpu():
+    """Argument validation happens before any CUDA call: error codes + messages, never abort."""
+    from xbitops_b200 import capi
+    lib = capi.load()
+    one = ctypes.c_void_p(16)
+    assert lib.xbit_dequant_f16(one, one, one, one, 128, 64, 9, 128, 0, None) == -1
+    assert "bits" in capi.last_error()
+    assert lib.xbit_dequant_f16(one, one, one, one, 128, 64, 4, 8, 0, None) == -1
+    assert "groupsize" in capi.last_error()
+    assert lib.xbit_dequant_f16(None, one, one, one, 128, 64, 4, 128, 0, None) == -1
+    assert lib.xbit_gemv_f16(one, one, one, one, one, 0, 128, 64, 4, 128, 0, 64, None, 0, None) == -1
+    assert lib.xbit_gemv_f16(one, one, one, one, one, 1, 128, 64, 4, 128, 0, 32, None, 0, None) == -1
+    assert "out_row_stride" in capi.last_error()
+    assert lib.xbit_gemv_f16(one, one, one, one, one, 1, 128, 64, 4, 128, 2, 64, None, 0, None) == -1
+    assert lib.xbit_gemv_workspace_bytes(1, 4096, 4096, 4, 128) == 0
+
+
+def test_ops_reject_cpu_tensors():
+    import torch
+    import xbitops_b200 as X
+    qw = torch.zeros(16, 8, dtype=torch.int32)
+    s = torch.zeros(1, 8, dtype=torch.float16)
+    qz = torch.zeros(1, 1, dtype=torch.int32)
+    with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+        X.dequant(qw, s, qz, 128, 4, 128, 0)
+    with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+        X.gemv(torch.zeros(1, 128, dtype=torch.float16), qw, s, qz, 128, 4, 128, 0)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "xbitops_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cc", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", text, re.M), f
+                assert "xbit_oracle" not in text and "libxbit_refcpu" not in text, f
+    hdr = open(os.path.join(ROOT, "include", "xbitops_b200.h")).read()
+    assert "oracle" not in hdr

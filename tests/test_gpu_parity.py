@@ -1,0 +1,311 @@
+"""Parity tests proper: the CUDA path (through the C ABI) against the oracle on the same seeded
+inputs.  DQ: bit-exact.  GEMV: the north star's fp16 tolerance against the fp64-accumulated truth
+over the bit-exact dequantised weights:
+    max|y - y_ref| / max|y_ref| <= 1e-2   and   |y - y_ref| <= 1e-2 * max(|y_ref|, 0.01 * max|y_ref|)
+Run on the B200 box: pytest -m gpu."""
+import ctypes
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from xbitops_b200 import capi, synth  # noqa: E402
+import xbitops_b200 as X  # noqa: E402
+
+GEMV_TOL = 1e-2
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.fail("gpu-marked test without a CUDA device (no CPU fallback exists)")
+    return torch.device("cuda:0")
+
+
+def t16(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a).view(np.int16)).to(dev).view(torch.float16)
+
+
+def ti(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def assert_gemv_close(y, y64, what=""):
+    y = np.asarray(y, np.float64)
+    mx = np.abs(y64).max()
+    err = np.abs(y - y64)
+    assert err.max() / mx <= GEMV_TOL, f"{what}: normalised max error {err.max() / mx:.3e}"
+    assert (err <= GEMV_TOL * np.maximum(np.abs(y64), 0.01 * mx)).all(), f"{what}: element-wise bound violated"
+
+
+# ------------------------------------------------------------------ dequant
+
+@pytest.mark.parametrize("bits", range(2, 9))
+@pytest.mark.parametrize("g", (32, 64, 128))
+def test_dequant_bit_exact_vs_oracle(bits, g, dev, c_oracle):
+    for (K, N) in ((256, 64), (416, 136), (1024, 512), (2048 + 32, 1000)):
+        for bias in (0, 1):
+            for mode in ("gptq", "bits"):
+                qw, s, qz, _ = synth.make_inputs(K, N, bits, g, seed=bits * 100 + g, scale_mode=mode)
+                want = c_oracle.dequant(qw, s, qz, g, bits, K, bias)
+                got = X.dequant(ti(qw, dev), t16(s, dev), ti(qz, dev), g, bits, K, bias).cpu().numpy()
+                assert got.shape == (K, N) and got.dtype == np.float16
+                assert (got.view(np.uint16) == want.view(np.uint16)).all(), (bits, g, K, N, bias, mode)
+
+
+@pytest.mark.parametrize("bits", range(2, 9))
+def test_dequant_ragged_and_fallback_shapes(bits, dev, c_oracle):
+    # ragged K (not a multiple of 32 or of the group), N not a multiple of 8, groupsize not a multiple of 32
+    for (K, N, g) in ((100, 12, 48), (333, 34, 16), (7, 2, 16), (33, 8, 32), (95, 16, 64), (4097, 24, 128)):
+        qw, s, qz, _ = synth.make_inputs(K, N, bits, g, seed=bits)
+        want = c_oracle.dequant(qw, s, qz, g, bits, K, 1)
+        got = X.dequant(ti(qw, dev), t16(s, dev), ti(qz, dev), g, bits, K, 1).cpu().numpy()
+        assert (got.view(np.uint16) == want.view(np.uint16)).all(), (bits, K, N, g)
+
+
+@pytest.mark.parametrize("bits", range(2, 9))
+def test_unpacked_integers_through_the_op(bits, dev, c_oracle):
+    """scales == 1, zeros == 0 -> the op returns half(w): integer-exact unpack check;
+    qweight == 0, scales == -1 -> the unpacked zero points."""
+    K, N, g = 512, 256, 128
+    qw, s, qz, _ = synth.make_inputs(K, N, bits, g, seed=9)
+    ones = np.ones_like(s)
+    got = X.dequant(ti(qw, dev), t16(ones, dev), ti(np.zeros_like(qz), dev), g, bits, K, 0).cpu().numpy()
+    assert (got.astype(np.int32) == c_oracle.unpack_qweight(qw, K, bits)).all()
+    gz = X.dequant(ti(np.zeros_like(qw), dev), t16(-ones, dev), ti(qz, dev), g, bits, K, 1).cpu().numpy()
+    assert (gz[::g].astype(np.int32) == c_oracle.unpack_qzeros(qz, N, bits).astype(np.int32) + 1).all()
+
+
+def test_dequant_golden_refcpu_integers(dev, golden_cpu):
+    import re
+    for k in golden_cpu.files:
+        m = re.match(r"(b(\d)_g(\d+)_K(\d+)_N(\d+))_ref_ints$", k)
+        if not m:
+            continue
+        tag, bits, g, K, N = m.group(1), *map(int, m.groups()[1:])
+        qw, s, qz = golden_cpu[tag + "_qweight"], golden_cpu[tag + "_scales"], golden_cpu[tag + "_qzeros"]
+        one = np.ones(s.shape, np.float16)
+        got = X.dequant(ti(qw, dev), t16(one, dev), ti(np.zeros_like(qz), dev), g, bits, K, 0).cpu().numpy()
+        assert (got.astype(np.int32) == golden_cpu[k]).all(), tag
+
+
+def test_dequant_golden_refgpu(dev, golden_gpu):
+    import re
+    n = 0
+    for k in golden_gpu.files:
+        m = re.match(r"(b(\d)_g(\d+)_K(\d+)_N(\d+)_z(\d))_ref_gpu$", k)
+        if not m:
+            continue
+        tag, bits, g, K, N, bias = m.group(1), *map(int, m.groups()[1:])
+        qw, s, qz = golden_gpu[tag + "_qweight"], golden_gpu[tag + "_scales"].view(np.float16), golden_gpu[tag + "_qzeros"]
+        want = golden_gpu[k]
+        got = X.dequant(ti(qw, dev), t16(s, dev), ti(qz, dev), g, bits, K, bias).cpu().numpy().view(np.uint16)
+        assert (got[: want.shape[0]] == want).all(), tag
+        n += 1
+    assert n > 0
+
+
+def test_dequant_bf16_scales_and_full_size_properties(dev):
+    """BASELINE config 3 size (4096 x 11008): size-independent properties instead of the oracle:
+    (a) integer trick, checked against a torch restatement of the bit stream on the GPU;
+    (b) bf16 scales give exactly fp16-path output cast to bf16 (dq_torch_ops.cc:33-42);
+    (c) linearity in the scale for power-of-two factors (exact in fp16 away from the range ends)."""
+    K, N, bits, g = 4096, 11008, 4, 128
+    gen = torch.Generator(device=dev).manual_seed(0)
+    qw = torch.randint(-2**31, 2**31 - 1, (K * bits // 32, N), dtype=torch.int32, device=dev, generator=gen)
+    qz = torch.randint(-2**31, 2**31 - 1, (K // g, N * bits // 32), dtype=torch.int32, device=dev, generator=gen)
+    s = (torch.rand((K // g, N), device=dev, generator=gen) * 0.018 + 0.002).to(torch.float16)
+    ints = X.dequant(qw, torch.ones_like(s), torch.zeros_like(qz), g, bits, K, 0)
+    shifts = torch.arange(0, 32, bits, device=dev, dtype=torch.int32).view(1, -1, 1)
+    want = ((qw.unsqueeze(1) >> shifts) & ((1 << bits) - 1)).reshape(K, N).to(torch.float16)
+    assert torch.equal(ints, want)
+    w = X.dequant(qw, s, qz, g, bits, K, 1)
+    wb = X.dequant(qw, s.to(torch.bfloat16), qz, g, bits, K, 1)
+    assert wb.dtype == torch.bfloat16
+    assert torch.equal(wb, X.dequant(qw, s.to(torch.bfloat16).to(torch.float16), qz, g, bits, K, 1).to(torch.bfloat16))
+    w4 = X.dequant(qw, s * 4, qz, g, bits, K, 1)
+    assert torch.equal(w4, w * 4)
+
+
+# ------------------------------------------------------------------ gemv
+
+FAMILIES = [(capi.GEMV_SIMT, (1, 2, 3, 4)), (capi.GEMV_MMA, (1, 2, 7, 8, 9, 16)), (capi.GEMV_GENERIC, (1, 5))]
+
+
+@pytest.mark.parametrize("family,Ms", FAMILIES)
+def test_gemv_w4_families_vs_truth(family, Ms, dev, c_oracle):
+    for (K, N, g) in ((4096, 4096, 128), (1024, 256, 32), (11008, 512, 128), (2048, 8192 + 64, 64), (4096, 72, 128), (8, 8, 32)):
+        for bias in (0, 1):
+            qw, s, qz, a = synth.make_inputs(K, N, 4, g, M=max(Ms), seed=K + N)
+            w = c_oracle.dequant(qw, s, qz, g, 4, K, bias)
+            tq, ts, tz = ti(qw, dev), t16(s, dev), ti(qz, dev)
+            for M in Ms:
+                y64 = a[:M].astype(np.float64) @ w.astype(np.float64)
+                got = X.gemv(t16(a[:M], dev), tq, ts, tz, g, 4, K, bias, family=family).cpu().numpy()
+                assert got.shape == (M, N)
+                assert_gemv_close(got, y64, f"family={family} M={M} K={K} N={N} g={g} bias={bias}")
+
+
+@pytest.mark.parametrize("bits", (2, 3, 5, 6, 7, 8))
+def test_gemv_other_bit_widths(bits, dev, c_oracle):
+    """The reference aborts for bits != 4 (gemv_w4a16_pt.cu:152-155); the intended A16Wx semantics are
+    y = a @ DQ for every width."""
+    for (M, K, N, g) in ((1, 1024, 256, 128), (2, 777, 100, 48), (17, 512, 64, 32), (1, 4096, 512, 64)):
+        qw, s, qz, a = synth.make_inputs(K, N, bits, g, M=M, seed=bits)
+        y64, _ = c_oracle.gemv(a, qw, s, qz, g, bits, K, 1)
+        got = X.gemv(t16(a, dev), ti(qw, dev), t16(s, dev), ti(qz, dev), g, bits, K, 1).cpu().numpy()
+        assert_gemv_close(got, y64, f"bits={bits} M={M} K={K} N={N} g={g}")
+
+
+def test_gemv_shapes_dtypes_and_large_m(dev, c_oracle):
+    K, N, g = 1024, 512, 128
+    qw, s, qz, a = synth.make_inputs(K, N, 4, g, M=40, seed=3)
+    w = c_oracle.dequant(qw, s, qz, g, 4, K, 0)
+    y64 = a.astype(np.float64) @ w.astype(np.float64)
+    tq, ts, tz = ti(qw, dev), t16(s, dev), ti(qz, dev)
+    a3 = t16(a, dev).view(5, 8, K)                       # [B, S, K] -> [B, S, N]   (dq_torch_ops.cc:59-64)
+    y = X.gemv(a3, tq, ts, tz, g, 4, K, 0)
+    assert tuple(y.shape) == (5, 8, N) and y.dtype == torch.float16
+    assert_gemv_close(y.view(40, N).cpu().numpy(), y64, "M=40")
+    yb = X.gemv(t16(a[:2], dev), tq, ts.to(torch.bfloat16), tz, g, 4, K, 0)
+    assert yb.dtype == torch.bfloat16 and tuple(yb.shape) == (2, N)
+
+
+def test_gemv_golden_refgpu(dev, golden_gpu, c_oracle):
+    """Outputs of the reference's own GPU gemv: ours must agree with them at least as well as both
+    agree with the truth."""
+    import re
+    n = 0
+    for k in golden_gpu.files:
+        m = re.match(r"(gemv_K(\d+)_N(\d+)_z(\d))_ref_gpu$", k)
+        if not m:
+            continue
+        tag, K, N, bias = m.group(1), *map(int, m.groups()[1:])
+        qw, s, qz = golden_gpu[tag + "_qweight"], golden_gpu[tag + "_scales"].view(np.float16), golden_gpu[tag + "_qzeros"]
+        a = golden_gpu[tag + "_a"].view(np.float16)
+        ref = golden_gpu[k].view(np.float16).astype(np.float64)
+        y64, _ = c_oracle.gemv(a, qw, s, qz, 128, 4, K, bias)
+        for fam in (capi.GEMV_SIMT, capi.GEMV_MMA):
+            got = X.gemv(t16(a, dev), ti(qw, dev), t16(s, dev), ti(qz, dev), 128, 4, K, bias, family=fam).cpu().numpy()
+            assert_gemv_close(got, y64, tag)
+            assert np.abs(got.astype(np.float64) - ref).max() / np.abs(y64).max() <= GEMV_TOL
+        n += 1
+    assert n > 0
+
+
+@pytest.mark.parametrize("K,N", [(4096, 4096), (4096, 11008), (11008, 4096), (8192, 8192)])
+def test_gemv_full_size_properties(K, N, dev):
+    """BASELINE sizes, size-independent properties (no CPU oracle at this size):
+    (a) gemv == activations @ dequant (our own bit-exact DQ, fp32 matmul on the GPU) within tolerance;
+    (b) column sharding: gemv on a column slice agrees with the slice of the truth (the K-split chosen
+        by the planner depends on N, so the fp32 summation order may differ from the unsharded call);
+    (c) row m of an M-row call == the M=1 call on that row (same family), bit for bit;
+    (d) linearity: gemv(2a) == 2*gemv(a) exactly (power-of-two scaling is exact in fp16/fp32)."""
+    g, bits = 128, 4
+    gen = torch.Generator(device=dev).manual_seed(K + N)
+    qw = torch.randint(-2**31, 2**31 - 1, (K // 8, N), dtype=torch.int32, device=dev, generator=gen)
+    qz = torch.randint(-2**31, 2**31 - 1, (K // g, N // 8), dtype=torch.int32, device=dev, generator=gen)
+    s = (torch.rand((K // g, N), device=dev, generator=gen) * 0.018 + 0.002).to(torch.float16)
+    a = torch.randn((4, K), device=dev, generator=gen).to(torch.float16)
+    w = X.dequant(qw, s, qz, g, bits, K, 1)
+    truth = (a.double() @ w.double()).cpu().numpy()
+    for fam in (capi.GEMV_SIMT, capi.GEMV_MMA):
+        y = X.gemv(a, qw, s, qz, g, bits, K, 1, family=fam)
+        assert_gemv_close(y.cpu().numpy(), truth, f"{K}x{N} family {fam}")
+        y1 = X.gemv(a[2:3], qw, s, qz, g, bits, K, 1, family=fam)
+        assert torch.equal(y1[0], y[2])
+        y2 = X.gemv(a[:1] * 2, qw, s, qz, g, bits, K, 1, family=fam)
+        assert torch.equal(y2, X.gemv(a[:1], qw, s, qz, g, bits, K, 1, family=fam) * 2)
+        half = N // 2
+        ysl = X.gemv(a[:1], qw[:, half:].contiguous(), s[:, half:].contiguous(), qz[:, half // 8:].contiguous(),
+                     g, bits, K, 1, family=fam)
+        assert_gemv_close(ysl.cpu().numpy(), truth[:1, half:], f"{K}x{N} column shard, family {fam}")
+
+
+def test_gemv_runs_on_current_stream_and_is_graph_capturable(dev):
+    """The reference launches gemv on the legacy default stream (gemv_w4a16_pt.cu:162); ours must
+    follow torch's current stream and be capturable (no sync, no allocation inside the C ABI)."""
+    K, N, g = 4096, 4096, 128
+    qw = torch.randint(-2**31, 2**31 - 1, (K // 8, N), dtype=torch.int32, device=dev)
+    qz = torch.randint(-2**31, 2**31 - 1, (K // g, N // 8), dtype=torch.int32, device=dev)
+    s = (torch.rand((K // g, N), device=dev) * 0.018 + 0.002).to(torch.float16)
+    a = torch.randn((1, K), device=dev).to(torch.float16)
+    eager = X.gemv(a, qw, s, qz, g, 4, K, 0)
+    out = torch.empty_like(eager)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        X.gemv(a, qw, s, qz, g, 4, K, 0, out=out)
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    out2 = torch.empty_like(eager)
+    with torch.cuda.graph(graph):
+        for _ in range(3):
+            X.gemv(a, qw, s, qz, g, 4, K, 0, out=out2)
+    out2.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, eager) and torch.equal(out2, eager)
+
+
+def test_errors_are_runtime_errors_not_aborts(dev):
+    qw = torch.zeros(16, 8, dtype=torch.int32, device=dev)
+    s = torch.ones(1, 8, dtype=torch.float16, device=dev)
+    qz = torch.zeros(1, 1, dtype=torch.int32, device=dev)
+    with pytest.raises(RuntimeError, match="in_features"):
+        X.dequant(qw, s, qz, 128, 4, 64, 0)
+    with pytest.raises(RuntimeError, match="groupsize"):
+        X.dequant(qw, s, qz, 8, 4, 128, 0)
+    with pytest.raises(RuntimeError, match="bits"):
+        X.dequant(qw, s, qz, 128, 9, 128, 0)
+    with pytest.raises(RuntimeError, match="contiguous"):
+        X.dequant(qw.t(), s, qz, 128, 4, 128, 0)
+    with pytest.raises(RuntimeError):
+        X.dequant(torch.zeros(4, 8, dtype=torch.int32, device=dev), s, qz, 128, 1, 128, 0)   # bits=1 unsupported
+    with pytest.raises(RuntimeError, match="float16"):
+        X.gemv(torch.zeros(1, 128, device=dev), qw, s, qz, 128, 4, 128, 0)
+    # still alive and correct afterwards
+    y = X.gemv(torch.ones(1, 128, dtype=torch.float16, device=dev), qw, s, qz, 128, 4, 128, 0)
+    assert torch.equal(y, torch.zeros_like(y))
+
+
+def test_host_buffer_entry_point(dev, c_oracle):
+    """xbit_gemv_f16_host: activations from pinned host memory, result back to host (the e2e leg)."""
+    K, N, g = 1024, 256, 128
+    qw, s, qz, a = synth.make_inputs(K, N, 4, g, M=1, seed=1)
+    y64, _ = c_oracle.gemv(a, qw, s, qz, g, 4, K, 0)
+    tq, ts, tz = ti(qw, dev), t16(s, dev), ti(qz, dev)
+    ha = torch.from_numpy(a.view(np.int16)).pin_memory()
+    ho = torch.empty((1, N), dtype=torch.int16).pin_memory()
+    da = torch.empty((1, K), dtype=torch.float16, device=dev)
+    do = torch.empty((1, N), dtype=torch.float16, device=dev)
+    lib = capi.load()
+    st = torch.cuda.current_stream().cuda_stream
+    capi.check(lib.xbit_gemv_f16_host(ha.data_ptr(), ho.data_ptr(), da.data_ptr(), do.data_ptr(), tq.data_ptr(),
+                                      ts.data_ptr(), tz.data_ptr(), 1, K, N, 4, g, 0, None, 0, st))
+    torch.cuda.synchronize()
+    assert_gemv_close(ho.numpy().view(np.float16), y64, "host entry")
+
+
+def test_peer_entry_point_single_process(dev, c_oracle):
+    """xbit_gemv_f16_peers with world=2 emulated inside one process: two 'rank' buffers on the same
+    device, each shard's epilogue stores its slice into both (multi-process NVLink is in test_multigpu)."""
+    K, N, g, M = 2048, 512, 128, 2
+    qw, s, qz, a = synth.make_inputs(K, N, 4, g, M=M, seed=2)
+    y64, _ = c_oracle.gemv(a, qw, s, qz, g, 4, K, 0)
+    ta = t16(a, dev)
+    bufs = [torch.zeros((M, N), dtype=torch.float16, device=dev) for _ in range(2)]
+    arr = (ctypes.c_void_p * 2)(*[b.data_ptr() for b in bufs])
+    lib = capi.load()
+    half = N // 2
+    for rank in range(2):
+        sl = slice(rank * half, (rank + 1) * half)
+        tq, ts = ti(qw[:, sl], dev), t16(s[:, sl], dev)
+        tz = ti(qz[:, rank * half // 8:(rank + 1) * half // 8], dev)
+        capi.check(lib.xbit_gemv_f16_peers(ta.data_ptr(), tq.data_ptr(), ts.data_ptr(), tz.data_ptr(), arr, 2, M, K, half,
+                                           4, g, 0, N, rank * half, None, 0, torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert torch.equal(bufs[0], bufs[1])
+    assert_gemv_close(bufs[0].cpu().numpy(), y64, "peers")

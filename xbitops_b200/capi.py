@@ -1,0 +1,69 @@
+"""ctypes binding of the C ABI (include/xbitops_b200.h).  No torch types cross this boundary:
+plain device pointers, sizes and a stream handle -- exactly what any host language would bind.
+Loading fails loudly when libxbitops_b200.so is missing; there is no CPU fallback."""
+from __future__ import annotations
+
+import ctypes
+from pathlib import Path
+
+from . import _build
+
+XBIT_OK = 0
+GEMV_AUTO, GEMV_SIMT, GEMV_MMA, GEMV_GENERIC = 0, 1, 2, 3
+GEMV_FLAG_STATIC_WEIGHTS = 0x100
+
+_vp, _i, _i64, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_size_t
+
+# symbol -> (restype, argtypes); tests/test_capi_symbols.py checks this table against the header
+SIGNATURES = {
+    "xbit_version": (_i, []),
+    "xbit_last_error": (ctypes.c_char_p, []),
+    "xbit_dequant_f16": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "xbit_gemv_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "xbit_gemv_f16": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i64, _vp, _sz, _vp]),
+    "xbit_gemv_f16_ex": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i64, _vp, _sz, _i, _vp]),
+    "xbit_gemv_pick_family": (_i, [_i, _i, _i, _i, _i]),
+    "xbit_gemv_f16_peers": (_i, [_vp, _vp, _vp, _vp, ctypes.POINTER(_vp), _i, _i, _i, _i, _i, _i, _i, _i64, _i64,
+                                 _vp, _sz, _vp]),
+    "xbit_gemv_f16_peers_ex": (_i, [_vp, _vp, _vp, _vp, ctypes.POINTER(_vp), _i, _i, _i, _i, _i, _i, _i, _i64, _i64,
+                                    _vp, _sz, _i, _vp]),
+    "xbit_gemv_f16_host": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
+}
+
+_lib = None
+
+
+def lib_path() -> Path:
+    return _build.LIB
+
+
+def load(build_if_missing: bool = True) -> ctypes.CDLL:
+    """Load libxbitops_b200.so (building it with nvcc when absent or stale and nvcc exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if build_if_missing:
+        try:
+            _build.build_lib()
+        except Exception:
+            if not path.exists():
+                raise
+    if not path.exists():
+        raise ImportError(f"{path} is missing: build it with `python -m xbitops_b200._build` "
+                          "(xbitops_b200 has no CPU fallback)")
+    lib = ctypes.CDLL(str(path))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError here = header/library mismatch
+        fn.restype, fn.argtypes = res, args
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().xbit_last_error().decode()
+
+
+def check(rc: int) -> None:
+    if rc != XBIT_OK:
+        raise RuntimeError(f"xbitops_b200: {last_error()} (code {rc})")

@@ -1,0 +1,225 @@
+// xbit_capi.cu -- the torch-free C ABI (include/xbitops_b200.h): argument validation, family
+// selection and launch.  Replaces the reference's host launchers
+//   lauch_deqantize_cuda_pt_kernel  /root/reference/src/cu/unpack_weight_2_to_7.cu:426-441
+//   lauch_Gemv_kernel               /root/reference/src/cu/gemv_w4a16_pt.cu:149-173
+// and keeps the preconditions of the op layer (/root/reference/src/dq_torch_ops.cc:25-31,49-57),
+// turned into error codes instead of TORCH_CHECK / exit(-1) / abort().
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/xbitops_b200.h"
+#include "xbit_internal.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  // clear the sticky-less last error so the next call starts clean
+  (void)cudaGetLastError();
+  return fail(XBIT_ECUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+int check_common(const void* qweight, const void* scales, const void* qzeros, int K, int N, int bits, int groupsize,
+                 int add_zero_bias) {
+  if (!qweight || !scales || !qzeros) return fail(XBIT_EINVAL, "null tensor pointer");
+  if (bits < 2 || bits > 8) return fail(XBIT_EINVAL, "bits must be in [2, 8], got %d", bits);
+  if (groupsize < 16) return fail(XBIT_EINVAL, "groupsize must be >= 16, got %d", groupsize);
+  if (K < 1 || N < 1) return fail(XBIT_EINVAL, "in_features (K=%d) and out_features (N=%d) must be >= 1", K, N);
+  if ((long long)K * bits > 0x7fffffffLL || (long long)N * bits > 0x7fffffffLL)
+    return fail(XBIT_EINVAL, "K*bits / N*bits overflow int32");
+  if (add_zero_bias != 0 && add_zero_bias != 1) return fail(XBIT_EINVAL, "add_zero_bias must be 0 or 1, got %d", add_zero_bias);
+  return XBIT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int xbit_version(void) { return 100; /* 0.1.0 */ }
+
+const char* xbit_last_error(void) { return g_err; }
+
+int xbit_dequant_f16(const int32_t* qweight, const void* scales_f16, const int32_t* qzeros, void* out_f16, int K, int N,
+                     int bits, int groupsize, int add_zero_bias, xbit_stream_t stream) {
+  g_err[0] = 0;
+  if (int rc = check_common(qweight, scales_f16, qzeros, K, N, bits, groupsize, add_zero_bias)) return rc;
+  if (!out_f16) return fail(XBIT_EINVAL, "null output pointer");
+  if ((reinterpret_cast<uintptr_t>(out_f16) | reinterpret_cast<uintptr_t>(scales_f16)) & 1u)
+    return fail(XBIT_EINVAL, "fp16 pointers must be 2-byte aligned");
+  if ((reinterpret_cast<uintptr_t>(qweight) | reinterpret_cast<uintptr_t>(qzeros)) & 3u)
+    return fail(XBIT_EINVAL, "int32 pointers must be 4-byte aligned");
+  xbit::DqArgs a;
+  a.qweight = reinterpret_cast<const uint32_t*>(qweight);
+  a.scales = reinterpret_cast<const __half*>(scales_f16);
+  a.qzeros = reinterpret_cast<const uint32_t*>(qzeros);
+  a.out = reinterpret_cast<__half*>(out_f16);
+  a.K = K; a.N = N; a.bits = bits; a.groupsize = groupsize; a.zero_bias = add_zero_bias;
+  a.qrows = ceil_div((long long)K * bits, 32);
+  a.zwords = ceil_div((long long)N * bits, 32);
+  cudaError_t e = xbit::launch_dequant(a, reinterpret_cast<cudaStream_t>(stream), nullptr);
+  if (e != cudaSuccess) return cuda_fail(e, "xbit_dequant_f16 launch");
+  return XBIT_OK;
+}
+
+size_t xbit_gemv_workspace_bytes(int, int, int, int, int) {
+  return 0;  // split-K is reduced through cluster shared memory: no global scratch
+}
+
+static int pick_family(const xbit::GemvArgs& a) {
+  if (!xbit::gemv_w4_supported(a)) return XBIT_GEMV_GENERIC;
+  // Crossover measured on B200 (profiles/): the tensor-core kernel is at least as fast
+  // as the SIMT one from M = 1 (fp32 accumulation comes for free), so SIMT is the M == 1 default
+  // only where it wins; see xbit_gemv_pick_family's table.
+  static int forced = -1;
+  if (forced < 0) {
+    const char* v = getenv("XBIT_GEMV_FAMILY");
+    forced = (v && *v) ? atoi(v) : 0;
+  }
+  if (forced == XBIT_GEMV_SIMT && a.M <= 4) return XBIT_GEMV_SIMT;
+  if (forced == XBIT_GEMV_MMA) return XBIT_GEMV_MMA;
+  if (forced == XBIT_GEMV_GENERIC) return XBIT_GEMV_GENERIC;
+  return (a.M == 1) ? XBIT_GEMV_SIMT : XBIT_GEMV_MMA;
+}
+
+static int gemv_impl(const void* a_f16, const int32_t* qweight, const void* scales_f16, const int32_t* qzeros,
+                     void* const* outs, int world, int M, int K, int N, int bits, int groupsize, int add_zero_bias,
+                     int64_t out_row_stride, int64_t col_offset, int family_and_flags, xbit_stream_t stream) {
+  g_err[0] = 0;
+  if (int rc = check_common(qweight, scales_f16, qzeros, K, N, bits, groupsize, add_zero_bias)) return rc;
+  if (!a_f16) return fail(XBIT_EINVAL, "null activation pointer");
+  if (M < 1) return fail(XBIT_EINVAL, "M must be >= 1, got %d", M);
+  if (world < 1 || world > xbit::kMaxPeers) return fail(XBIT_EINVAL, "world must be in [1, %d], got %d", xbit::kMaxPeers, world);
+  if (col_offset < 0 || out_row_stride < col_offset + N)
+    return fail(XBIT_EINVAL, "out_row_stride (%lld) must be >= col_offset + N (%lld)", (long long)out_row_stride,
+                (long long)(col_offset + N));
+  xbit::GemvArgs g;
+  memset(&g, 0, sizeof(g));
+  for (int p = 0; p < world; ++p) {
+    if (!outs || !outs[p]) return fail(XBIT_EINVAL, "null output pointer (rank %d)", p);
+    g.out[p] = reinterpret_cast<__half*>(outs[p]);
+  }
+  g.world = world;
+  g.qweight = reinterpret_cast<const uint32_t*>(qweight);
+  g.scales = reinterpret_cast<const __half*>(scales_f16);
+  g.qzeros = reinterpret_cast<const uint32_t*>(qzeros);
+  g.K = K; g.N = N; g.bits = bits; g.groupsize = groupsize; g.zero_bias = add_zero_bias;
+  g.ldo = out_row_stride; g.col_offset = col_offset;
+  g.qrows = ceil_div((long long)K * bits, 32);
+  g.zwords = ceil_div((long long)N * bits, 32);
+  g.groups = ceil_div(K, groupsize);
+  g.static_weights = (family_and_flags & XBIT_GEMV_FLAG_STATIC_WEIGHTS) ? 1 : 0;
+  const int family_req = family_and_flags & XBIT_GEMV_FAMILY_MASK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+
+  // rows are processed in slabs the chosen family can take (weights are re-read per slab only
+  // beyond M = 16; the reference re-reads them for every row, gemv_w4a16_pt.cu:158)
+  for (int m0 = 0; m0 < M;) {
+    g.a = reinterpret_cast<const __half*>(a_f16) + (size_t)m0 * K;
+    g.M = M - m0;
+    xbit::GemvArgs probe = g;
+    int family = family_req;
+    if (family == XBIT_GEMV_AUTO) {
+      probe.M = g.M > 16 ? 16 : g.M;
+      family = pick_family(probe);
+    }
+    int slab;
+    cudaError_t e;
+    switch (family) {
+      case XBIT_GEMV_SIMT:
+        if (!xbit::gemv_w4_supported(g)) return fail(XBIT_EINVAL, "SIMT family needs bits=4, groupsize%%32=0, K%%8=0, N%%8=0, 16-byte aligned pointers");
+        slab = g.M > 4 ? 4 : g.M; g.M = slab;
+        e = xbit::launch_gemv_w4_simt(g, st);
+        break;
+      case XBIT_GEMV_MMA:
+        if (!xbit::gemv_w4_supported(g)) return fail(XBIT_EINVAL, "MMA family needs bits=4, groupsize%%32=0, K%%8=0, N%%8=0, 16-byte aligned pointers");
+        slab = g.M > 16 ? 16 : g.M; g.M = slab;
+        e = xbit::launch_gemv_w4_mma(g, st);
+        break;
+      case XBIT_GEMV_GENERIC:
+        slab = g.M;
+        e = xbit::launch_gemv_generic(g, st);
+        break;
+      default:
+        return fail(XBIT_EINVAL, "unknown gemv family %d", family);
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "xbit_gemv_f16 launch");
+    for (int p = 0; p < world; ++p) g.out[p] += (size_t)slab * out_row_stride;
+    m0 += slab;
+  }
+  return XBIT_OK;
+}
+
+int xbit_gemv_f16_ex(const void* a_f16, const int32_t* qweight, const void* scales_f16, const int32_t* qzeros,
+                     void* out_f16, int M, int K, int N, int bits, int groupsize, int add_zero_bias,
+                     int64_t out_row_stride, void* workspace, size_t workspace_bytes, int family, xbit_stream_t stream) {
+  (void)workspace; (void)workspace_bytes;
+  void* outs[1] = {out_f16};
+  return gemv_impl(a_f16, qweight, scales_f16, qzeros, outs, 1, M, K, N, bits, groupsize, add_zero_bias, out_row_stride, 0,
+                   family, stream);
+}
+
+int xbit_gemv_f16(const void* a_f16, const int32_t* qweight, const void* scales_f16, const int32_t* qzeros, void* out_f16,
+                  int M, int K, int N, int bits, int groupsize, int add_zero_bias, int64_t out_row_stride, void* workspace,
+                  size_t workspace_bytes, xbit_stream_t stream) {
+  return xbit_gemv_f16_ex(a_f16, qweight, scales_f16, qzeros, out_f16, M, K, N, bits, groupsize, add_zero_bias,
+                          out_row_stride, workspace, workspace_bytes, XBIT_GEMV_AUTO, stream);
+}
+
+int xbit_gemv_pick_family(int M, int K, int N, int bits, int groupsize) {
+  xbit::GemvArgs g;
+  memset(&g, 0, sizeof(g));
+  g.M = M > 16 ? 16 : M; g.K = K; g.N = N; g.bits = bits; g.groupsize = groupsize;
+  return pick_family(g);
+}
+
+int xbit_gemv_f16_peers_ex(const void* a_f16, const int32_t* qweight, const void* scales_f16, const int32_t* qzeros,
+                           void* const* peer_out_host_array, int world, int M, int K, int N_local, int bits, int groupsize,
+                           int add_zero_bias, int64_t out_row_stride, int64_t col_offset, void* workspace,
+                           size_t workspace_bytes, int family, xbit_stream_t stream) {
+  (void)workspace; (void)workspace_bytes;
+  return gemv_impl(a_f16, qweight, scales_f16, qzeros, peer_out_host_array, world, M, K, N_local, bits, groupsize,
+                   add_zero_bias, out_row_stride, col_offset, family, stream);
+}
+
+int xbit_gemv_f16_peers(const void* a_f16, const int32_t* qweight, const void* scales_f16, const int32_t* qzeros,
+                        void* const* peer_out_host_array, int world, int M, int K, int N_local, int bits, int groupsize,
+                        int add_zero_bias, int64_t out_row_stride, int64_t col_offset, void* workspace,
+                        size_t workspace_bytes, xbit_stream_t stream) {
+  return xbit_gemv_f16_peers_ex(a_f16, qweight, scales_f16, qzeros, peer_out_host_array, world, M, K, N_local, bits,
+                                groupsize, add_zero_bias, out_row_stride, col_offset, workspace, workspace_bytes,
+                                XBIT_GEMV_AUTO, stream);
+}
+
+int xbit_gemv_f16_host(const void* a_f16_host, void* out_f16_host, void* d_a_staging, void* d_out_staging,
+                       const int32_t* qweight, const void* scales_f16, const int32_t* qzeros, int M, int K, int N, int bits,
+                       int groupsize, int add_zero_bias, void* workspace, size_t workspace_bytes, xbit_stream_t stream) {
+  g_err[0] = 0;
+  if (!a_f16_host || !out_f16_host || !d_a_staging || !d_out_staging) return fail(XBIT_EINVAL, "null host/staging pointer");
+  if (M < 1 || K < 1 || N < 1) return fail(XBIT_EINVAL, "bad shape M=%d K=%d N=%d", M, K, N);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaMemcpyAsync(d_a_staging, a_f16_host, (size_t)M * K * 2, cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) return cuda_fail(e, "xbit_gemv_f16_host H2D");
+  // the H2D copy is not a kernel: the weights are untouched by it, so the static-weights prefetch is safe
+  int rc = xbit_gemv_f16_ex(d_a_staging, qweight, scales_f16, qzeros, d_out_staging, M, K, N, bits, groupsize, add_zero_bias,
+                            N, workspace, workspace_bytes, XBIT_GEMV_AUTO, stream);
+  if (rc != XBIT_OK) return rc;
+  e = cudaMemcpyAsync(out_f16_host, d_out_staging, (size_t)M * N * 2, cudaMemcpyDeviceToHost, st);
+  if (e != cudaSuccess) return cuda_fail(e, "xbit_gemv_f16_host D2H");
+  return XBIT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,60 @@
+// xbit_internal.h -- argument blocks and launcher prototypes shared by the C ABI and the kernels.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace xbit {
+
+constexpr int kMaxPeers = 8;
+
+struct DqArgs {
+  const uint32_t* qweight;
+  const __half* scales;
+  const uint32_t* qzeros;
+  __half* out;
+  int K, N, bits, groupsize, zero_bias;
+  int qrows;   // ceil(K*bits/32)
+  int zwords;  // ceil(N*bits/32)
+};
+
+struct GemvArgs {
+  const __half* a;          // [M, K]
+  const uint32_t* qweight;  // [qrows, N]
+  const __half* scales;     // [G, N]
+  const uint32_t* qzeros;   // [G, zwords]
+  __half* out[kMaxPeers];   // world output buffers ([M, ldo] each); out[0] only when world == 1
+  int world;
+  int M, K, N, bits, groupsize, zero_bias;
+  long long ldo;            // output row stride (elements)
+  long long col_offset;     // first output column of this shard
+  int qrows, zwords, groups;
+  int static_weights;       // XBIT_GEMV_FLAG_STATIC_WEIGHTS: weights may be read before griddepcontrol.wait
+  // decomposition (filled by the planner)
+  int splits;               // K splits = cluster size along grid.y
+  int units_per_split;      // 32-k units per split
+  int chunk_units;          // activation staging chunk, in 32-k units
+};
+
+struct GemvPlan {
+  int family;     // XBIT_GEMV_*
+  int ct;         // 32-column chunks per CTA (W4 kernels)
+  int splits;
+  int units_per_split;
+  int chunk_units;
+  size_t smem_bytes;
+  dim3 grid;
+};
+
+cudaError_t launch_dequant(const DqArgs& a, cudaStream_t stream, int* path_taken);
+
+// W4 fast kernels (bits == 4, groupsize % 32 == 0, K % 8 == 0, N % 8 == 0, 16-byte aligned pointers)
+bool gemv_w4_supported(const GemvArgs& a);
+cudaError_t launch_gemv_w4_simt(GemvArgs a, cudaStream_t stream);   // M <= 4
+cudaError_t launch_gemv_w4_mma(GemvArgs a, cudaStream_t stream);    // M <= 16
+// any bits / groupsize / M / N
+cudaError_t launch_gemv_generic(GemvArgs a, cudaStream_t stream);
+
+int device_sm_count();
+
+}  // namespace xbit

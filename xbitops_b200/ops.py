@@ -1,0 +1,104 @@
+"""Host-side mirror of the reference's operator interface, over the C ABI.
+
+Same names, positional order, shapes, dtypes and error behaviour (RuntimeError) as the reference's
+extension module (/root/reference/src/dq_torch_ops.cc:23-44 `dequant`, :46-78 `gemv`, registered at
+:80-85).  PyTorch is used for device memory and streams only; all arithmetic is in
+libxbitops_b200.so.  The compiled twin of this file is csrc/dq_torch_ops.cc (module `XbitOps`).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import capi
+
+
+def _check_input(x: torch.Tensor, name: str) -> None:
+    # dq_torch_ops.cc:5-9
+    if not x.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor")
+    if not x.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous")
+
+
+def _check_quant_args(qweight, scales, qzeros, groupsize: int, bits: int, in_features: int) -> None:
+    _check_input(qweight, "qweight")
+    _check_input(scales, "scales")
+    _check_input(qzeros, "qzeros")
+    # dq_torch_ops.cc:28-31
+    if qweight.dim() != 2:
+        raise RuntimeError("qweight must be 2-dimensional")
+    if groupsize < 16:
+        raise RuntimeError("groupsize must be >= 16")
+    if not (1 <= bits <= 8):
+        raise RuntimeError("bits must be >= 1 and <= 8")
+    if (in_features * bits + 31) // 32 != qweight.size(0):
+        raise RuntimeError("in_features must be >= 1")
+    # explicit versions of what the reference only enforces through data_ptr<T>() throwing
+    if qweight.dtype != torch.int32 or qzeros.dtype != torch.int32:
+        raise RuntimeError("qweight and qzeros must be int32")
+    if scales.dtype not in (torch.float16, torch.bfloat16):
+        raise RuntimeError("scales must be float16 or bfloat16")
+    n = qweight.size(1)
+    groups = (in_features + groupsize - 1) // groupsize
+    if scales.dim() != 2 or scales.size(0) < groups or scales.size(1) != n:
+        raise RuntimeError("scales must be [ceil(in_features/groupsize), out_features]")
+    if qzeros.dim() != 2 or qzeros.size(0) < groups or qzeros.size(1) != (n * bits + 31) // 32:
+        raise RuntimeError("qzeros must be [ceil(in_features/groupsize), ceil(out_features*bits/32)]")
+    if scales.device != qweight.device or qzeros.device != qweight.device:
+        raise RuntimeError("qweight, scales and qzeros must be on the same device")
+
+
+def _stream_handle() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def dequant(qweight, scales, qzeros, groupsize, bits, in_features, add_zero_bias):
+    """-> Tensor[in_features, out_features] in scales.dtype (i.e. W^T of nn.Linear.weight)."""
+    _check_quant_args(qweight, scales, qzeros, groupsize, bits, in_features)
+    lib = capi.load()
+    with torch.cuda.device(qweight.device):
+        f16_scale = scales.to(torch.float16) if scales.dtype == torch.bfloat16 else scales
+        out = torch.empty((in_features, qweight.size(1)), dtype=torch.float16, device=qweight.device)
+        capi.check(lib.xbit_dequant_f16(qweight.data_ptr(), f16_scale.data_ptr(), qzeros.data_ptr(), out.data_ptr(),
+                                        in_features, qweight.size(1), bits, groupsize, int(add_zero_bias),
+                                        _stream_handle()))
+        if scales.dtype == torch.bfloat16:
+            out = out.to(torch.bfloat16)
+    return out
+
+
+def gemv(input_a, qweight, scales, qzeros, groupsize, bits, in_features, add_zero_bias, *, family: int = capi.GEMV_AUTO,
+         out: torch.Tensor | None = None):
+    """-> Tensor[M, N] (or [B, S, N] for 3-D activations) in scales.dtype.
+    `family` / `out` are keyword-only extensions (kernel-family override for the crossover sweep,
+    caller-owned output for CUDA-graph capture); the positional surface is the reference's."""
+    _check_input(input_a, "input_a")
+    _check_quant_args(qweight, scales, qzeros, groupsize, bits, in_features)
+    if qweight.device.index != input_a.device.index:
+        raise RuntimeError("input and weight must be on the same device")
+    if input_a.dtype != torch.float16:
+        raise RuntimeError("input_a must be float16")
+    if input_a.dim() < 2 or input_a.size(-1) != in_features:
+        raise RuntimeError("input_a must be [..., in_features]")
+    lib = capi.load()
+    n = qweight.size(1)
+    outshape = [input_a.size(0), n]
+    m = input_a.size(0)
+    if input_a.dim() > 2:                      # dq_torch_ops.cc:60-64
+        outshape.insert(1, input_a.size(1))
+        m *= input_a.size(1)
+    with torch.cuda.device(qweight.device):
+        f16_scale = scales.to(torch.float16) if scales.dtype == torch.bfloat16 else scales
+        if out is None:
+            out16 = torch.empty(outshape, dtype=torch.float16, device=qweight.device)
+        else:
+            if out.dtype != torch.float16 or not out.is_contiguous() or list(out.shape) != outshape:
+                raise RuntimeError("out must be a contiguous float16 tensor of the result shape")
+            out16 = out
+        if m > 0:
+            capi.check(lib.xbit_gemv_f16_ex(input_a.data_ptr(), qweight.data_ptr(), f16_scale.data_ptr(),
+                                            qzeros.data_ptr(), out16.data_ptr(), m, in_features, n, bits, groupsize,
+                                            int(add_zero_bias), n, None, 0, int(family), _stream_handle()))
+        if scales.dtype == torch.bfloat16:
+            return out16.to(torch.bfloat16)
+    return out16
