@@ -60,7 +60,7 @@ enum {
 /* GEMV kernel families; XBIT_GEMV_AUTO lets the library pick by (M, bits, groupsize, shape). */
 enum {
   XBIT_GEMV_AUTO = 0,
-  XBIT_GEMV_SIMT = 1,     /* W4 SIMT kernel: LOP3 magic-number unpack, half2 FMA, M <= 4            */
+  XBIT_GEMV_SIMT = 1,     /* W4 SIMT GEMV: LOP3 magic-number unpack, half2 FMA, one row per launch  */
   XBIT_GEMV_MMA = 2,      /* W4 tensor-core kernel: register-level unpack straight into mma.sync
                              m16n8k16 fragments, fp32 accumulation, M <= 16                          */
   XBIT_GEMV_GENERIC = 3   /* any bits 2..8, any groupsize >= 16, any M: SIMT, fp32 accumulation      */

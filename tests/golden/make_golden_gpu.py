@@ -18,8 +18,8 @@ sys.path.insert(0, ROOT)
 from oracle import oracle as O  # noqa: E402
 from xbitops_b200 import synth  # noqa: E402
 
-CASES = [(bits, g, K, N, bias) for bits in range(2, 9) for (g, K, N) in ((32, 128, 64), (128, 256, 128)) for bias in (0, 1)]
-GEMV_CASES = [(4096, 64, 0), (4096, 128, 1), (1024, 64, 0)]      # (K, N, bias): b=4, g=128, M=1
+CASES = [(bits, g, K, N, bias) for bits in range(2, 9) for (g, K, N) in ((32, 96, 32), (128, 256, 64)) for bias in (0, 1)]
+GEMV_CASES = [(1024, 64, 0), (1024, 128, 1), (4096, 64, 0)]      # (K, N, bias): b=4, g=128, M=1
 
 
 def main():

@@ -110,10 +110,10 @@ def main():
 
     print("== GEMV vs fp64 truth (normalised max error; bar 1e-2)")
     worst = {}
-    for fam, name, Ms in ((capi.GEMV_SIMT, "simt", (1, 2, 3, 4)), (capi.GEMV_MMA, "mma", (1, 2, 5, 8, 9, 16)),
+    for fam, name, Ms in ((capi.GEMV_SIMT, "simt", (1, 3)), (capi.GEMV_MMA, "mma", (1, 2, 5, 8, 9, 16)),
                           (capi.GEMV_GENERIC, "generic", (1, 3, 5))):
         for M in Ms:
-            for (K, N, g) in ((4096, 4096, 128), (1024, 256, 32), (11008, 512, 128), (2048, 8192 + 64, 64), (4096, 72, 128)):
+            for (K, N, g) in ((4096, 4096, 128), (1024, 256, 32), (11008, 512, 128), (2048, 8192 + 64, 64), (4096, 96, 128), (384, 32, 64)):
                 for bias in (0, 1):
                     try:
                         e = gemv_case(M, K, N, 4, g, bias, fam, seed=M)
@@ -225,10 +225,10 @@ def main():
             qz = torch.randint(-2**31, 2**31 - 1, (R, G, N // 8), dtype=torch.int32, device=dev)
             a = torch.randn((16, K), device=dev, dtype=torch.float16)
             out = torch.empty((R, 16, N), device=dev, dtype=torch.float16)
-            for M in (1, 2, 3, 4, 8, 16):
+            for M in (1, 2, 4, 8, 16):
                 line = f"   skinny 8192x8192 M={M}:"
                 for fam, name in ((capi.GEMV_SIMT, "simt"), (capi.GEMV_MMA, "mma")):
-                    if fam == capi.GEMV_SIMT and M > 4:
+                    if fam == capi.GEMV_SIMT and M > 2:
                         continue
                     def fn(i, fam=fam):
                         j = i % R

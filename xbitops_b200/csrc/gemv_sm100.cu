@@ -2,33 +2,39 @@
 //
 // Replaces /root/reference/src/cu/gemv_w4a16_pt.cu: gemv<T> (:35-145), warpReduceSum (:20-33) and
 // lauch_Gemv_kernel (:149-173).  Semantics: y[m, n] = RN16( sum_k a[m, k] * DQ[k, n] ) where DQ is
-// the dequantised weight of dq_sm100.cu; accumulation is fp32 (the reference: fp16 chains of 4).
+// the dequantised weight of dq_sm100.cu.
 //
 // What the reference does and why it cannot approach the B200 roofline:
 // CTA = 64 columns x all of K, so N = 4096 gives 64 CTAs on 148 SMs; 8 bytes of weights in flight
 // per thread; one I2F per weight; M > 1 re-reads the weights M times; legacy default stream.
 //
-// This file (all kernels: 256 threads, 128-bit streaming loads, K split over warps, then over a
-// thread-block cluster with a DSMEM reduction -- deterministic, no atomics, no workspace):
+// Kernels in this file:
 //
-//   gemv_w4_kernel<kMma=false>  W4 SIMT GEMV, M <= 4.  Lane (r = lane%4, c = lane/4) streams
-//       word-row 4u+r, columns 4c..4c+3 (LDG.128, 8 deep register ring = 128 B in flight per
-//       thread); nibbles become exact fp16 integers with LOP3 (mask|magic) and one HSUB2 that also
-//       removes the zero point; half2 FMA chains over (k, k+4) pairs, flushed to fp32 every 2
-//       word-rows; per-group fp32 scale; split-K over the 4 r-lanes by warp shuffle, over warps by
-//       shared memory, over the cluster by DSMEM.
-//   gemv_w4_kernel<kMma=true>   W4 skinny GEMM, M <= 16.  Same streaming geometry; the unpacked
-//       half2 pairs ARE the m16n8k16 A fragments (weights on the MMA M axis, batch on the MMA N
-//       axis; the K permutation inside a fragment is absorbed by the activation layout in shared
-//       memory), so no shuffle or shared-memory round trip for weights; fp32 accumulators.
-//       Weights are read once for all M rows (the reference re-reads them M times, :158).
-//   gemv_generic_kernel         any bits 2..8, any groupsize >= 16, any M, any N: one column per
+//   gemv_w4_kernel<MT, UPG, WC>   the W4 path (bits == 4, groupsize 32 / 64 / 128).
+//       A producer thread streams [rows x 128 B] boxes of packed weights, plus the matching scale
+//       and zero rows, with 2-D tiled TMA loads (cp.async.bulk.tensor, 128-byte swizzle) through a
+//       4-stage shared-memory ring guarded by full/empty mbarriers; 8 consumer warps unpack
+//       straight out of shared memory with one conflict-free LDS.128 per 32-k unit.
+//       MT == 0  SIMT GEMV (M == 1): nibbles -> exact fp16 integers with LOP3 (mask|magic) and one
+//                HSUB2 that also removes the zero point; half2 FMA chains over (k, k+4) pairs
+//                flushed to fp32 every 64 k; per-group fp32 scale; split-K over the 4 r-lanes by
+//                warp shuffle, over warps by shared memory, over the cluster by DSMEM.
+//       MT >= 1  tensor-core skinny GEMM (M <= 8*MT): the masked nibble bits ARE fp16 values
+//                (subnormals w * 2^-24, or w * 2^-20 for the high nibble of a byte, compensated
+//                by a 2^-4 on the matching activations), so ONE LOP3 per half2 produces an
+//                m16n8k16 A fragment; products are exact and accumulate in fp32 inside the tensor
+//                core; the zero point is folded per group: s * (2^24 * acc - z * sum_k a_k).
+//                Weights are read once for all M rows (the reference re-reads them M times, :158).
+//   gemv_generic_kernel           any bits 2..8, any groupsize >= 16, any M, any N: one column per
 //       thread, bit-reader over the LSB-first stream, fp32 math with the zero point folded per
 //       group.  Correctness path for the combinations the reference aborts on (:152-155).
 //
+// Split-K is deterministic (no atomics, no global workspace): lanes -> warps -> cluster (DSMEM).
 // Programmatic dependent launch: weights do not depend on the previous kernel in a decode step, so
-// the weight ring is filled BEFORE griddepcontrol.wait and only the activation staging waits.
+// (with XBIT_GEMV_FLAG_STATIC_WEIGHTS) the weight stream starts BEFORE griddepcontrol.wait and
+// only the activation staging waits for the previous kernel.
 #include <cooperative_groups.h>
+#include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -56,6 +62,14 @@ __device__ __forceinline__ void mma_m16n8k16(float (&d)[4], uint32_t a0, uint32_
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
+// D = A * B with a zero C operand (first MMA of a scale group)
+__device__ __forceinline__ void mma_m16n8k16_zero(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                                  uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+      : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "f"(0.f));
+}
 
 // One packed W4 word (8 consecutive k of one column) -> four half2 of EXACT (w - z):
 //   e[0] = (k0, k4)  e[1] = (k1, k5)  e[2] = (k2, k6)  e[3] = (k3, k7)
@@ -68,313 +82,387 @@ __device__ __forceinline__ void unpack_w4_minus_zero(uint32_t w, uint32_t zc_lo,
   e[3] = h22u(__hsub2(u2h2(and_or(w8, 0x00F000F0u, magic2(4))), u2h2(zc_hi)));
 }
 
-// activations [8 consecutive k] (pairs (0,1)(2,3)(4,5)(6,7)) -> pairs (0,4)(1,5)(2,6)(3,7)
+// Same four pairs as raw fp16 SUBNORMALS: a nibble at mantissa bits [0,4) reads as w * 2^-24, at
+// bits [4,8) as w * 2^-20.  No arithmetic at all: one AND per half2.  (Tensor-core path only: the
+// products with fp16 activations are exact and are accumulated in fp32.)
+__device__ __forceinline__ void unpack_w4_subnormal(uint32_t w, uint32_t (&e)[4]) {
+  const uint32_t w8 = w >> 8;
+  e[0] = w & 0x000F000Fu;
+  e[1] = w & 0x00F000F0u;
+  e[2] = w8 & 0x000F000Fu;
+  e[3] = w8 & 0x00F000F0u;
+}
+
+// activations [8 consecutive k] (pairs (0,1)(2,3)(4,5)(6,7)) -> pairs (0,4)(1,5)(2,6)(3,7);
+// kScaleOdd: the odd-k pairs (which meet high nibbles) are pre-multiplied by 2^-4.
+template <bool kScaleOdd>
 __device__ __forceinline__ uint4 permute_act8(uint4 v) {
   uint4 o;
   o.x = prmt(v.x, v.z, 0x5410);
   o.y = prmt(v.x, v.z, 0x7632);
   o.z = prmt(v.y, v.w, 0x5410);
   o.w = prmt(v.y, v.w, 0x7632);
+  if (kScaleOdd) {
+    const __half2 sixteenth = u2h2(0x2C002C00u);   // 0.0625
+    o.y = h22u(__hmul2(u2h2(o.y), sixteenth));
+    o.w = h22u(__hmul2(u2h2(o.w), sixteenth));
+  }
   return o;
 }
 
-// kMma = false: MV = number of activation rows (1..4).  kMma = true: MV = number of n8 batch tiles
-// (1: M <= 8, 2: M <= 16).  CT = 32-column chunks per CTA.
-template <bool kMma, int MV, int CT>
-__global__ void __launch_bounds__(kThreads)
-gemv_w4_kernel(const GemvArgs a) {
-  constexpr int NT = 32 * CT;                      // columns per CTA
-  constexpr int PF = (CT == 1) ? 8 : 4;            // ring depth: 128 B of weights in flight per thread
-  constexpr int MROWS = kMma ? 8 * MV : MV;        // activation rows this instantiation can take
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+// ---- mbarrier / TMA primitives
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {}
+}
+// 2-D tiled TMA load (cp.async.bulk.tensor; SASS: UTMALDG): one instruction moves a whole box and
+// zero-fills anything outside the tensor.  L2 evict-first: every weight byte is used exactly once.
+__device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* tmap, int c0, int c1, uint64_t* bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
+      ::"r"(smem_u32(dst_smem)), "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+
+// CTA = 8 consumer warps (WC column chunks of 32 columns x WK = 8/WC K-slices) + 1 producer warp.
+constexpr int kStages = 4;
+constexpr int kConsumerThreads = 8 * 32;
+constexpr int kW4Threads = kConsumerThreads + 32;
+
+template <int UPG, int WC>
+struct W4Cfg {
+  static constexpr int WK = 8 / WC;
+  static constexpr int NT = 32 * WC;                 // columns per CTA
+  static constexpr int GPB = 4 / UPG;                // scale groups per 128-k block
+  static constexpr int kBoxRows = WK * 16;           // packed word-rows per stage (WK blocks of 128 k)
+  static constexpr int kBoxBytes = kBoxRows * 128;   // one weight box: kBoxRows x 32 columns, SWIZZLE_128B
+  static constexpr int kWeights = WC * kBoxBytes;    // = 16 KiB for every WC
+  static constexpr int kGroupRows = WK * GPB;        // scale / zero rows per stage
+  static constexpr int kScales = kGroupRows * NT * 2;
+  static constexpr int kZeros = kGroupRows * (NT / 8) * 4;
+  static constexpr int kStageBytes = (kWeights + kScales + kZeros + 1023) / 1024 * 1024;
+  static constexpr uint32_t kTxBytes = kWeights + kScales + kZeros;   // TMA boxes always deliver their full size
+};
+
+// MT = 0: SIMT kernel, M == 1.  MT = 1, 2: mma.sync kernel, M <= 8 * MT.
+// UPG = 32-k units per scale group inside a 128-k block: 4 (groupsize 128), 2 (64), 1 (32).
+//
+// K is cut into 128-k blocks (16 packed word-rows); blocks [b0, b1) belong to this CTA (cluster
+// rank = blockIdx.y).  One elected producer thread streams them through a kStages-deep shared-
+// memory ring, WK blocks per stage: WC weight boxes + one scale box + one zero box per stage, all
+// completing on the stage's "full" mbarrier.  (Per-row 512-byte cp.async.bulk copies were measured
+// first: the TMA unit then limits a CTA to ~8 B/clk -- profiles/r01_bw_probe_access_patterns.log.)
+// Consumer warp (wc, wk) takes block wk of every stage, columns [32*wc, 32*wc+32): lane
+// (r = lane%4, c8 = lane/4) reads, per 32-k unit u, word-row 8*(u/2) + 2r + (u%2) of its block
+// (4u + r when a unit must stay inside one 32-k group), columns 4*c8..4*c8+3, with one LDS.128 --
+// the row choice makes the swizzled access conflict-free, and because the order of K inside an MMA
+// is free as long as the activation fragment follows it, those four words ARE the A-fragment
+// sources of two m16n8k16 tiles.  When a warp has consumed a stage it arrives on the stage's
+// "empty" mbarrier and the producer refills it.  No global address arithmetic, bounds checks or
+// register landing buffers in the consumer loop; bytes in flight are bounded by shared memory
+// (4 stages x 17 KiB per CTA), not by registers.
+template <int MT, int UPG, int WC>
+__global__ void __launch_bounds__(kW4Threads, 2)
+gemv_w4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap smap,
+               const __grid_constant__ CUtensorMap zmap, const GemvArgs a) {
+  using Cfg = W4Cfg<UPG, WC>;
+  constexpr bool kMma = MT > 0;
+  constexpr int MROWS = kMma ? 8 * MT : 1;
+  constexpr int WK = Cfg::WK, NT = Cfg::NT, GPB = Cfg::GPB;
+  // lane-independent part of the word-row index of unit u
+  auto unit_row = [](int u) constexpr { return (UPG == 1) ? 4 * u : 8 * (u >> 1) + (u & 1); };
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int r = lane & 3, c8 = lane >> 2;
-  const int n_cta = blockIdx.x * NT;
   const int split = blockIdx.y;
-  const int total_units = (a.K + 31) >> 5;
-  const int u_begin = min(split * a.units_per_split, total_units);
-  const int u_end = min(u_begin + a.units_per_split, total_units);
-  const int upg = a.groupsize >> 5;                // 32-k units per group
-  const int pitch = a.chunk_units * 32 + 32;       // halves per staged activation row (+64 B: bank spread)
-  __half* act_sm = reinterpret_cast<__half*>(smem_raw);
-  float* red_sm = reinterpret_cast<float*>(smem_raw + (size_t)MROWS * pitch * sizeof(__half));
-  float* clus_sm = red_sm + kWarps * MROWS * NT;   // [splits][MROWS][NT], only the cluster leader's is used
+  const int n_cta = blockIdx.x * NT;
+  const int cw = min(NT, a.N - n_cta);              // valid columns of this tile (multiple of 32)
+  const int nblocks = a.K >> 7;
+  const int b0 = min(split * a.units_per_split, nblocks);
+  const int b1 = min(b0 + a.units_per_split, nblocks);
+  const int ntiles = (b1 - b0 + WK - 1) / WK;
+  const int pitch = a.units_per_split * 128 + 32;   // halves per staged activation row (+64 B: bank spread)
+  const int ngroups = a.units_per_split * GPB;      // scale groups in this CTA's K range
+
+  // SWIZZLE_128B boxes need 1024-byte aligned destinations; the dynamic segment only promises 16
+  unsigned char* stage_base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_base + kStages * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  __half* act_sm = reinterpret_cast<__half*>(stage_base + kStages * Cfg::kStageBytes + 128);        // [M][pitch]
+  float* asum_sm = reinterpret_cast<float*>(act_sm + (size_t)a.M * pitch);                         // [ngroups][MROWS] (mma only)
+  float* red_sm = asum_sm + (kMma ? ngroups * MROWS : 0);                                          // [WK][M][NT]
+  float* clus_sm = red_sm + WK * a.M * NT;          // [splits][M][NT], only the cluster leader's is used
 
   const bool clustered = a.splits > 1;
   if (clustered) asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");   // "I have started"
-  // Default: nothing is read before the previous kernel in the stream has completed.  With
-  // XBIT_GEMV_FLAG_STATIC_WEIGHTS the caller promises the weights were not produced by that
-  // kernel, and only the activation staging below waits.
-  if (!a.static_weights) griddep_wait();
-
-  int ncol[CT];
-  bool cvalid[CT];
-#pragma unroll
-  for (int ct = 0; ct < CT; ++ct) {
-    ncol[ct] = n_cta + 32 * ct + 4 * c8;
-    cvalid[ct] = ncol[ct] < a.N;                   // N % 8 == 0: a lane's 4 columns are all in or all out
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  __syncthreads();
+  // Let the next kernel in the stream become resident now: its producer starts streaming ITS weights
+  // while this kernel is still running (its consumers block in griddepcontrol.wait until this grid
+  // has completed and flushed).  One kernel uses at most about half of an SM's shared memory.
+  griddep_launch_dependents();
 
-  auto load_w = [&](int unit, int ct) -> uint4 {
-    const int row = unit * 4 + r;
-    if (cvalid[ct] && row < a.qrows) return ldg_stream_v4(a.qweight + (size_t)row * a.N + ncol[ct]);
-    return make_uint4(0, 0, 0, 0);
-  };
+  float tot[kMma ? 2 * MT : 1][4];
+#pragma unroll
+  for (int v = 0; v < (kMma ? 2 * MT : 1); ++v)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) tot[v][i] = 0.f;
+  const int r = lane & 3, c8 = lane >> 2;
+  const int wc = warp & (WC - 1), wk = (warp / WC) & (WK - 1);
 
-  // ---- accumulators
-  //  SIMT: tot[ct][m][j]              column 4*c8+j, row m, partial over this lane's word-rows
-  //  MMA : tot[ct][t][mt][i]  as [ct][t*MV+mt][i]   t = column pair, i = mma accumulator index
-  constexpr int AV = kMma ? 2 * MV : MV;
-  float tot[CT][AV][4];
-  float grp[CT][AV][4];
+  if (warp == 8) {
+    // =========================== producer ===========================
+    // Default: nothing is read before the previous kernel in the stream has completed.  With
+    // XBIT_GEMV_FLAG_STATIC_WEIGHTS the caller promises the weights were not produced by that
+    // kernel: the weight stream starts at once and only the activation staging waits.
+    if (!a.static_weights) griddep_wait();
+    if (lane == 0) {
+      uint64_t policy;
+      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&wmap) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&smap) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&zmap) : "memory");
+      for (int t = 0; t < ntiles; ++t) {
+        const int s = t % kStages;
+        if (t >= kStages) mbar_wait(&empty_bar[s], ((t / kStages) - 1) & 1);
+        const int blk = b0 + t * WK;
+        unsigned char* st = stage_base + s * Cfg::kStageBytes;
+        mbar_arrive_expect_tx(&full_bar[s], Cfg::kTxBytes);
 #pragma unroll
-  for (int ct = 0; ct < CT; ++ct)
-#pragma unroll
-    for (int v = 0; v < AV; ++v)
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { tot[ct][v][i] = 0.f; grp[ct][v][i] = 0.f; }
-
-  bool first_chunk = true;
-  for (int cu0 = u_begin; cu0 < u_end || first_chunk; cu0 += a.chunk_units) {
-    const int cu1 = min(cu0 + a.chunk_units, u_end);
-    const int wq = (max(cu1 - cu0, 0) + kWarps - 1) / kWarps;
-    const int my0 = min(cu0 + warp * wq, cu1);
-    const int my1 = min(my0 + wq, cu1);
-
-    // ---- fill the weight ring (independent of the previous kernel)
-    uint4 ring[PF][CT];
-#pragma unroll
-    for (int p = 0; p < PF; ++p)
-#pragma unroll
-      for (int ct = 0; ct < CT; ++ct) ring[p][ct] = (my0 + p < my1) ? load_w(my0 + p, ct) : make_uint4(0, 0, 0, 0);
-
-    // ---- group state for this warp's first unit
-    int cur_g = (my0 < my1) ? my0 / upg : 0;
-    int next_switch = (cur_g + 1) * upg;
-    uint2 raw_s[CT];
-    uint32_t raw_z[CT];
-    auto fetch_group_raw = [&](int g) {
-#pragma unroll
-      for (int ct = 0; ct < CT; ++ct) {
-        raw_s[ct] = make_uint2(0, 0);
-        raw_z[ct] = 0;
-        if (cvalid[ct] && g < a.groups) {
-          raw_s[ct] = __ldg(reinterpret_cast<const uint2*>(a.scales + (size_t)g * a.N + ncol[ct]));
-          raw_z[ct] = __ldg(a.qzeros + (size_t)g * a.zwords + (ncol[ct] >> 3)) >> (16 * (c8 & 1));
-        }
+        for (int c = 0; c < WC; ++c) tma_load_2d(st + c * Cfg::kBoxBytes, &wmap, n_cta + 32 * c, blk * 16, &full_bar[s], policy);
+        tma_load_2d(st + Cfg::kWeights, &smap, n_cta, blk * GPB, &full_bar[s], policy);
+        tma_load_2d(st + Cfg::kWeights + Cfg::kScales, &zmap, n_cta >> 3, blk * GPB, &full_bar[s], policy);
       }
-    };
-    float sf[CT][4];
-    uint32_t zc_lo[CT][4], zc_hi[CT][4];
-    auto decode_group = [&]() {
-#pragma unroll
-      for (int ct = 0; ct < CT; ++ct) {
-        const float2 s01 = __half22float2(u2h2(raw_s[ct].x));
-        const float2 s23 = __half22float2(u2h2(raw_s[ct].y));
-        sf[ct][0] = s01.x; sf[ct][1] = s01.y; sf[ct][2] = s23.x; sf[ct][3] = s23.y;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t zb = ((raw_z[ct] >> (4 * j)) & 0xFu) + (uint32_t)a.zero_bias;   // <= 16
-          zc_lo[ct][j] = dup16(magic_base_bits(0) + zb);          // half(1024 + z)
-          zc_hi[ct][j] = dup16(magic_base_bits(4) + (zb << 4));   // half(64 + z)
-        }
-      }
-    };
-    if (my0 < my1) {
-      fetch_group_raw(cur_g);
-      decode_group();
-      fetch_group_raw(cur_g + 1);     // prefetch the next group's scale/zero words
     }
-
-    // ---- stage this chunk's activations (the only data that depends on the previous kernel)
-    if (first_chunk && a.static_weights) griddep_wait();
+    __syncwarp();
+  } else {
+    // =========================== consumers ===========================
+    // stage the activations of this CTA's K range (the only data that depends on the previous
+    // kernel); the mma path also needs sum_k a_k per scale group for the folded zero point
+    griddep_wait();
     {
-      const int chunk_k0 = cu0 * 32;
-      const int vecs_per_row = max(cu1 - cu0, 0) * 4;      // 8-half vectors
-      for (int idx = tid; idx < MROWS * vecs_per_row; idx += kThreads) {
-        const int m = idx / vecs_per_row, v = idx - m * vecs_per_row;
-        const int k = chunk_k0 + v * 8;
+      const int k0 = b0 * 128;
+      const int vecs_per_row = (b1 - b0) * 16;      // 8-half vectors; a scale group = 4*UPG consecutive vectors
+      for (int base = 0; base < a.M * vecs_per_row; base += kConsumerThreads) {
+        const int idx = base + tid;
+        const bool ok = idx < a.M * vecs_per_row;
+        const int m = ok ? idx / vecs_per_row : 0, v = ok ? idx - m * vecs_per_row : 0;
         uint4 val = make_uint4(0, 0, 0, 0);
-        if (m < a.M && k < a.K) val = __ldg(reinterpret_cast<const uint4*>(a.a + (size_t)m * a.K + k));  // K % 8 == 0
-        *reinterpret_cast<uint4*>(act_sm + (size_t)m * pitch + v * 8) = permute_act8(val);
+        if (ok) {
+          val = __ldg(reinterpret_cast<const uint4*>(a.a + (size_t)m * a.K + k0) + v);
+          *reinterpret_cast<uint4*>(act_sm + (size_t)m * pitch + v * 8) = permute_act8<kMma>(val);
+        }
+        if constexpr (kMma) {
+          const float2 f0 = __half22float2(u2h2(val.x)), f1 = __half22float2(u2h2(val.y));
+          const float2 f2 = __half22float2(u2h2(val.z)), f3 = __half22float2(u2h2(val.w));
+          float sum = ((f0.x + f0.y) + (f1.x + f1.y)) + ((f2.x + f2.y) + (f3.x + f3.y));
+          // vecs_per_row is a multiple of 16, so a group's 4*UPG vectors sit in 4*UPG consecutive lanes
+#pragma unroll
+          for (int o = 1; o < 4 * UPG; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+          if (ok && (lane & (4 * UPG - 1)) == 0) asum_sm[(v / (4 * UPG)) * MROWS + m] = sum;
+        }
       }
     }
-    __syncthreads();
+    asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");
 
-    // SIMT fp16 chains (flushed to fp32 every 2 units)
-    __half2 acc16[CT][kMma ? 1 : MV][4];
-    if constexpr (!kMma) {
-#pragma unroll
-      for (int ct = 0; ct < CT; ++ct)
-#pragma unroll
-        for (int m = 0; m < MV; ++m)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) acc16[ct][m][j] = __float2half2_rn(0.f);
-    }
-    auto flush16 = [&]() {
-      if constexpr (!kMma) {
-#pragma unroll
-        for (int ct = 0; ct < CT; ++ct)
-#pragma unroll
-          for (int m = 0; m < MV; ++m)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 f = __half22float2(acc16[ct][m][j]);
-              grp[ct][m][j] += f.x + f.y;
-              acc16[ct][m][j] = __float2half2_rn(0.f);
-            }
-      }
-    };
-    auto close_group = [&]() {       // tot += scale * group sum
-      flush16();
-#pragma unroll
-      for (int ct = 0; ct < CT; ++ct)
-#pragma unroll
-        for (int v = 0; v < AV; ++v)
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            // SIMT: i = column j.  MMA: v = t*MV+mt, accumulators 0,1 -> column 2t, 2,3 -> column 2t+1
-            const float s = kMma ? sf[ct][2 * (v / MV) + (i >> 1)] : sf[ct][i];
-            tot[ct][v][i] = fmaf(s, grp[ct][v][i], tot[ct][v][i]);
-            grp[ct][v][i] = 0.f;
-          }
-    };
+    const int col_local = 32 * wc + 4 * c8;                       // this lane's first column inside the tile
+    // swizzled box of this warp's column chunk: 16-byte chunk c8 of row rho lives at chunk c8 ^ (rho & 7)
+    constexpr int kLaneRowMul = (UPG == 1) ? 1 : 2;
+    constexpr int kOddRowAdd = (UPG == 1) ? 4 : 1;
+    const int lane_row = kLaneRowMul * r;
+    const uint32_t w_row = (uint32_t)(wc * Cfg::kBoxBytes + (wk * 16 + lane_row) * 128);
+    const uint32_t w_x0 = w_row + (uint32_t)((c8 ^ lane_row) * 16);                // units with u % 2 == 0
+    const uint32_t w_x1 = w_row + (uint32_t)((c8 ^ (lane_row + kOddRowAdd)) * 16); // units with u % 2 == 1
+    const uint32_t s_off = (uint32_t)(Cfg::kWeights + wk * GPB * (NT * 2) + col_local * 2);
+    const uint32_t z_off = (uint32_t)(Cfg::kWeights + Cfg::kScales + wk * GPB * (NT / 2) + (col_local >> 3) * 4);
+    const int zshift = 16 * (c8 & 1);
+    const __half* aptr = act_sm + wk * 128 + lane_row * 8;        // this lane's word-row; + t * WK * 128 per stage
+    const float zbias = (float)a.zero_bias;
 
-    for (int u = my0; u < my1; u += PF) {
+    for (int t = 0; t < ntiles; ++t) {
+      const int s = t % kStages;
+      mbar_wait(&full_bar[s], (t / kStages) & 1);
+      const unsigned char* st = stage_base + s * Cfg::kStageBytes;
+      const int blk_local = t * WK + wk;                          // block index inside this CTA's range
+      if (b0 + blk_local < b1) {                                  // warp-uniform (the last stage may be partly empty)
+        const __half* ablk = aptr + t * (WK * 128);
 #pragma unroll
-      for (int p = 0; p < PF; ++p) {
-        const int uu = u + p;
-        if (uu < my1) {                                     // warp-uniform
-          uint4 wv[CT];
-#pragma unroll
-          for (int ct = 0; ct < CT; ++ct) {
-            wv[ct] = ring[p][ct];
-            ring[p][ct] = (uu + PF < my1) ? load_w(uu + PF, ct) : make_uint4(0, 0, 0, 0);
+        for (int q = 0; q < GPB; ++q) {
+          const uint2 sraw = *reinterpret_cast<const uint2*>(st + s_off + q * (NT * 2));
+          const uint32_t zraw = *reinterpret_cast<const uint32_t*>(st + z_off + q * (NT / 2)) >> zshift;
+          float sf[4];
+          {
+            const float2 s01 = __half22float2(u2h2(sraw.x));
+            const float2 s23 = __half22float2(u2h2(sraw.y));
+            sf[0] = s01.x; sf[1] = s01.y; sf[2] = s23.x; sf[3] = s23.y;
           }
-          if (uu == next_switch) {                          // warp-uniform: entering the next group
-            close_group();
-            ++cur_g;
-            next_switch += upg;
-            decode_group();
-            fetch_group_raw(cur_g + 1);
-          }
-          const __half* arow = act_sm + (uu - cu0) * 32 + r * 8;
           if constexpr (kMma) {
-            uint4 bfrag[MV];
+            float grp[2 * MT][4];
 #pragma unroll
-            for (int mt = 0; mt < MV; ++mt) {
-              bfrag[mt] = make_uint4(0, 0, 0, 0);
-              const int m = c8 + 8 * mt;
-              if (m < a.M) bfrag[mt] = *reinterpret_cast<const uint4*>(arow + (size_t)m * pitch);
-            }
+            for (int uu = 0; uu < UPG; ++uu) {
+              const int u = q * UPG + uu;
+              const uint4 wv = *reinterpret_cast<const uint4*>(st + ((u & 1) ? w_x1 : w_x0) + unit_row(u) * 128);
+              uint4 bfrag[MT];
 #pragma unroll
-            for (int ct = 0; ct < CT; ++ct) {
-              const uint32_t w4[4] = {wv[ct].x, wv[ct].y, wv[ct].z, wv[ct].w};
+              for (int mt = 0; mt < MT; ++mt) {
+                bfrag[mt] = make_uint4(0, 0, 0, 0);
+                if (c8 + 8 * mt < a.M)
+                  bfrag[mt] = *reinterpret_cast<const uint4*>(ablk + (size_t)(c8 + 8 * mt) * pitch + unit_row(u) * 8);
+              }
+              const uint32_t w4[4] = {wv.x, wv.y, wv.z, wv.w};
 #pragma unroll
-              for (int t = 0; t < 2; ++t) {
+              for (int tt = 0; tt < 2; ++tt) {
                 uint32_t ea[4], eb[4];
-                unpack_w4_minus_zero(w4[2 * t], zc_lo[ct][2 * t], zc_hi[ct][2 * t], ea);
-                unpack_w4_minus_zero(w4[2 * t + 1], zc_lo[ct][2 * t + 1], zc_hi[ct][2 * t + 1], eb);
+                unpack_w4_subnormal(w4[2 * tt], ea);
+                unpack_w4_subnormal(w4[2 * tt + 1], eb);
 #pragma unroll
-                for (int mt = 0; mt < MV; ++mt) {
-                  mma_m16n8k16(grp[ct][t * MV + mt], ea[0], eb[0], ea[1], eb[1], bfrag[mt].x, bfrag[mt].y);
-                  mma_m16n8k16(grp[ct][t * MV + mt], ea[2], eb[2], ea[3], eb[3], bfrag[mt].z, bfrag[mt].w);
+                for (int mt = 0; mt < MT; ++mt) {
+                  if (uu == 0) mma_m16n8k16_zero(grp[tt * MT + mt], ea[0], eb[0], ea[1], eb[1], bfrag[mt].x, bfrag[mt].y);
+                  else         mma_m16n8k16(grp[tt * MT + mt], ea[0], eb[0], ea[1], eb[1], bfrag[mt].x, bfrag[mt].y);
+                  mma_m16n8k16(grp[tt * MT + mt], ea[2], eb[2], ea[3], eb[3], bfrag[mt].z, bfrag[mt].w);
                 }
               }
             }
+            // grp = 2^-24 * sum_k a_k w_k (exact products, fp32 accumulation).  y += s * (2^24 grp - z * sum_k a_k).
+            // accumulators 0,1 belong to column 2*tt (rows m = 2r, 2r+1), accumulators 2,3 to column 2*tt+1.
+            float s24[4], nsz[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              s24[j] = sf[j] * 16777216.f;
+              nsz[j] = -sf[j] * ((float)((zraw >> (4 * j)) & 0xFu) + zbias);
+            }
+            const float* asum = asum_sm + (blk_local * GPB + q) * MROWS + 2 * r;
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+              const float2 as = *reinterpret_cast<const float2*>(asum + 8 * mt);
+#pragma unroll
+              for (int tt = 0; tt < 2; ++tt)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const int j = 2 * tt + (i >> 1);
+                  float acc = tot[tt * MT + mt][i];
+                  acc = fmaf(s24[j], grp[tt * MT + mt][i], acc);
+                  acc = fmaf(nsz[j], (i & 1) ? as.y : as.x, acc);
+                  tot[tt * MT + mt][i] = acc;
+                }
+            }
           } else {
-            uint4 av[MV];
+            uint32_t zlo[4], zhi[4];
 #pragma unroll
-            for (int m = 0; m < MV; ++m) av[m] = *reinterpret_cast<const uint4*>(arow + (size_t)m * pitch);
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t zb = ((zraw >> (4 * j)) & 0xFu) + (uint32_t)a.zero_bias;   // <= 16
+              zlo[j] = (magic_base_bits(0) + zb) * 0x00010001u;          // half2(1024 + z)
+              zhi[j] = (magic_base_bits(4) + (zb << 4)) * 0x00010001u;   // half2(64 + z)
+            }
+            float grp[4] = {0.f, 0.f, 0.f, 0.f};
+            __half2 acc[4];
 #pragma unroll
-            for (int ct = 0; ct < CT; ++ct) {
-              const uint32_t w4[4] = {wv[ct].x, wv[ct].y, wv[ct].z, wv[ct].w};
+            for (int uu = 0; uu < UPG; ++uu) {
+              const int u = q * UPG + uu;
+              const uint4 wv = *reinterpret_cast<const uint4*>(st + ((u & 1) ? w_x1 : w_x0) + unit_row(u) * 128);
+              const uint4 av = *reinterpret_cast<const uint4*>(ablk + unit_row(u) * 8);
+              const uint32_t w4[4] = {wv.x, wv.y, wv.z, wv.w};
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 uint32_t e[4];
-                unpack_w4_minus_zero(w4[j], zc_lo[ct][j], zc_hi[ct][j], e);
+                unpack_w4_minus_zero(w4[j], zlo[j], zhi[j], e);
+                __half2 c;
+                if (uu & 1) c = __hfma2(u2h2(e[0]), u2h2(av.x), acc[j]);
+                else        c = __hmul2(u2h2(e[0]), u2h2(av.x));
+                c = __hfma2(u2h2(e[1]), u2h2(av.y), c);
+                c = __hfma2(u2h2(e[2]), u2h2(av.z), c);
+                c = __hfma2(u2h2(e[3]), u2h2(av.w), c);
+                acc[j] = c;
+              }
+              if ((uu & 1) || uu == UPG - 1) {      // flush the fp16 chains to fp32 every 2 units
 #pragma unroll
-                for (int m = 0; m < MV; ++m) {
-                  __half2 c = acc16[ct][m][j];
-                  c = __hfma2(u2h2(e[0]), u2h2(av[m].x), c);
-                  c = __hfma2(u2h2(e[1]), u2h2(av[m].y), c);
-                  c = __hfma2(u2h2(e[2]), u2h2(av[m].z), c);
-                  c = __hfma2(u2h2(e[3]), u2h2(av[m].w), c);
-                  acc16[ct][m][j] = c;
+                for (int j = 0; j < 4; ++j) {
+                  const float2 f = __half22float2(acc[j]);
+                  grp[j] += f.x + f.y;
                 }
               }
             }
-            if (p & 1) flush16();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) tot[0][j] = fmaf(sf[j], grp[j], tot[0][j]);
           }
         }
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[s]);
     }
-    if (my0 < my1) close_group();
-    first_chunk = false;
-    if (cu0 + a.chunk_units < u_end) __syncthreads();      // the next chunk overwrites act_sm
   }
 
-  // Let the next kernel in the stream start its prologue / weight prefetch.
-  griddep_launch_dependents();
-
-  // ---- split-K reduction: r-lanes (shuffle) -> warps (smem) -> cluster (DSMEM)
-  if constexpr (!kMma) {
+  // ---- split-K reduction: r-lanes (shuffle, SIMT only) -> K-slices (smem) -> cluster (DSMEM)
+  if (warp < 8) {
+    if constexpr (!kMma) {
 #pragma unroll
-    for (int ct = 0; ct < CT; ++ct)
+      for (int j = 0; j < 4; ++j) {
+        float v = tot[0][j];
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        if (r == 0) red_sm[wk * NT + 32 * wc + 4 * c8 + j] = v;
+      }
+    } else {
 #pragma unroll
-      for (int m = 0; m < MV; ++m)
+      for (int tt = 0; tt < 2; ++tt)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float v = tot[ct][m][j];
-          v += __shfl_xor_sync(0xffffffffu, v, 1);
-          v += __shfl_xor_sync(0xffffffffu, v, 2);
-          if (r == 0) red_sm[(warp * MROWS + m) * NT + 32 * ct + 4 * c8 + j] = v;
-        }
-  } else {
-#pragma unroll
-    for (int ct = 0; ct < CT; ++ct)
-#pragma unroll
-      for (int t = 0; t < 2; ++t)
-#pragma unroll
-        for (int mt = 0; mt < MV; ++mt)
+        for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int m = 8 * mt + 2 * r + (i & 1);
-            const int col = 32 * ct + 4 * c8 + 2 * t + (i >> 1);
-            red_sm[(warp * MROWS + m) * NT + col] = tot[ct][t * MV + mt][i];
+            const int col = 32 * wc + 4 * c8 + 2 * tt + (i >> 1);
+            if (m < a.M) red_sm[(wk * a.M + m) * NT + col] = tot[tt * MT + mt][i];
           }
+    }
   }
   __syncthreads();
 
-  const int nout = a.M * NT;                                // M <= MROWS
+  const int nout = a.M * NT;
   if (clustered) {
     cg::cluster_group cluster = cg::this_cluster();
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");   // every CTA of the cluster has started
     float* leader = cluster.map_shared_rank(clus_sm, 0);
-    for (int o = tid; o < nout; o += kThreads) {
-      const int m = o / NT, col = o - m * NT;
+    for (int o = tid; o < nout; o += kW4Threads) {
       float v = 0.f;
 #pragma unroll
-      for (int w = 0; w < kWarps; ++w) v += red_sm[(w * MROWS + m) * NT + col];
-      leader[(split * MROWS + m) * NT + col] = v;
+      for (int w = 0; w < WK; ++w) v += red_sm[w * nout + o];
+      leader[split * nout + o] = v;
     }
     cluster.sync();
     if (split != 0) return;
   }
-  for (int o = tid; o < nout; o += kThreads) {
+  for (int o = tid; o < nout; o += kW4Threads) {
     const int m = o / NT, col = o - m * NT;
-    const int n = n_cta + col;
     float v = 0.f;
     if (clustered) {
-      for (int s = 0; s < a.splits; ++s) v += clus_sm[(s * MROWS + m) * NT + col];
+      for (int s = 0; s < a.splits; ++s) v += clus_sm[s * nout + o];
     } else {
 #pragma unroll
-      for (int w = 0; w < kWarps; ++w) v += red_sm[(w * MROWS + m) * NT + col];
+      for (int w = 0; w < WK; ++w) v += red_sm[w * nout + o];
     }
-    if (n < a.N) {
+    if (col < cw) {
       const __half h = __float2half_rn(v);
-      const size_t off = (size_t)m * a.ldo + a.col_offset + n;
+      const size_t off = (size_t)m * a.ldo + a.col_offset + n_cta + col;
       a.out[0][off] = h;
       for (int p = 1; p < a.world; ++p) a.out[p][off] = h;   // fused all-gather: NVLink peer stores
     }
@@ -477,8 +565,10 @@ int device_sm_count() {
 
 bool gemv_w4_supported(const GemvArgs& a) {
   const uintptr_t al = reinterpret_cast<uintptr_t>(a.a) | reinterpret_cast<uintptr_t>(a.qweight) |
-                       reinterpret_cast<uintptr_t>(a.scales);
-  return a.bits == 4 && a.groupsize % 32 == 0 && a.K % 8 == 0 && a.N % 8 == 0 && (al & 15u) == 0 && a.M >= 1;
+                       reinterpret_cast<uintptr_t>(a.scales) | reinterpret_cast<uintptr_t>(a.qzeros);
+  const bool group_ok = (a.groupsize == 32) || (a.groupsize == 64) || (a.groupsize == 128);
+  // N % 32 == 0: TMA global strides (N*4, N*2, N/2 bytes) must be multiples of 16
+  return a.bits == 4 && group_ok && a.K % 128 == 0 && a.N % 32 == 0 && (al & 15u) == 0 && a.M >= 1;
 }
 
 static int env_int(const char* name, int dflt) {
@@ -486,53 +576,112 @@ static int env_int(const char* name, int dflt) {
   return (v && *v) ? atoi(v) : dflt;
 }
 
-// Decomposition: CT (tile = 32*CT columns), K splits (cluster size) and activation chunking.
-static void plan_w4(GemvArgs& a, int mrows, int& ct, size_t& smem, dim3& grid) {
+constexpr size_t kMaxDynSmem = 220 * 1024;
+
+struct W4Plan {
+  int wc, splits, blocks_per_split;
+  size_t smem;
+  dim3 grid;
+};
+
+static size_t w4_smem_bytes(int upg, int wc, int mt, int m, int blocks_per_split, int splits) {
+  const int wk = 8 / wc, nt = 32 * wc, gpb = 4 / upg;
+  const size_t stage = ((size_t)(wc * wk * 16 * 128) + (size_t)wk * gpb * nt * 2 + (size_t)wk * gpb * (nt / 8) * 4 + 1023) / 1024 * 1024;
+  return 1024 /* alignment slack */ + kStages * stage + 128                          // ring + mbarriers
+         + (size_t)m * (blocks_per_split * 128 + 32) * sizeof(__half)                 // act_sm
+         + (size_t)(mt > 0 ? blocks_per_split * gpb * 8 * mt : 0) * sizeof(float)     // asum_sm
+         + (size_t)wk * m * nt * sizeof(float)                                        // red_sm
+         + (size_t)(splits > 1 ? splits : 0) * m * nt * sizeof(float);                // clus_sm
+}
+
+// Decomposition.  The kernel is a pure stream: what matters is that every CTA is resident at once
+// (one wave, <= 2 CTAs per SM) and that enough bytes are in flight (CTAs x 4 stages x 17 KiB).
+// Prefer narrow tiles (more CTAs, no cross-CTA reduction); split K over a cluster only when the
+// column tiles alone cannot fill the machine.
+static bool plan_w4(GemvArgs& a, int mt, int upg, W4Plan& p) {
   const int sms = device_sm_count();
-  const int total_units = (a.K + 31) / 32;
-  // tuning knobs for the sweep harness (tools/sweep): XBIT_GEMV_CT / XBIT_GEMV_SPLITS
-  ct = env_int("XBIT_GEMV_CT", 0);
-  if (ct != 1 && ct != 2) ct = (a.N >= 16384) ? 2 : 1;
-  const int tiles = (a.N + 32 * ct - 1) / (32 * ct);
+  const int nblocks = a.K / 128;
+  const int cap = 2 * sms;
+  int wc = env_int("XBIT_GEMV_WC", 0);               // tuning knobs for tools/sweep.py
+  if (wc != 1 && wc != 2 && wc != 4) {
+    wc = 1;
+    while (wc < 4 && (a.N + 32 * wc - 1) / (32 * wc) > cap) wc *= 2;
+  }
+  const int tiles = (a.N + 32 * wc - 1) / (32 * wc);
+  const int wk = 8 / wc;
   int splits = env_int("XBIT_GEMV_SPLITS", 0);
   if (splits < 1 || splits > 8 || (splits & (splits - 1))) {
     splits = 1;
-    // enough CTAs for ~2 per SM, while every warp keeps at least 4 units (128 k) of work
-    while (splits < 8 && tiles * splits < 2 * sms && total_units / (splits * 2 * kWarps) >= 4) splits *= 2;
+    // fill at least ~3/4 of the SMs; every CTA keeps at least two full stages
+    while (splits < 8 && tiles * splits * 4 < 3 * sms && tiles * splits * 2 <= cap && nblocks / (splits * 2) >= 2 * wk) splits *= 2;
   }
+  auto smem_of = [&](int sp) { return w4_smem_bytes(upg, wc, mt, a.M, (nblocks + sp - 1) / sp, sp); };
+  while (splits < 8 && smem_of(splits) > kMaxDynSmem) splits *= 2;
+  if (smem_of(splits) > kMaxDynSmem) return false;   // K too long for the staged-activation design at this M
+  p.wc = wc;
+  p.splits = splits;
+  p.blocks_per_split = (nblocks + splits - 1) / splits;
+  p.smem = smem_of(splits);
+  p.grid = dim3((unsigned)tiles, (unsigned)splits, 1);
   a.splits = splits;
-  a.units_per_split = (total_units + splits - 1) / splits;
-  // activation staging: at most 32 Ki halves (64 KiB); whole split slab when it fits
-  int chunk = a.units_per_split;
-  const int max_units = (32768 / mrows) / 32;
-  if (chunk > max_units) chunk = max_units / kWarps * kWarps;
-  a.chunk_units = chunk < 1 ? 1 : chunk;
-  const int nt = 32 * ct;
-  smem = (size_t)mrows * (a.chunk_units * 32 + 32) * sizeof(__half)       // act_sm
-         + (size_t)kWarps * mrows * nt * sizeof(float)                     // red_sm
-         + (size_t)(splits > 1 ? splits : 0) * mrows * nt * sizeof(float); // clus_sm
-  grid = dim3((unsigned)tiles, (unsigned)splits, 1);
+  a.units_per_split = p.blocks_per_split;
+  a.chunk_units = 0;
+  return true;
 }
 
-constexpr size_t kMaxDynSmem = 200 * 1024;
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-template <typename Kern>
-static cudaError_t launch_w4(Kern kern, const GemvArgs& a, dim3 grid, size_t smem, cudaStream_t stream) {
-  if (smem > kMaxDynSmem) return cudaErrorInvalidValue;
-  // opt in to large dynamic shared memory once per (kernel, device)
-  static bool configured[64] = {false};
-  int dev = 0;
-  cudaError_t e = cudaGetDevice(&dev);
-  if (e != cudaSuccess) return e;
-  if (dev < 0 || dev >= 64 || !configured[dev]) {
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
-    if (e != cudaSuccess) return e;
-    if (dev >= 0 && dev < 64) configured[dev] = true;
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
   }
+  return fn;
+}
+
+static cudaError_t encode_2d(CUtensorMap* map, CUtensorMapDataType dt, const void* base, uint64_t inner, uint64_t outer,
+                             uint64_t row_bytes, uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle sw) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return cudaErrorNotSupported;
+  const cuuint64_t dims[2] = {inner, outer};
+  const cuuint64_t strides[1] = {row_bytes};
+  const cuuint32_t box[2] = {box_inner, box_outer};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+using W4Kernel = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemvArgs);
+
+static cudaError_t launch_w4(W4Kernel kern, const GemvArgs& a, const W4Plan& p, int upg, cudaStream_t stream) {
+  const int wk = 8 / p.wc, nt = 32 * p.wc, gpb = 4 / upg;
+  alignas(64) CUtensorMap wmap, smap, zmap;
+  // qweight [qrows, N] u32: box = wk*16 rows x 32 columns (128 B), 128-byte swizzle
+  cudaError_t e = encode_2d(&wmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, a.qweight, (uint64_t)a.N, (uint64_t)a.qrows,
+                            (uint64_t)a.N * 4, 32, (uint32_t)(wk * 16), CU_TENSOR_MAP_SWIZZLE_128B);
+  if (e != cudaSuccess) return e;
+  // scales [groups, N] f16 (moved as u16): box = wk*gpb rows x nt columns, dense
+  e = encode_2d(&smap, CU_TENSOR_MAP_DATA_TYPE_UINT16, a.scales, (uint64_t)a.N, (uint64_t)a.groups, (uint64_t)a.N * 2,
+                (uint32_t)nt, (uint32_t)(wk * gpb), CU_TENSOR_MAP_SWIZZLE_NONE);
+  if (e != cudaSuccess) return e;
+  // qzeros [groups, N/8] u32: box = wk*gpb rows x nt/8 words, dense
+  e = encode_2d(&zmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, a.qzeros, (uint64_t)a.zwords, (uint64_t)a.groups,
+                (uint64_t)a.zwords * 4, (uint32_t)(nt / 8), (uint32_t)(wk * gpb), CU_TENSOR_MAP_SWIZZLE_NONE);
+  if (e != cudaSuccess) return e;
+  // opt in to large dynamic shared memory (idempotent, not a stream operation)
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
+  if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid;
-  cfg.blockDim = dim3(kThreads, 1, 1);
-  cfg.dynamicSmemBytes = smem;
+  cfg.gridDim = p.grid;
+  cfg.blockDim = dim3(kW4Threads, 1, 1);
+  cfg.dynamicSmemBytes = p.smem;
   cfg.stream = stream;
   cudaLaunchAttribute attrs[2];
   int na = 0;
@@ -548,32 +697,37 @@ static cudaError_t launch_w4(Kern kern, const GemvArgs& a, dim3 grid, size_t sme
   }
   cfg.attrs = attrs;
   cfg.numAttrs = na;
-  return cudaLaunchKernelEx(&cfg, kern, a);
+  return cudaLaunchKernelEx(&cfg, kern, wmap, smap, zmap, a);
+}
+
+static int upg_of(int groupsize) { return groupsize == 32 ? 1 : (groupsize == 64 ? 2 : 4); }
+
+template <int MT>
+static W4Kernel pick_w4_kernel(int upg, int wc) {
+#define XBIT_W4_CASE(UPG_, WC_) if (upg == UPG_ && wc == WC_) return gemv_w4_kernel<MT, UPG_, WC_>;
+  XBIT_W4_CASE(1, 1) XBIT_W4_CASE(1, 2) XBIT_W4_CASE(1, 4)
+  XBIT_W4_CASE(2, 1) XBIT_W4_CASE(2, 2) XBIT_W4_CASE(2, 4)
+  XBIT_W4_CASE(4, 1) XBIT_W4_CASE(4, 2) XBIT_W4_CASE(4, 4)
+#undef XBIT_W4_CASE
+  return nullptr;
 }
 
 cudaError_t launch_gemv_w4_simt(GemvArgs a, cudaStream_t stream) {
-  int ct; size_t smem; dim3 grid;
-  plan_w4(a, a.M, ct, smem, grid);
-#define XBIT_SIMT_CASE(MV_, CT_) \
-  if (a.M == MV_ && ct == CT_) return launch_w4(gemv_w4_kernel<false, MV_, CT_>, a, grid, smem, stream);
-  XBIT_SIMT_CASE(1, 1) XBIT_SIMT_CASE(1, 2)
-  XBIT_SIMT_CASE(2, 1) XBIT_SIMT_CASE(2, 2)
-  XBIT_SIMT_CASE(3, 1) XBIT_SIMT_CASE(3, 2)
-  XBIT_SIMT_CASE(4, 1) XBIT_SIMT_CASE(4, 2)
-#undef XBIT_SIMT_CASE
-  return cudaErrorInvalidValue;
+  if (a.M != 1) return cudaErrorInvalidValue;
+  const int upg = upg_of(a.groupsize);
+  W4Plan p;
+  if (!plan_w4(a, 0, upg, p)) return cudaErrorInvalidValue;
+  W4Kernel k = pick_w4_kernel<0>(upg, p.wc);
+  return k ? launch_w4(k, a, p, upg, stream) : cudaErrorInvalidValue;
 }
 
 cudaError_t launch_gemv_w4_mma(GemvArgs a, cudaStream_t stream) {
-  const int mv = a.M <= 8 ? 1 : 2;
-  int ct; size_t smem; dim3 grid;
-  plan_w4(a, 8 * mv, ct, smem, grid);
-#define XBIT_MMA_CASE(MV_, CT_) \
-  if (mv == MV_ && ct == CT_) return launch_w4(gemv_w4_kernel<true, MV_, CT_>, a, grid, smem, stream);
-  XBIT_MMA_CASE(1, 1) XBIT_MMA_CASE(1, 2)
-  XBIT_MMA_CASE(2, 1) XBIT_MMA_CASE(2, 2)
-#undef XBIT_MMA_CASE
-  return cudaErrorInvalidValue;
+  const int mt = a.M <= 8 ? 1 : 2;
+  const int upg = upg_of(a.groupsize);
+  W4Plan p;
+  if (!plan_w4(a, mt, upg, p)) return cudaErrorInvalidValue;
+  W4Kernel k = mt == 1 ? pick_w4_kernel<1>(upg, p.wc) : pick_w4_kernel<2>(upg, p.wc);
+  return k ? launch_w4(k, a, p, upg, stream) : cudaErrorInvalidValue;
 }
 
 cudaError_t launch_gemv_generic(GemvArgs a, cudaStream_t stream) {

@@ -89,7 +89,7 @@ static int pick_family(const xbit::GemvArgs& a) {
     const char* v = getenv("XBIT_GEMV_FAMILY");
     forced = (v && *v) ? atoi(v) : 0;
   }
-  if (forced == XBIT_GEMV_SIMT && a.M <= 4) return XBIT_GEMV_SIMT;
+  if (forced == XBIT_GEMV_SIMT && a.M == 1) return XBIT_GEMV_SIMT;
   if (forced == XBIT_GEMV_MMA) return XBIT_GEMV_MMA;
   if (forced == XBIT_GEMV_GENERIC) return XBIT_GEMV_GENERIC;
   return (a.M == 1) ? XBIT_GEMV_SIMT : XBIT_GEMV_MMA;
@@ -140,12 +140,12 @@ static int gemv_impl(const void* a_f16, const int32_t* qweight, const void* scal
     cudaError_t e;
     switch (family) {
       case XBIT_GEMV_SIMT:
-        if (!xbit::gemv_w4_supported(g)) return fail(XBIT_EINVAL, "SIMT family needs bits=4, groupsize%%32=0, K%%8=0, N%%8=0, 16-byte aligned pointers");
-        slab = g.M > 4 ? 4 : g.M; g.M = slab;
+        if (!xbit::gemv_w4_supported(g)) return fail(XBIT_EINVAL, "SIMT family needs bits=4, groupsize in {32, 64, 128*j}, K%%128=0, N%%8=0, 16-byte aligned pointers");
+        slab = 1; g.M = 1;   // one activation row per launch (the GEMV kernel proper)
         e = xbit::launch_gemv_w4_simt(g, st);
         break;
       case XBIT_GEMV_MMA:
-        if (!xbit::gemv_w4_supported(g)) return fail(XBIT_EINVAL, "MMA family needs bits=4, groupsize%%32=0, K%%8=0, N%%8=0, 16-byte aligned pointers");
+        if (!xbit::gemv_w4_supported(g)) return fail(XBIT_EINVAL, "MMA family needs bits=4, groupsize in {32, 64, 128*j}, K%%128=0, N%%8=0, 16-byte aligned pointers");
         slab = g.M > 16 ? 16 : g.M; g.M = slab;
         e = xbit::launch_gemv_w4_mma(g, st);
         break;
