@@ -192,6 +192,13 @@ class ShapeSet:
         self.a = torch.randn((1, K), device=dev, generator=gen).to(torch.float16)
         self.out = torch.zeros((self.R, 1, N_total), device=dev, dtype=torch.float16)
         self.col0 = rank * self.N
+        self.symm = None          # (buffer, handle, peer base pointers) for the fused peer-store epilogue
+
+    def make_symmetric(self, torch, dist):
+        import torch.distributed._symmetric_memory as symm_mem
+        buf = symm_mem.empty((self.R, 1, self.N_total), dtype=torch.float16, device=self.out.device)
+        hdl = symm_mem.rendezvous(buf, dist.group.WORLD.group_name)
+        self.symm = (buf, hdl, [int(p) for p in hdl.buffer_ptrs])
 
 
 def run_gpu_arm(args):
@@ -220,23 +227,45 @@ def run_gpu_arm(args):
     flags = 0 if args.no_pdl else capi.GEMV_FLAG_STATIC_WEIGHTS
     peak, peak_src = measured_peak_gbs()
 
-    def launch(ss: ShapeSet, j: int):
+    combine = args.combine if world > 1 else "none"
+    if combine == "peers":
+        try:
+            for ss in sets:
+                ss.make_symmetric(torch, dist)
+        except Exception as ex:  # noqa: BLE001
+            if rank == 0:
+                print(f"[bench] symmetric memory unavailable ({ex}); falling back to nccl all-gather", file=sys.stderr)
+            combine = "nccl"
+
+    def launch(ss: ShapeSet, j: int, mode: str = None):
+        mode = mode or combine
         st = torch.cuda.current_stream().cuda_stream
+        if mode == "peers":
+            buf, hdl, bases = ss.symm
+            off = j * ss.N_total * 2
+            arr = (ctypes.c_void_p * world)(*[b + off for b in bases])
+            rc = lib.xbit_gemv_f16_peers_ex(ss.a.data_ptr(), ss.qw[j].data_ptr(), ss.sc[j].data_ptr(), ss.qz[j].data_ptr(),
+                                            arr, world, 1, ss.K, ss.N, BITS, GROUP, 0, ss.N_total, ss.col0, None, 0,
+                                            family | flags, st)
+            if rc != 0:
+                raise RuntimeError(capi.last_error())
+            hdl.barrier()          # every rank's slice has landed in every buffer
+            return
         out = ss.out[j]
         rc = lib.xbit_gemv_f16_peers_ex(ss.a.data_ptr(), ss.qw[j].data_ptr(), ss.sc[j].data_ptr(), ss.qz[j].data_ptr(),
                                         (ctypes.c_void_p * 1)(out.data_ptr()), 1, 1, ss.K, ss.N, BITS, GROUP, 0,
                                         ss.N_total, ss.col0, None, 0, family | flags, st)
         if rc != 0:
             raise RuntimeError(capi.last_error())
-        if world > 1 and not args.no_gather:
+        if mode == "nccl":
             dist.all_gather_into_tensor(out.view(-1), out[:, ss.col0:ss.col0 + ss.N].reshape(-1))
 
-    def capture(set_list):
+    def capture(set_list, mode=None):
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):          # warm outside capture (module load, NCCL channels)
             for ss in set_list:
-                launch(ss, 0)
+                launch(ss, 0, mode)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
@@ -244,7 +273,7 @@ def run_gpu_arm(args):
         with torch.cuda.graph(g):
             for ss in set_list:
                 for j in range(ss.R):
-                    launch(ss, j)
+                    launch(ss, j, mode)
                     n += 1
         return g, n
 
@@ -289,6 +318,14 @@ def run_gpu_arm(args):
             "frac_of_8TBps_nominal": round(gbs / (8000.0 * world), 4), "algorithmic_bytes": ss.bytes_call,
             "rotating_sets": ss.R, "family": lib.xbit_gemv_pick_family(1, ss.K, ss.N, BITS, GROUP) if family == 0 else family}
         del g1
+        if world > 1:
+            for mode in ("none", "nccl", "peers"):
+                if mode == combine or (mode == "peers" and ss.symm is None):
+                    continue
+                g2, n2 = capture([ss], mode)
+                ms2 = timed(g2, max(3, args.steps // 4), 3) / max(3, args.steps // 4)
+                per_shape[f"{ss.K}x{ss.N_total}"][f"us_per_call_{'kernel_only' if mode == 'none' else mode}"] = round(ms2 * 1e3 / n2, 3)
+                del g2
 
     line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms_per_step, 5), "higher_is_better": True,
@@ -297,7 +334,9 @@ def run_gpu_arm(args):
                        "calls_per_step": calls_per_step,
                        "l2_policy": "inputs larger than L2: every call reads a distinct weight set, >= 1 GiB rotated per shape",
                        "launch": "one CUDA graph per step, programmatic dependent launch" + (" off" if args.no_pdl else ""),
-                       "combine": ("nccl all_gather_into_tensor per call" if world > 1 and not args.no_gather else "none"),
+                       "combine": {"nccl": "nccl all_gather_into_tensor per call",
+                                   "peers": "fused epilogue: NVLink peer stores into every rank's buffer + one symmetric-memory barrier per call",
+                                   "none": "none"}[combine],
                        "parallelism": f"n-split x{world}" if world > 1 else "single"},
             "per_shape": per_shape, "clocks": clk.summary(), "gpu_launches": calls_per_step * args.steps}
 
@@ -357,16 +396,58 @@ def run_gpu_arm(args):
     elif rank == 0:
         line["cpu_baseline"] = None
 
-    if world > 1 and rank == 0 and not args.no_single:
-        # the same (unsharded) workload on one GPU, for the strong-scaling context
-        del sets, graph
-        torch.cuda.empty_cache()
-        os.environ["WORLD_SIZE_OVERRIDE"] = "1"
-    if rank == 0:
-        print(json.dumps(line))
-    if world > 1:
+    if world > 1 and not args.no_single:
+        # the same (unsharded) workload on ONE GPU, for the strong-scaling context: rank 0 alone, others wait
+        del graph
+        sets_single = None
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        if rank == 0:
+            for ss in sets:
+                ss.qw = ss.sc = ss.qz = ss.out = None
+            torch.cuda.empty_cache()
+            sets_single = [ShapeSet(torch, dev, K, N, 1, 0, gen) for (K, N) in shapes]
+            saved = (world, combine)
+
+            def launch1(ss, j):
+                rc = lib.xbit_gemv_f16_peers_ex(ss.a.data_ptr(), ss.qw[j].data_ptr(), ss.sc[j].data_ptr(), ss.qz[j].data_ptr(),
+                                                (ctypes.c_void_p * 1)(ss.out[j].data_ptr()), 1, 1, ss.K, ss.N, BITS, GROUP, 0,
+                                                ss.N_total, 0, None, 0, family | flags, torch.cuda.current_stream().cuda_stream)
+                if rc != 0:
+                    raise RuntimeError(capi.last_error())
+
+            side = torch.cuda.Stream()
+            with torch.cuda.stream(side):
+                for ss in sets_single:
+                    launch1(ss, 0)
+            torch.cuda.synchronize()
+            g1 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g1):
+                for ss in sets_single:
+                    for j in range(ss.R):
+                        launch1(ss, j)
+            for _ in range(3):
+                g1.replay()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = max(3, args.steps // 4)
+            e0.record()
+            for _ in range(reps):
+                g1.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            ms1 = e0.elapsed_time(e1) / reps
+            b1 = sum(ss.bytes_call * ss.R for ss in sets_single)
+            line["single_gpu_same_workload"] = {"value": round(b1 / (ms1 * 1e-3) / 1e9, 2), "unit": UNIT,
+                                                "ms_per_step": round(ms1, 5), "calls_per_step": sum(ss.R for ss in sets_single)}
+            del g1
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        os._exit(0)      # NCCL communicators captured in CUDA graphs can stall interpreter teardown
     return 0
 
 
@@ -379,7 +460,8 @@ def main():
     ap.add_argument("--workload", default=None, choices=[None, *WORKLOADS])
     ap.add_argument("--family", default="auto", choices=["auto", "simt", "mma"])
     ap.add_argument("--no-pdl", action="store_true", help="do not assert static weights (no prefetch before griddepcontrol.wait)")
-    ap.add_argument("--no-gather", action="store_true", help="N>1: kernel only, skip the all-gather")
+    ap.add_argument("--combine", default="peers", choices=["peers", "nccl", "none"],
+                    help="N>1: how output slices are combined (fused NVLink peer stores | NCCL all-gather | kernel only)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-single", action="store_true")
     args = ap.parse_args()

@@ -86,7 +86,9 @@ __device__ __forceinline__ void unpack_w4_minus_zero(uint32_t w, uint32_t zc_lo,
 // bits [4,8) as w * 2^-20.  No arithmetic at all: one AND per half2.  (Tensor-core path only: the
 // products with fp16 activations are exact and are accumulated in fp32.)
 __device__ __forceinline__ void unpack_w4_subnormal(uint32_t w, uint32_t (&e)[4]) {
-  const uint32_t w8 = w >> 8;
+  // w >> 8 as a multiply-high: IMAD.HI runs on the FMA pipe, which idles here, while the ALU pipe
+  // (LOP3 / SHF) is the kernel's scarcest resource (profiles/r01_v3_ncu_gemv_mma_8192x28672.txt)
+  const uint32_t w8 = __umulhi(w, 0x01000000u);
   e[0] = w & 0x000F000Fu;
   e[1] = w & 0x00F000F0u;
   e[2] = w8 & 0x000F000Fu;
@@ -298,6 +300,9 @@ gemv_w4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
     const int zshift = 16 * (c8 & 1);
     const __half* aptr = act_sm + wk * 128 + lane_row * 8;        // this lane's word-row; + t * WK * 128 per stage
     const float zbias = (float)a.zero_bias;
+    int brow_off[kMma ? MT : 1];                                  // activation row of this lane's batch column(s)
+#pragma unroll
+    for (int mt = 0; mt < (kMma ? MT : 1); ++mt) brow_off[mt] = min(c8 + 8 * mt, a.M - 1) * pitch;
 
     for (int t = 0; t < ntiles; ++t) {
       const int s = t % kStages;
@@ -322,13 +327,11 @@ gemv_w4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
             for (int uu = 0; uu < UPG; ++uu) {
               const int u = q * UPG + uu;
               const uint4 wv = *reinterpret_cast<const uint4*>(st + ((u & 1) ? w_x1 : w_x0) + unit_row(u) * 128);
+              // batch rows >= M read a clamped (valid) row: their accumulators are never stored
               uint4 bfrag[MT];
 #pragma unroll
-              for (int mt = 0; mt < MT; ++mt) {
-                bfrag[mt] = make_uint4(0, 0, 0, 0);
-                if (c8 + 8 * mt < a.M)
-                  bfrag[mt] = *reinterpret_cast<const uint4*>(ablk + (size_t)(c8 + 8 * mt) * pitch + unit_row(u) * 8);
-              }
+              for (int mt = 0; mt < MT; ++mt)
+                bfrag[mt] = *reinterpret_cast<const uint4*>(ablk + brow_off[mt] + unit_row(u) * 8);
               const uint32_t w4[4] = {wv.x, wv.y, wv.z, wv.w};
 #pragma unroll
               for (int tt = 0; tt < 2; ++tt) {

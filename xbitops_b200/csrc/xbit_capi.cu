@@ -81,9 +81,10 @@ size_t xbit_gemv_workspace_bytes(int, int, int, int, int) {
 
 static int pick_family(const xbit::GemvArgs& a) {
   if (!xbit::gemv_w4_supported(a)) return XBIT_GEMV_GENERIC;
-  // Crossover measured on B200 (profiles/): the tensor-core kernel is at least as fast
-  // as the SIMT one from M = 1 (fp32 accumulation comes for free), so SIMT is the M == 1 default
-  // only where it wins; see xbit_gemv_pick_family's table.
+  // Crossover measured on B200 (BASELINE.json configs[4]; profiles/): with the nibble
+  // bits fed to the tensor core as fp16 subnormals the mma.sync kernel needs one ALU op per weight
+  // pair and accumulates in fp32, so it is at least as fast as the SIMT half2-FMA kernel already
+  // at M = 1 and strictly more accurate.  SIMT stays selectable (family / XBIT_GEMV_FAMILY).
   static int forced = -1;
   if (forced < 0) {
     const char* v = getenv("XBIT_GEMV_FAMILY");
@@ -92,7 +93,7 @@ static int pick_family(const xbit::GemvArgs& a) {
   if (forced == XBIT_GEMV_SIMT && a.M == 1) return XBIT_GEMV_SIMT;
   if (forced == XBIT_GEMV_MMA) return XBIT_GEMV_MMA;
   if (forced == XBIT_GEMV_GENERIC) return XBIT_GEMV_GENERIC;
-  return (a.M == 1) ? XBIT_GEMV_SIMT : XBIT_GEMV_MMA;
+  return XBIT_GEMV_MMA;
 }
 
 static int gemv_impl(const void* a_f16, const int32_t* qweight, const void* scales_f16, const int32_t* qzeros,

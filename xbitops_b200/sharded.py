@@ -1,0 +1,128 @@
+"""N-split multi-GPU wrapper for the A16Wx GEMV; no reference counterpart -- the
+reference is single-GPU (no nccl / torch.distributed anywhere in /root/reference).
+
+Output columns are independent, so rank p of P owns columns [p*N/P, (p+1)*N/P): qweight[:, slice],
+scales[:, slice] and qzeros[:, slice*bits/32] (the slice must fall on qzeros word boundaries, i.e.
+(N/P * bits) % 32 == 0).  Activations are replicated.  The only exchange step is the gather of the
+fp16 output slices (2-56 KiB in total at batch 1), done either
+  * "nccl":  in-place all_gather_into_tensor on the compute stream (baseline), or
+  * "peers": fused into the GEMV epilogue -- every rank's kernel stores its slice straight into every
+             rank's output buffer through NVLink peer mappings (torch symmetric memory), followed by
+             one symmetric-memory barrier.
+One process per GPU; torch.distributed supplies the plumbing only.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+import torch.distributed as dist
+
+from . import capi
+
+
+def shard_columns(qweight, scales, qzeros, bits: int, world: int, rank: int):
+    """Column shard `rank` of `world` of (qweight [R, N], scales [G, N], qzeros [G, N*bits/32]).
+    Works on numpy arrays and torch tensors; returns contiguous copies."""
+    n_total = qweight.shape[1]
+    if n_total % world:
+        raise ValueError(f"out_features {n_total} not divisible by world size {world}")
+    n = n_total // world
+    if (n * bits) % 32:
+        raise ValueError(f"shard width {n} x {bits} bits does not fall on qzeros word boundaries")
+    zw = n * bits // 32
+    cols = slice(rank * n, (rank + 1) * n)
+    zcols = slice(rank * zw, (rank + 1) * zw)
+    parts = (qweight[:, cols], scales[:, cols], qzeros[:, zcols])
+    if isinstance(qweight, torch.Tensor):
+        return tuple(p.contiguous() for p in parts)
+    import numpy as np
+    return tuple(np.ascontiguousarray(p) for p in parts)
+
+
+def _device_gemv_into(x, qweight, scales, qzeros, groupsize, bits, in_features, add_zero_bias, out_full, col_offset,
+                      peer_ptrs=None, family=capi.GEMV_AUTO):
+    """Local shard GEMV through the C ABI, written into out_full[:, col_offset:col_offset+n]
+    (and, with peer_ptrs, into every rank's buffer)."""
+    lib = capi.load()
+    m, n = x.shape[0], qweight.shape[1]
+    ptrs = peer_ptrs if peer_ptrs is not None else [out_full.data_ptr()]
+    arr = (ctypes.c_void_p * len(ptrs))(*ptrs)
+    capi.check(lib.xbit_gemv_f16_peers_ex(x.data_ptr(), qweight.data_ptr(), scales.data_ptr(), qzeros.data_ptr(), arr,
+                                          len(ptrs), m, in_features, n, bits, groupsize, int(add_zero_bias),
+                                          out_full.shape[1], col_offset, None, 0, int(family),
+                                          torch.cuda.current_stream().cuda_stream))
+
+
+class ShardedQLinear:
+    """y = x @ DQ(W) with W split by output columns over the ranks of `group`.
+
+    local_gemv(x, out_full, col_offset) may be injected (the CPU/gloo tests do) -- the default is the
+    CUDA path through the C ABI."""
+
+    def __init__(self, qweight_shard, scales_shard, qzeros_shard, groupsize: int, bits: int, in_features: int,
+                 out_features: int, add_zero_bias: int = 0, group=None, combine: str = "nccl", local_gemv=None):
+        self.qweight, self.scales, self.qzeros = qweight_shard, scales_shard, qzeros_shard
+        self.groupsize, self.bits, self.in_features = groupsize, bits, in_features
+        self.out_features, self.add_zero_bias = out_features, add_zero_bias
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        if out_features % self.world:
+            raise ValueError("out_features must be divisible by the world size")
+        self.n_local = out_features // self.world
+        if qweight_shard.shape[1] != self.n_local:
+            raise ValueError(f"qweight shard has {qweight_shard.shape[1]} columns, expected {self.n_local}")
+        if combine not in ("nccl", "peers", "none"):
+            raise ValueError(combine)
+        self.combine = combine
+        self._local = local_gemv
+        self._symm = None      # (buffer, handle, peer_ptrs) for combine == "peers"
+
+    # -- local compute -------------------------------------------------------------------------
+    def _local_gemv(self, x, out_full, peer_ptrs=None):
+        col0 = self.rank * self.n_local
+        if self._local is not None:
+            self._local(x, out_full, col0)
+        else:
+            _device_gemv_into(x, self.qweight, self.scales, self.qzeros, self.groupsize, self.bits, self.in_features,
+                              self.add_zero_bias, out_full, col0, peer_ptrs)
+
+    # -- symmetric memory for the fused epilogue -------------------------------------------------
+    def _symm_buffer(self, m: int, device):
+        if self._symm is not None and self._symm[0].shape[0] >= m:
+            return self._symm
+        import torch.distributed._symmetric_memory as symm_mem
+        buf = symm_mem.empty((m, self.out_features), dtype=torch.float16, device=device)
+        hdl = symm_mem.rendezvous(buf, self.group.group_name if self.group is not None else dist.group.WORLD.group_name)
+        ptrs = [int(p) for p in hdl.buffer_ptrs]
+        self._symm = (buf, hdl, ptrs)
+        return self._symm
+
+    # -- forward -----------------------------------------------------------------------------------
+    def forward(self, x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """x [M, K] fp16 (replicated on every rank) -> [M, out_features] fp16 on every rank."""
+        m = x.shape[0]
+        if self.combine == "peers" and self.world > 1:
+            buf, hdl, ptrs = self._symm_buffer(m, x.device)
+            hdl.barrier()                      # everyone has consumed the previous result
+            self._local_gemv(x, buf[:m], ptrs)
+            hdl.barrier()                      # every slice has landed everywhere
+            return buf[:m]
+        if out is None:
+            out = torch.empty((m, self.out_features), dtype=torch.float16, device=x.device)
+        self._local_gemv(x, out)
+        if self.world == 1 or self.combine == "none":
+            return out
+        col0 = self.rank * self.n_local
+        if m == 1:
+            # in place: send = recv + rank*count
+            dist.all_gather_into_tensor(out.view(-1), out[:, col0:col0 + self.n_local].reshape(-1), group=self.group)
+            return out
+        # gathered layout is [P][M][N/P]: gather into scratch, then one strided copy back
+        scratch = torch.empty((self.world, m, self.n_local), dtype=torch.float16, device=x.device)
+        dist.all_gather_into_tensor(scratch.view(-1), out[:, col0:col0 + self.n_local].contiguous().view(-1), group=self.group)
+        out.view(m, self.world, self.n_local).copy_(scratch.permute(1, 0, 2))
+        return out
+
+    __call__ = forward
