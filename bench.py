@@ -219,6 +219,9 @@ def run_gpu_arm(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = capi.load()
+    ws_bytes = max(256, lib.xbit_gemv_workspace_bytes(1, 0, 0, BITS, GROUP)) if not args.no_streamk else 0
+    ws = torch.zeros(max(ws_bytes, 256), dtype=torch.uint8, device=dev)
+    ws_ptr, ws_len = (ws.data_ptr(), ws_bytes) if ws_bytes else (None, 0)
     workload = args.workload or ("llama2-7b" if world == 1 else "llama2-70b")
     shapes = WORKLOADS[workload]
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
@@ -245,7 +248,7 @@ def run_gpu_arm(args):
             off = j * ss.N_total * 2
             arr = (ctypes.c_void_p * world)(*[b + off for b in bases])
             rc = lib.xbit_gemv_f16_peers_ex(ss.a.data_ptr(), ss.qw[j].data_ptr(), ss.sc[j].data_ptr(), ss.qz[j].data_ptr(),
-                                            arr, world, 1, ss.K, ss.N, BITS, GROUP, 0, ss.N_total, ss.col0, None, 0,
+                                            arr, world, 1, ss.K, ss.N, BITS, GROUP, 0, ss.N_total, ss.col0, ws_ptr, ws_len,
                                             family | flags, st)
             if rc != 0:
                 raise RuntimeError(capi.last_error())
@@ -254,7 +257,7 @@ def run_gpu_arm(args):
         out = ss.out[j]
         rc = lib.xbit_gemv_f16_peers_ex(ss.a.data_ptr(), ss.qw[j].data_ptr(), ss.sc[j].data_ptr(), ss.qz[j].data_ptr(),
                                         (ctypes.c_void_p * 1)(out.data_ptr()), 1, 1, ss.K, ss.N, BITS, GROUP, 0,
-                                        ss.N_total, ss.col0, None, 0, family | flags, st)
+                                        ss.N_total, ss.col0, ws_ptr, ws_len, family | flags, st)
         if rc != 0:
             raise RuntimeError(capi.last_error())
         if mode == "nccl":
@@ -334,6 +337,7 @@ def run_gpu_arm(args):
                        "calls_per_step": calls_per_step,
                        "l2_policy": "inputs larger than L2: every call reads a distinct weight set, >= 1 GiB rotated per shape",
                        "launch": "one CUDA graph per step, programmatic dependent launch" + (" off" if args.no_pdl else ""),
+                       "schedule": "cluster split-K" if args.no_streamk else "persistent stream-K (one CTA per SM) where applicable",
                        "combine": {"nccl": "nccl all_gather_into_tensor per call",
                                    "peers": "fused epilogue: NVLink peer stores into every rank's buffer + one symmetric-memory barrier per call",
                                    "none": "none"}[combine],
@@ -367,7 +371,7 @@ def run_gpu_arm(args):
             for ss, (ha, ho, da, do) in zip(sets, hs):
                 for j in range(ss.R):
                     rc = lib.xbit_gemv_f16_host(ha.data_ptr(), ho.data_ptr(), da.data_ptr(), do.data_ptr(), ss.qw[j].data_ptr(),
-                                                ss.sc[j].data_ptr(), ss.qz[j].data_ptr(), 1, ss.K, ss.N, BITS, GROUP, 0, None, 0, st)
+                                                ss.sc[j].data_ptr(), ss.qz[j].data_ptr(), 1, ss.K, ss.N, BITS, GROUP, 0, ws_ptr, ws_len, st)
                     if rc != 0:
                         raise RuntimeError(capi.last_error())
             torch.cuda.synchronize()
@@ -412,7 +416,7 @@ def run_gpu_arm(args):
             def launch1(ss, j):
                 rc = lib.xbit_gemv_f16_peers_ex(ss.a.data_ptr(), ss.qw[j].data_ptr(), ss.sc[j].data_ptr(), ss.qz[j].data_ptr(),
                                                 (ctypes.c_void_p * 1)(ss.out[j].data_ptr()), 1, 1, ss.K, ss.N, BITS, GROUP, 0,
-                                                ss.N_total, 0, None, 0, family | flags, torch.cuda.current_stream().cuda_stream)
+                                                ss.N_total, 0, ws_ptr, ws_len, family | flags, torch.cuda.current_stream().cuda_stream)
                 if rc != 0:
                     raise RuntimeError(capi.last_error())
 
@@ -463,6 +467,7 @@ def main():
     ap.add_argument("--combine", default="peers", choices=["peers", "nccl", "none"],
                     help="N>1: how output slices are combined (fused NVLink peer stores | NCCL all-gather | kernel only)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-streamk", action="store_true", help="no workspace: cluster split-K kernel instead of the persistent stream-K schedule")
     ap.add_argument("--no-single", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -85,8 +85,12 @@ XBIT_API int xbit_dequant_f16(const int32_t* qweight, const void* scales_f16, co
                               void* out_f16, int K, int N, int bits, int groupsize, int add_zero_bias,
                               xbit_stream_t stream);
 
-/* Bytes of scratch xbit_gemv_f16 needs for this problem (may be 0).  The scratch must be
- * 256-byte aligned and must not be shared by calls that can run concurrently. */
+/* Bytes of OPTIONAL scratch for xbit_gemv_f16 (0 when none is useful).  With a workspace of at
+ * least this size the W4 path runs a persistent, perfectly balanced stream-K schedule (fp32
+ * partial tiles + ready flags); without one (NULL / smaller) split-K is reduced through cluster
+ * shared memory.  The scratch must be 256-byte aligned, ZERO-INITIALISED before its first use
+ * (every call leaves it zeroed again), and must not be shared by calls that can run concurrently
+ * (calls ordered on one stream may share it). */
 XBIT_API size_t xbit_gemv_workspace_bytes(int M, int K, int N, int bits, int groupsize);
 
 /* y[m, n] = RN16( sum_k a[m, k] * DQ[k, n] ), fp32 accumulation.

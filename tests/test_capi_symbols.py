@@ -45,7 +45,8 @@ def test_validation_errors_without_gpu():
     assert lib.xbit_gemv_f16(one, one, one, one, one, 1, 128, 64, 4, 128, 0, 32, None, 0, None) == -1
     assert "out_row_stride" in capi.last_error()
     assert lib.xbit_gemv_f16(one, one, one, one, one, 1, 128, 64, 4, 128, 2, 64, None, 0, None) == -1
-    assert lib.xbit_gemv_workspace_bytes(1, 4096, 4096, 4, 128) == 0
+    assert lib.xbit_gemv_workspace_bytes(1, 4096, 4096, 4, 128) > 0       # optional stream-K scratch (W4 only)
+    assert lib.xbit_gemv_workspace_bytes(1, 4096, 4096, 3, 128) == 0
 
 
 def test_ops_reject_cpu_tensors():

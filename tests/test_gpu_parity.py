@@ -1,12 +1,13 @@
 """Parity tests proper: the CUDA path (through the C ABI) against the oracle on the same seeded
 inputs.  DQ: bit-exact.  GEMV: the north star's fp16 tolerance (max relative error <= 1e-2) against
 the fp64-accumulated truth over the bit-exact dequantised weights, written as
-    max|y - y_ref| / max|y_ref| <= 1e-2            (normalised max error, every family)
-    |y - y_ref| <= 1e-2 * max(|y_ref|, f * max|y_ref|)   element-wise, with the floor f stopping
-        near-zero outputs from blowing the relative error up: f = 0.01 for the tensor-core family
-        (fp32 accumulation), f = 0.1 for the SIMT / generic families, whose fp16
-        half2-FMA chains sit where the reference's own shipped arithmetic sits (about 5e-4 normalised,
-        tests/test_oracle.py::test_reference_arith_gemv_is_close_to_truth).
+    max|y - y_ref| / max|y_ref| <= 1e-2                      (normalised max error)
+    |y - y_ref| <= 1e-2 * |y_ref| + 2e-3 * max|y_ref|         (element-wise: 1 % relative plus an absolute
+        floor so that near-zero outputs do not blow the relative error up)
+    The truth is defined over the fp16-ROUNDED dequantised weights (the reference semantics: every
+    weight is rounded to fp16 before the dot product), which alone puts any exact-arithmetic kernel
+    ~3e-4 (normalised) away from it; the reference's own shipped kernel sits at ~5e-4
+    (tests/test_oracle.py::test_reference_arith_gemv_is_close_to_truth), ours at 4e-4 .. 9e-4.
 Run on the B200 box: pytest -m gpu."""
 import ctypes
 
@@ -42,11 +43,11 @@ def assert_gemv_close(y, y64, what="", floor=0.1):
     mx = np.abs(y64).max()
     err = np.abs(y - y64)
     assert err.max() / mx <= GEMV_TOL, f"{what}: normalised max error {err.max() / mx:.3e}"
-    assert (err <= GEMV_TOL * np.maximum(np.abs(y64), floor * mx)).all(), f"{what}: element-wise bound violated"
+    assert (err <= GEMV_TOL * np.abs(y64) + 2e-3 * mx).all(), f"{what}: element-wise bound violated"
 
 
 def floor_of(family):
-    return 0.01 if family == capi.GEMV_MMA else 0.1
+    return 0.1
 
 
 # ------------------------------------------------------------------ dequant

@@ -172,6 +172,7 @@ def main():
     if not args.no_time:
         print("== timings (us/call: median, min) ; rotating weights > L2 unless noted")
         lib = capi.load()
+        WS = torch.zeros(max(256, lib.xbit_gemv_workspace_bytes(16, 0, 0, 4, 128)), dtype=torch.uint8, device=dev)
         peak = 6549.8
         shapes = [(4096, 4096), (4096, 11008), (11008, 4096)] + ([] if args.quick else [(8192, 8192), (8192, 28672), (28672, 8192)])
         for (K, N) in shapes:
@@ -191,7 +192,7 @@ def main():
                         j = i % R
                         st = torch.cuda.current_stream().cuda_stream
                         rc = lib.xbit_gemv_f16_ex(a.data_ptr(), qw[j].data_ptr(), sc[j].data_ptr(), qz[j].data_ptr(),
-                                                  out[j].data_ptr(), 1, K, N, bits, g, 0, N, None, 0, fam | flags, st)
+                                                  out[j].data_ptr(), 1, K, N, bits, g, 0, N, WS.data_ptr(), WS.numel(), fam | flags, st)
                         assert rc == 0, capi.last_error()
                     med, mn = time_graph(fn, R)
                     line += f"  {name}{fl} {med:.2f}/{mn:.2f}us ({nbytes/med/1e3/peak*100:.0f}%)"
@@ -234,7 +235,7 @@ def main():
                         j = i % R
                         st = torch.cuda.current_stream().cuda_stream
                         rc = lib.xbit_gemv_f16_ex(a.data_ptr(), qw[j].data_ptr(), sc[j].data_ptr(), qz[j].data_ptr(),
-                                                  out[j].data_ptr(), M, K, N, bits, g, 0, N, None, 0,
+                                                  out[j].data_ptr(), M, K, N, bits, g, 0, N, WS.data_ptr(), WS.numel(),
                                                   fam | capi.GEMV_FLAG_STATIC_WEIGHTS, st)
                         assert rc == 0, capi.last_error()
                     med, mn = time_graph(fn, R)

@@ -11,6 +11,7 @@ from xbitops_b200 import capi, synth  # noqa: E402
 
 dev = torch.device("cuda:0")
 lib = capi.load()
+WS = torch.zeros(max(256, lib.xbit_gemv_workspace_bytes(16, 0, 0, 4, 128)), dtype=torch.uint8, device=dev)
 PEAK = 6549.8
 
 
@@ -60,7 +61,7 @@ def main():
         R, qw, sc, qz, a, out, nbytes = make(K, N, R=8)
         for i in range(8):
             rc = lib.xbit_gemv_f16_ex(a.data_ptr(), qw[i % R].data_ptr(), sc[i % R].data_ptr(), qz[i % R].data_ptr(),
-                                      out[i % R].data_ptr(), M, K, N, 4, 128, 0, N, None, 0, fam,
+                                      out[i % R].data_ptr(), M, K, N, 4, 128, 0, N, WS.data_ptr(), WS.numel(), fam,
                                       torch.cuda.current_stream().cuda_stream)
             assert rc == 0, capi.last_error()
         torch.cuda.synchronize()
@@ -72,27 +73,25 @@ def main():
         R, qw, sc, qz, a, out, nbytes = make(K, N)
         print(f"== {K}x{N} {nbytes/1e6:.1f} MB R={R} roofline {nbytes/PEAK/1e3:.2f} us")
         for fam, name in ((capi.GEMV_SIMT, "simt"), (capi.GEMV_MMA, "mma")):
-            for wc in (0, 1, 2, 4):
-                row = f"   {name} wc={wc if wc else 'A'}:"
-                for splits in ((0,) if wc == 0 else (1, 2, 4, 8)):
-                    for flags, fl in ((0, ""), (capi.GEMV_FLAG_STATIC_WEIGHTS, "p")):
-                        if wc and not flags:
-                            continue
-                        os.environ["XBIT_GEMV_SPLITS"] = str(splits)
-                        os.environ["XBIT_GEMV_WC"] = str(wc)
+            row = f"   {name}:"
+            for label, use_ws, ring in (("cluster", False, 0), ("sk-auto", True, 0), ("sk-r3", True, 3), ("sk-r4", True, 4),
+                                        ("sk-r5", True, 5), ("sk-r6", True, 6), ("sk-r8", True, 8)):
+                for flags, fl in ((0, ""), (capi.GEMV_FLAG_STATIC_WEIGHTS, "p")):
+                    if not flags and label not in ("cluster", "sk-auto"):
+                        continue
+                    os.environ["XBIT_GEMV_RING"] = str(ring)
+                    wsp, wsn = (WS.data_ptr(), WS.numel()) if use_ws else (None, 0)
 
-                        def fn(i):
-                            j = i % R
-                            rc = lib.xbit_gemv_f16_ex(a.data_ptr(), qw[j].data_ptr(), sc[j].data_ptr(), qz[j].data_ptr(),
-                                                      out[j].data_ptr(), 1, K, N, 4, 128, 0, N, None, 0,
-                                                      fam | flags, torch.cuda.current_stream().cuda_stream)
-                            assert rc == 0, capi.last_error()
-                        try:
-                            us = time_graph(fn, R)
-                            row += f"  s{splits if splits else 'A'}{fl} {us:6.2f}us {nbytes/us/1e3/PEAK*100:3.0f}%"
-                        except AssertionError as ex:
-                            row += f"  s{splits}{fl} n/a"
-                print(row, flush=True)
+                    def fn(i):
+                        j = i % R
+                        rc = lib.xbit_gemv_f16_ex(a.data_ptr(), qw[j].data_ptr(), sc[j].data_ptr(), qz[j].data_ptr(),
+                                                  out[j].data_ptr(), 1, K, N, 4, 128, 0, N, wsp, wsn,
+                                                  fam | flags, torch.cuda.current_stream().cuda_stream)
+                        assert rc == 0, capi.last_error()
+                    us = time_graph(fn, R)
+                    row += f"  {label}{fl} {us:6.2f}us {nbytes/us/1e3/PEAK*100:3.0f}%"
+            print(row, flush=True)
+        os.environ["XBIT_GEMV_RING"] = "0"
         os.environ["XBIT_GEMV_WC"] = "0"
         os.environ["XBIT_GEMV_SPLITS"] = "0"
         del qw, sc, qz, out

@@ -21,6 +21,9 @@
 #include <torch/extension.h>
 
 #include <cstdint>
+#include <map>
+#include <mutex>
+#include <utility>
 #include <vector>
 
 #include "../../include/xbitops_b200.h"
@@ -57,6 +60,21 @@ void check_quant_args(const torch::Tensor& qweight, const torch::Tensor& scales,
 }
 
 void raise_if(int rc) { TORCH_CHECK(rc == XBIT_OK, "xbitops_b200: ", xbit_last_error()); }
+
+// Zero-initialised scratch for the persistent stream-K GEMV schedule, one per (device, stream):
+// calls on one stream are ordered, calls on different streams must not share it.
+at::Tensor& gemv_workspace(const at::Device& device, cudaStream_t stream) {
+  static std::mutex mu;
+  static std::map<std::pair<int, void*>, at::Tensor> cache;
+  std::lock_guard<std::mutex> lock(mu);
+  auto key = std::make_pair((int)device.index(), (void*)stream);
+  auto it = cache.find(key);
+  if (it == cache.end()) {
+    const int64_t nbytes = (int64_t)xbit_gemv_workspace_bytes(16, 0, 0, 4, 128);
+    it = cache.emplace(key, at::zeros({nbytes < 256 ? 256 : nbytes}, at::TensorOptions().dtype(at::kByte).device(device))).first;
+  }
+  return it->second;
+}
 
 }  // namespace
 
@@ -96,9 +114,10 @@ torch::Tensor op_gemv(const torch::Tensor& input_a, const torch::Tensor& qweight
   at::Tensor output = at::empty(outputshape, f16_scale.options());
   auto stream = at::cuda::getCurrentCUDAStream().stream();
   if (mat_m > 0) {
+    at::Tensor& ws = gemv_workspace(qweight.device(), stream);
     raise_if(xbit_gemv_f16(input_a.data_ptr(), qweight.data_ptr<int32_t>(), f16_scale.data_ptr(),
                            qzeros.data_ptr<int32_t>(), output.data_ptr(), (int)mat_m, in_features, (int)qweight.size(1),
-                           bits, groupsize, add_zero_bias, qweight.size(1), nullptr, 0,
+                           bits, groupsize, add_zero_bias, qweight.size(1), ws.data_ptr(), (size_t)ws.numel(),
                            reinterpret_cast<xbit_stream_t>(stream)));
   }
   if (ori_dtype == torch::kBFloat16) output = output.to(torch::kBFloat16);

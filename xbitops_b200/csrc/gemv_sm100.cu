@@ -160,6 +160,162 @@ struct W4Cfg {
   static constexpr uint32_t kTxBytes = kWeights + kScales + kZeros;   // TMA boxes always deliver their full size
 };
 
+// Per-lane constants of a consumer warp (wc = column chunk, wk = K-slice of the stage).
+template <int MT>
+struct W4Lane {
+  uint32_t w_x0, w_x1;      // byte offsets of this lane's 16-byte chunk for units with u%2 == 0 / 1
+  uint32_t s_off, z_off;    // byte offsets of this lane's scales / zero word inside a stage
+  int zshift;               // 0 or 16: which half of the zero word holds this lane's 4 nibbles
+  int r;                    // lane % 4
+  int brow_off[MT > 0 ? MT : 1];   // activation row offset (halves) of this lane's batch column(s)
+  float zbias;
+  uint32_t zero_bias;
+};
+
+// One 128-k block (GPB scale groups of UPG 32-k units) of one stage: `st` = stage base, `ablk` = this
+// lane's activations of the block (act_sm + block offset + lane word-row), `asum_blk` = group sums of
+// the block ([GPB][MROWS], mma only).  Accumulates into tot.
+template <int MT, int UPG, int WC>
+__device__ __forceinline__ void w4_consume_block(const unsigned char* __restrict__ st, const __half* __restrict__ ablk,
+                                                 const float* __restrict__ asum_blk, const W4Lane<MT>& L,
+                                                 float (&tot)[MT > 0 ? 2 * MT : 1][4]) {
+  using Cfg = W4Cfg<UPG, WC>;
+  constexpr bool kMma = MT > 0;
+  constexpr int MROWS = kMma ? 8 * MT : 1;
+  constexpr int NT = Cfg::NT, GPB = Cfg::GPB;
+  auto unit_row = [](int u) constexpr { return (UPG == 1) ? 4 * u : 8 * (u >> 1) + (u & 1); };
+  const uint32_t s_off = L.s_off, z_off = L.z_off, w_x0 = L.w_x0, w_x1 = L.w_x1;
+  const int zshift = L.zshift, r = L.r;
+  const float zbias = L.zbias;
+  (void)r; (void)zbias; (void)asum_blk; (void)MROWS;
+#pragma unroll
+  for (int q = 0; q < GPB; ++q) {
+    const uint2 sraw = *reinterpret_cast<const uint2*>(st + s_off + q * (NT * 2));
+    const uint32_t zraw = *reinterpret_cast<const uint32_t*>(st + z_off + q * (NT / 2)) >> zshift;
+    float sf[4];
+    {
+      const float2 s01 = __half22float2(u2h2(sraw.x));
+      const float2 s23 = __half22float2(u2h2(sraw.y));
+      sf[0] = s01.x; sf[1] = s01.y; sf[2] = s23.x; sf[3] = s23.y;
+    }
+    if constexpr (kMma) {
+      float grp[2 * MT][4];
+#pragma unroll
+      for (int uu = 0; uu < UPG; ++uu) {
+        const int u = q * UPG + uu;
+        const uint4 wv = *reinterpret_cast<const uint4*>(st + ((u & 1) ? w_x1 : w_x0) + unit_row(u) * 128);
+        // batch rows >= M read a clamped (valid) row: their accumulators are never stored
+        uint4 bfrag[MT];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+          bfrag[mt] = *reinterpret_cast<const uint4*>(ablk + L.brow_off[mt] + unit_row(u) * 8);
+        const uint32_t w4[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+        for (int tt = 0; tt < 2; ++tt) {
+          uint32_t ea[4], eb[4];
+          unpack_w4_subnormal(w4[2 * tt], ea);
+          unpack_w4_subnormal(w4[2 * tt + 1], eb);
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            if (uu == 0) mma_m16n8k16_zero(grp[tt * MT + mt], ea[0], eb[0], ea[1], eb[1], bfrag[mt].x, bfrag[mt].y);
+            else         mma_m16n8k16(grp[tt * MT + mt], ea[0], eb[0], ea[1], eb[1], bfrag[mt].x, bfrag[mt].y);
+            mma_m16n8k16(grp[tt * MT + mt], ea[2], eb[2], ea[3], eb[3], bfrag[mt].z, bfrag[mt].w);
+          }
+        }
+      }
+      // grp = 2^-24 * sum_k a_k w_k (exact products, fp32 accumulation).  y += s * (2^24 grp - z * sum_k a_k).
+      // accumulators 0,1 belong to column 2*tt (rows m = 2r, 2r+1), accumulators 2,3 to column 2*tt+1.
+      float s24[4], nsz[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        s24[j] = sf[j] * 16777216.f;
+        nsz[j] = -sf[j] * ((float)((zraw >> (4 * j)) & 0xFu) + zbias);
+      }
+      const float* asum = asum_blk + q * MROWS + 2 * r;
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        const float2 as = *reinterpret_cast<const float2*>(asum + 8 * mt);
+#pragma unroll
+        for (int tt = 0; tt < 2; ++tt)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int j = 2 * tt + (i >> 1);
+            float acc = tot[tt * MT + mt][i];
+            acc = fmaf(s24[j], grp[tt * MT + mt][i], acc);
+            acc = fmaf(nsz[j], (i & 1) ? as.y : as.x, acc);
+            tot[tt * MT + mt][i] = acc;
+          }
+      }
+    } else {
+      uint32_t zlo[4], zhi[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t zb = ((zraw >> (4 * j)) & 0xFu) + L.zero_bias;   // <= 16
+        zlo[j] = (magic_base_bits(0) + zb) * 0x00010001u;          // half2(1024 + z)
+        zhi[j] = (magic_base_bits(4) + (zb << 4)) * 0x00010001u;   // half2(64 + z)
+      }
+      float grp[4] = {0.f, 0.f, 0.f, 0.f};
+      __half2 acc[4];
+#pragma unroll
+      for (int uu = 0; uu < UPG; ++uu) {
+        const int u = q * UPG + uu;
+        const uint4 wv = *reinterpret_cast<const uint4*>(st + ((u & 1) ? w_x1 : w_x0) + unit_row(u) * 128);
+        const uint4 av = *reinterpret_cast<const uint4*>(ablk + unit_row(u) * 8);
+        const uint32_t w4[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t e[4];
+          unpack_w4_minus_zero(w4[j], zlo[j], zhi[j], e);
+          __half2 c;
+          if (uu & 1) c = __hfma2(u2h2(e[0]), u2h2(av.x), acc[j]);
+          else        c = __hmul2(u2h2(e[0]), u2h2(av.x));
+          c = __hfma2(u2h2(e[1]), u2h2(av.y), c);
+          c = __hfma2(u2h2(e[2]), u2h2(av.z), c);
+          c = __hfma2(u2h2(e[3]), u2h2(av.w), c);
+          acc[j] = c;
+        }
+        if ((uu & 1) || uu == UPG - 1) {      // flush the fp16 chains to fp32 every 2 units
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = __half22float2(acc[j]);
+            grp[j] += f.x + f.y;
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) tot[0][j] = fmaf(sf[j], grp[j], tot[0][j]);
+    }
+  }
+}
+
+template <int UPG>
+__device__ __forceinline__ int w4_lane_row(int lane) { return ((UPG == 1) ? 1 : 2) * (lane & 3); }
+
+// Word-row of (unit u, lane r) inside a 16-row block: UPG >= 2: 8*(u/2) + 2r + (u%2) -- conflict-free
+// under the 128-byte swizzle; UPG == 1 (groupsize 32): 4u + r, so that a unit stays inside one scale
+// group (2-way conflict).  16-byte chunk c8 of row rho lives at chunk c8 ^ (rho & 7).
+template <int MT, int UPG, int WC>
+__device__ __forceinline__ W4Lane<MT> make_w4_lane(int lane, int wc, int wk, int M, int pitch, int zero_bias) {
+  using Cfg = W4Cfg<UPG, WC>;
+  constexpr int kOddRowAdd = (UPG == 1) ? 4 : 1;
+  W4Lane<MT> L;
+  const int r = lane & 3, c8 = lane >> 2;
+  const int lane_row = w4_lane_row<UPG>(lane);
+  const int col_local = 32 * wc + 4 * c8;                         // this lane's first column inside the tile
+  const uint32_t w_row = (uint32_t)(wc * Cfg::kBoxBytes + (wk * 16 + lane_row) * 128);
+  L.w_x0 = w_row + (uint32_t)((c8 ^ lane_row) * 16);
+  L.w_x1 = w_row + (uint32_t)((c8 ^ (lane_row + kOddRowAdd)) * 16);
+  L.s_off = (uint32_t)(Cfg::kWeights + wk * Cfg::GPB * (Cfg::NT * 2) + col_local * 2);
+  L.z_off = (uint32_t)(Cfg::kWeights + Cfg::kScales + wk * Cfg::GPB * (Cfg::NT / 2) + (col_local >> 3) * 4);
+  L.zshift = 16 * (c8 & 1);
+  L.r = r;
+#pragma unroll
+  for (int mt = 0; mt < (MT > 0 ? MT : 1); ++mt) L.brow_off[mt] = min(c8 + 8 * mt, M - 1) * pitch;
+  L.zbias = (float)zero_bias;
+  L.zero_bias = (uint32_t)zero_bias;
+  return L;
+}
+
 // MT = 0: SIMT kernel, M == 1.  MT = 1, 2: mma.sync kernel, M <= 8 * MT.
 // UPG = 32-k units per scale group inside a 128-k block: 4 (groupsize 128), 2 (64), 1 (32).
 //
@@ -287,22 +443,8 @@ gemv_w4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
     }
     asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");
 
-    const int col_local = 32 * wc + 4 * c8;                       // this lane's first column inside the tile
-    // swizzled box of this warp's column chunk: 16-byte chunk c8 of row rho lives at chunk c8 ^ (rho & 7)
-    constexpr int kLaneRowMul = (UPG == 1) ? 1 : 2;
-    constexpr int kOddRowAdd = (UPG == 1) ? 4 : 1;
-    const int lane_row = kLaneRowMul * r;
-    const uint32_t w_row = (uint32_t)(wc * Cfg::kBoxBytes + (wk * 16 + lane_row) * 128);
-    const uint32_t w_x0 = w_row + (uint32_t)((c8 ^ lane_row) * 16);                // units with u % 2 == 0
-    const uint32_t w_x1 = w_row + (uint32_t)((c8 ^ (lane_row + kOddRowAdd)) * 16); // units with u % 2 == 1
-    const uint32_t s_off = (uint32_t)(Cfg::kWeights + wk * GPB * (NT * 2) + col_local * 2);
-    const uint32_t z_off = (uint32_t)(Cfg::kWeights + Cfg::kScales + wk * GPB * (NT / 2) + (col_local >> 3) * 4);
-    const int zshift = 16 * (c8 & 1);
-    const __half* aptr = act_sm + wk * 128 + lane_row * 8;        // this lane's word-row; + t * WK * 128 per stage
-    const float zbias = (float)a.zero_bias;
-    int brow_off[kMma ? MT : 1];                                  // activation row of this lane's batch column(s)
-#pragma unroll
-    for (int mt = 0; mt < (kMma ? MT : 1); ++mt) brow_off[mt] = min(c8 + 8 * mt, a.M - 1) * pitch;
+    const W4Lane<MT> L = make_w4_lane<MT, UPG, WC>(lane, wc, wk, a.M, pitch, a.zero_bias);
+    const __half* aptr = act_sm + wk * 128 + w4_lane_row<UPG>(lane) * 8;   // this lane's word-row; + t * WK * 128 per stage
 
     for (int t = 0; t < ntiles; ++t) {
       const int s = t % kStages;
@@ -310,105 +452,7 @@ gemv_w4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
       const unsigned char* st = stage_base + s * Cfg::kStageBytes;
       const int blk_local = t * WK + wk;                          // block index inside this CTA's range
       if (b0 + blk_local < b1) {                                  // warp-uniform (the last stage may be partly empty)
-        const __half* ablk = aptr + t * (WK * 128);
-#pragma unroll
-        for (int q = 0; q < GPB; ++q) {
-          const uint2 sraw = *reinterpret_cast<const uint2*>(st + s_off + q * (NT * 2));
-          const uint32_t zraw = *reinterpret_cast<const uint32_t*>(st + z_off + q * (NT / 2)) >> zshift;
-          float sf[4];
-          {
-            const float2 s01 = __half22float2(u2h2(sraw.x));
-            const float2 s23 = __half22float2(u2h2(sraw.y));
-            sf[0] = s01.x; sf[1] = s01.y; sf[2] = s23.x; sf[3] = s23.y;
-          }
-          if constexpr (kMma) {
-            float grp[2 * MT][4];
-#pragma unroll
-            for (int uu = 0; uu < UPG; ++uu) {
-              const int u = q * UPG + uu;
-              const uint4 wv = *reinterpret_cast<const uint4*>(st + ((u & 1) ? w_x1 : w_x0) + unit_row(u) * 128);
-              // batch rows >= M read a clamped (valid) row: their accumulators are never stored
-              uint4 bfrag[MT];
-#pragma unroll
-              for (int mt = 0; mt < MT; ++mt)
-                bfrag[mt] = *reinterpret_cast<const uint4*>(ablk + brow_off[mt] + unit_row(u) * 8);
-              const uint32_t w4[4] = {wv.x, wv.y, wv.z, wv.w};
-#pragma unroll
-              for (int tt = 0; tt < 2; ++tt) {
-                uint32_t ea[4], eb[4];
-                unpack_w4_subnormal(w4[2 * tt], ea);
-                unpack_w4_subnormal(w4[2 * tt + 1], eb);
-#pragma unroll
-                for (int mt = 0; mt < MT; ++mt) {
-                  if (uu == 0) mma_m16n8k16_zero(grp[tt * MT + mt], ea[0], eb[0], ea[1], eb[1], bfrag[mt].x, bfrag[mt].y);
-                  else         mma_m16n8k16(grp[tt * MT + mt], ea[0], eb[0], ea[1], eb[1], bfrag[mt].x, bfrag[mt].y);
-                  mma_m16n8k16(grp[tt * MT + mt], ea[2], eb[2], ea[3], eb[3], bfrag[mt].z, bfrag[mt].w);
-                }
-              }
-            }
-            // grp = 2^-24 * sum_k a_k w_k (exact products, fp32 accumulation).  y += s * (2^24 grp - z * sum_k a_k).
-            // accumulators 0,1 belong to column 2*tt (rows m = 2r, 2r+1), accumulators 2,3 to column 2*tt+1.
-            float s24[4], nsz[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              s24[j] = sf[j] * 16777216.f;
-              nsz[j] = -sf[j] * ((float)((zraw >> (4 * j)) & 0xFu) + zbias);
-            }
-            const float* asum = asum_sm + (blk_local * GPB + q) * MROWS + 2 * r;
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {
-              const float2 as = *reinterpret_cast<const float2*>(asum + 8 * mt);
-#pragma unroll
-              for (int tt = 0; tt < 2; ++tt)
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const int j = 2 * tt + (i >> 1);
-                  float acc = tot[tt * MT + mt][i];
-                  acc = fmaf(s24[j], grp[tt * MT + mt][i], acc);
-                  acc = fmaf(nsz[j], (i & 1) ? as.y : as.x, acc);
-                  tot[tt * MT + mt][i] = acc;
-                }
-            }
-          } else {
-            uint32_t zlo[4], zhi[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint32_t zb = ((zraw >> (4 * j)) & 0xFu) + (uint32_t)a.zero_bias;   // <= 16
-              zlo[j] = (magic_base_bits(0) + zb) * 0x00010001u;          // half2(1024 + z)
-              zhi[j] = (magic_base_bits(4) + (zb << 4)) * 0x00010001u;   // half2(64 + z)
-            }
-            float grp[4] = {0.f, 0.f, 0.f, 0.f};
-            __half2 acc[4];
-#pragma unroll
-            for (int uu = 0; uu < UPG; ++uu) {
-              const int u = q * UPG + uu;
-              const uint4 wv = *reinterpret_cast<const uint4*>(st + ((u & 1) ? w_x1 : w_x0) + unit_row(u) * 128);
-              const uint4 av = *reinterpret_cast<const uint4*>(ablk + unit_row(u) * 8);
-              const uint32_t w4[4] = {wv.x, wv.y, wv.z, wv.w};
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                uint32_t e[4];
-                unpack_w4_minus_zero(w4[j], zlo[j], zhi[j], e);
-                __half2 c;
-                if (uu & 1) c = __hfma2(u2h2(e[0]), u2h2(av.x), acc[j]);
-                else        c = __hmul2(u2h2(e[0]), u2h2(av.x));
-                c = __hfma2(u2h2(e[1]), u2h2(av.y), c);
-                c = __hfma2(u2h2(e[2]), u2h2(av.z), c);
-                c = __hfma2(u2h2(e[3]), u2h2(av.w), c);
-                acc[j] = c;
-              }
-              if ((uu & 1) || uu == UPG - 1) {      // flush the fp16 chains to fp32 every 2 units
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float2 f = __half22float2(acc[j]);
-                  grp[j] += f.x + f.y;
-                }
-              }
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) tot[0][j] = fmaf(sf[j], grp[j], tot[0][j]);
-          }
-        }
+        w4_consume_block<MT, UPG, WC>(st, aptr + t * (WK * 128), asum_sm + blk_local * GPB * MROWS, L, tot);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bar[s]);
@@ -468,6 +512,215 @@ gemv_w4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
       const size_t off = (size_t)m * a.ldo + a.col_offset + n_cta + col;
       a.out[0][off] = h;
       for (int p = 1; p < a.world; ++p) a.out[p][off] = h;   // fused all-gather: NVLink peer stores
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Persistent stream-K variant: one CTA per SM, perfectly balanced.
+//
+// Work = (128-column tile, stage of 2 x 128 k) items in tile-major order, W = tiles * stages_per_tile.
+// CTA c of G owns the contiguous range [W*c/G, W*(c+1)/G): at most the tail of one tile, some whole
+// tiles and the head of another.  Whole tiles are written directly.  For a tile shared by several
+// CTAs the one holding its LAST stage is the finisher: the others publish their fp32 partial tile in
+// the workspace (release flag), the finisher adds them in CTA order (deterministic, no atomics) after
+// it has finished all of its own streaming, and clears the flags.  Every CTA is resident (G <= #SMs),
+// contributors never wait on anybody, so the wait cannot deadlock.
+// Same producer / consumer pipeline and per-block math as gemv_w4_kernel (WC = 4, WK = 2); the
+// whole activation vector is staged once per CTA.
+constexpr int kSkMaxRing = 8;
+
+template <int MT, int UPG>
+__global__ void __launch_bounds__(kW4Threads, 1)
+gemv_w4_streamk_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap smap,
+                       const __grid_constant__ CUtensorMap zmap, const GemvArgs a) {
+  constexpr int WC = 4;
+  using Cfg = W4Cfg<UPG, WC>;
+  constexpr bool kMma = MT > 0;
+  constexpr int MROWS = kMma ? 8 * MT : 1;
+  constexpr int WK = Cfg::WK, NT = Cfg::NT, GPB = Cfg::GPB;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int G = gridDim.x, c = blockIdx.x;
+  const int S_t = a.sk_stages_per_tile;
+  const long long W = a.sk_total_stages;
+  const int s_lo = (int)(W * c / G), s_hi = (int)(W * (c + 1) / G);
+  const int nst = s_hi - s_lo;
+  const int ring = a.sk_ring;
+  const int kpad = S_t * WK * 128;                  // K rounded up to whole stages
+  const int pitch = kpad + 32;                      // halves per staged activation row (+64 B: bank spread)
+  const int ngroups = S_t * WK * GPB;
+
+  unsigned char* stage_base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_base + ring * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + kSkMaxRing;
+  __half* act_sm = reinterpret_cast<__half*>(stage_base + ring * Cfg::kStageBytes + 128);          // [M][pitch]
+  float* asum_sm = reinterpret_cast<float*>(act_sm + (size_t)a.M * pitch);                         // [ngroups][MROWS] (mma only)
+  float* red_sm = asum_sm + (kMma ? ngroups * MROWS : 0);                                          // [WK][M][NT]
+  float* first_sm = red_sm + WK * a.M * NT;                                                        // [M][NT] deferred first tile
+
+  if (tid == 0) {
+    for (int s = 0; s < ring; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  griddep_launch_dependents();     // see gemv_w4_kernel
+
+  if (warp == 8) {
+    // =========================== producer ===========================
+    if (!a.static_weights) griddep_wait();
+    if (lane == 0 && nst > 0) {
+      uint64_t policy;
+      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&wmap) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&smap) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&zmap) : "memory");
+      int tile = s_lo / S_t, stg = s_lo - tile * S_t;
+      for (int it = 0; it < nst; ++it) {
+        const int s = it % ring;
+        if (it >= ring) mbar_wait(&empty_bar[s], ((it / ring) - 1) & 1);
+        unsigned char* st = stage_base + s * Cfg::kStageBytes;
+        const int n0 = tile * NT, blk = stg * WK;
+        mbar_arrive_expect_tx(&full_bar[s], Cfg::kTxBytes);
+#pragma unroll
+        for (int cc = 0; cc < WC; ++cc) tma_load_2d(st + cc * Cfg::kBoxBytes, &wmap, n0 + 32 * cc, blk * 16, &full_bar[s], policy);
+        tma_load_2d(st + Cfg::kWeights, &smap, n0, blk * GPB, &full_bar[s], policy);
+        tma_load_2d(st + Cfg::kWeights + Cfg::kScales, &zmap, n0 >> 3, blk * GPB, &full_bar[s], policy);
+        if (++stg == S_t) { stg = 0; ++tile; }
+      }
+    }
+    __syncwarp();
+  } else {
+    // =========================== consumers ===========================
+    const int r = lane & 3, c8 = lane >> 2;
+    const int wc = warp & (WC - 1), wk = (warp / WC) & (WK - 1);
+    griddep_wait();
+    {
+      // whole activation vector, zero padded to kpad; mma path: sum_k a_k per scale group
+      const int vecs_per_row = kpad / 8, vecs_valid = a.K / 8;
+      for (int base = 0; base < a.M * vecs_per_row; base += kConsumerThreads) {
+        const int idx = base + tid;
+        const bool ok = idx < a.M * vecs_per_row;
+        const int m = ok ? idx / vecs_per_row : 0, v = ok ? idx - m * vecs_per_row : 0;
+        uint4 val = make_uint4(0, 0, 0, 0);
+        if (ok) {
+          if (v < vecs_valid) val = __ldg(reinterpret_cast<const uint4*>(a.a + (size_t)m * a.K) + v);
+          *reinterpret_cast<uint4*>(act_sm + (size_t)m * pitch + v * 8) = permute_act8<kMma>(val);
+        }
+        if constexpr (kMma) {
+          const float2 f0 = __half22float2(u2h2(val.x)), f1 = __half22float2(u2h2(val.y));
+          const float2 f2 = __half22float2(u2h2(val.z)), f3 = __half22float2(u2h2(val.w));
+          float sum = ((f0.x + f0.y) + (f1.x + f1.y)) + ((f2.x + f2.y) + (f3.x + f3.y));
+#pragma unroll
+          for (int o = 1; o < 4 * UPG; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+          if (ok && (lane & (4 * UPG - 1)) == 0) asum_sm[(v / (4 * UPG)) * MROWS + m] = sum;
+        }
+      }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");
+
+    const W4Lane<MT> L = make_w4_lane<MT, UPG, WC>(lane, wc, wk, a.M, pitch, a.zero_bias);
+    const __half* aptr = act_sm + w4_lane_row<UPG>(lane) * 8;     // + blk * 128 per block (blk includes this warp's K-slice)
+    const int nout = a.M * NT;
+    float tot[kMma ? 2 * MT : 1][4];
+#pragma unroll
+    for (int v = 0; v < (kMma ? 2 * MT : 1); ++v)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) tot[v][i] = 0.f;
+
+    int tile = nst > 0 ? s_lo / S_t : 0;
+    int stg = nst > 0 ? s_lo - tile * S_t : 0;
+    int seg_lo = stg;
+    int first_tile = -1;                            // tile whose fix-up is deferred to the end
+
+    auto store_tile = [&](int tl, int o, float v) {
+      const int m = o / NT, col = o - m * NT;
+      const int n = tl * NT + col;
+      if (n < a.N) {
+        const __half h = __float2half_rn(v);
+        const size_t off = (size_t)m * a.ldo + a.col_offset + n;
+        a.out[0][off] = h;
+        for (int p = 1; p < a.world; ++p) a.out[p][off] = h;   // fused all-gather: NVLink peer stores
+      }
+    };
+
+    for (int it = 0; it < nst; ++it) {
+      const int s = it % ring;
+      mbar_wait(&full_bar[s], (it / ring) & 1);
+      const unsigned char* st = stage_base + s * Cfg::kStageBytes;
+      const int blk = stg * WK + wk;                // block index inside the tile's K range (past K: all zeros)
+      w4_consume_block<MT, UPG, WC>(st, aptr + blk * 128, asum_sm + blk * GPB * MROWS, L, tot);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[s]);
+      ++stg;
+      if (stg == S_t || it == nst - 1) {
+        // ---- end of a segment [seg_lo, stg) of `tile`: K-slices -> one fp32 partial tile
+        if constexpr (!kMma) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float v = tot[0][j];
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            if (r == 0) red_sm[wk * NT + 32 * wc + 4 * c8 + j] = v;
+            tot[0][j] = 0.f;
+          }
+        } else {
+#pragma unroll
+          for (int tt = 0; tt < 2; ++tt)
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int m = 8 * mt + 2 * r + (i & 1);
+                const int col = 32 * wc + 4 * c8 + 2 * tt + (i >> 1);
+                if (m < a.M) red_sm[(wk * a.M + m) * NT + col] = tot[tt * MT + mt][i];
+                tot[tt * MT + mt][i] = 0.f;
+              }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");
+        const bool whole = (seg_lo == 0 && stg == S_t);
+        const bool is_end = (stg == S_t);
+        for (int o = tid; o < nout; o += kConsumerThreads) {
+          float v = 0.f;
+#pragma unroll
+          for (int w = 0; w < WK; ++w) v += red_sm[w * nout + o];
+          if (whole) store_tile(tile, o, v);
+          else if (is_end) first_sm[o] = v;                          // finisher: add the other CTAs' parts at the end
+          else a.sk_partials[(size_t)c * nout + o] = v;              // contributor: publish
+        }
+        if (!whole && is_end) first_tile = tile;
+        if (!whole && !is_end) {
+          __threadfence();
+          asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");
+          if (tid == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.sk_flags + c), "r"(1u) : "memory");
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");   // red_sm is reused by the next segment
+        seg_lo = 0;
+        if (stg == S_t) { stg = 0; ++tile; }
+      }
+    }
+
+    if (first_tile >= 0) {
+      // contributors = the CTAs before this one whose ranges touch the tile, in order
+      const long long x = (long long)first_tile * S_t;                // first stage of the tile
+      const int c_first = (int)(((x + 1) * G + W - 1) / W) - 1;
+      for (int o = tid; o < nout; o += kConsumerThreads) {
+        float v = first_sm[o];
+        for (int cc = c_first; cc < c; ++cc) {
+          unsigned int f;
+          do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(f) : "l"(a.sk_flags + cc) : "memory");
+          } while (f == 0u);
+          v += __ldcg(a.sk_partials + (size_t)cc * nout + o);
+        }
+        store_tile(first_tile, o, v);
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");
+      for (int cc = c_first + tid; cc < c; cc += kConsumerThreads) a.sk_flags[cc] = 0u;   // leave the workspace clean
     }
   }
 }
@@ -663,6 +916,8 @@ static cudaError_t encode_2d(CUtensorMap* map, CUtensorMapDataType dt, const voi
 
 using W4Kernel = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemvArgs);
 
+static int upg_of(int groupsize) { return groupsize == 32 ? 1 : (groupsize == 64 ? 2 : 4); }
+
 static cudaError_t launch_w4(W4Kernel kern, const GemvArgs& a, const W4Plan& p, int upg, cudaStream_t stream) {
   const int wk = 8 / p.wc, nt = 32 * p.wc, gpb = 4 / upg;
   alignas(64) CUtensorMap wmap, smap, zmap;
@@ -703,7 +958,6 @@ static cudaError_t launch_w4(W4Kernel kern, const GemvArgs& a, const W4Plan& p, 
   return cudaLaunchKernelEx(&cfg, kern, wmap, smap, zmap, a);
 }
 
-static int upg_of(int groupsize) { return groupsize == 32 ? 1 : (groupsize == 64 ? 2 : 4); }
 
 template <int MT>
 static W4Kernel pick_w4_kernel(int upg, int wc) {
@@ -731,6 +985,89 @@ cudaError_t launch_gemv_w4_mma(GemvArgs a, cudaStream_t stream) {
   if (!plan_w4(a, mt, upg, p)) return cudaErrorInvalidValue;
   W4Kernel k = mt == 1 ? pick_w4_kernel<1>(upg, p.wc) : pick_w4_kernel<2>(upg, p.wc);
   return k ? launch_w4(k, a, p, upg, stream) : cudaErrorInvalidValue;
+}
+
+// ---- persistent stream-K launch
+size_t gemv_w4_streamk_workspace_bytes(int M) {
+  const int sms = device_sm_count();
+  return (size_t)sms * ((size_t)M * 128 * sizeof(float)) + (((size_t)sms * sizeof(unsigned int) + 255) / 256) * 256 + 256;
+}
+
+
+static size_t streamk_smem(int upg, int mt, int m, int K, int ring) {
+  const int gpb = 4 / upg, wk = 2, nt = 128;
+  const size_t stage = ((size_t)(4 * wk * 16 * 128) + (size_t)wk * gpb * nt * 2 + (size_t)wk * gpb * (nt / 8) * 4 + 1023) / 1024 * 1024;
+  const int s_t = (K / 128 + wk - 1) / wk;
+  const int kpad = s_t * wk * 128;
+  return 1024 + (size_t)ring * stage + 128 + (size_t)m * (kpad + 32) * sizeof(__half)
+         + (size_t)(mt > 0 ? s_t * wk * gpb * 8 * mt : 0) * sizeof(float) + (size_t)(wk + 1) * m * nt * sizeof(float);
+}
+
+bool gemv_w4_streamk_applicable(const GemvArgs& a, int family) {
+  if (!gemv_w4_supported(a)) return false;
+  if (family == XBIT_GEMV_SIMT && a.M != 1) return false;
+  if (a.M > 16) return false;
+  const int mt = family == XBIT_GEMV_SIMT ? 0 : (a.M <= 8 ? 1 : 2);
+  const int tiles = (a.N + 127) / 128, s_t = (a.K / 128 + 1) / 2;
+  if ((long long)tiles * s_t < 2LL * device_sm_count()) return false;   // too little work to balance
+  return streamk_smem(upg_of(a.groupsize), mt, a.M, a.K, 3) <= kMaxDynSmem;
+}
+
+template <int MT>
+static W4Kernel pick_sk_kernel(int upg) {
+  if (upg == 1) return gemv_w4_streamk_kernel<MT, 1>;
+  if (upg == 2) return gemv_w4_streamk_kernel<MT, 2>;
+  return gemv_w4_streamk_kernel<MT, 4>;
+}
+
+cudaError_t launch_gemv_w4_streamk(GemvArgs a, int family, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  const int sms = device_sm_count();
+  const int upg = upg_of(a.groupsize), gpb = 4 / upg;
+  const int mt = family == XBIT_GEMV_SIMT ? 0 : (a.M <= 8 ? 1 : 2);
+  if (workspace_bytes < gemv_w4_streamk_workspace_bytes(a.M) || (reinterpret_cast<uintptr_t>(workspace) & 255u)) return cudaErrorInvalidValue;
+  const int tiles = (a.N + 127) / 128;
+  a.sk_stages_per_tile = (a.K / 128 + 1) / 2;
+  a.sk_total_stages = tiles * a.sk_stages_per_tile;
+  const int grid = a.sk_total_stages < sms ? a.sk_total_stages : sms;
+  // deepest ring that leaves room for a second (next) kernel on the SM, at least 3, at most kSkMaxRing
+  int ring = env_int("XBIT_GEMV_RING", 0);
+  if (ring < 2 || ring > kSkMaxRing) {
+    ring = kSkMaxRing;
+    while (ring > 3 && streamk_smem(upg, mt, a.M, a.K, ring) > 112 * 1024) --ring;
+  }
+  while (ring > 2 && streamk_smem(upg, mt, a.M, a.K, ring) > kMaxDynSmem) --ring;
+  const size_t smem = streamk_smem(upg, mt, a.M, a.K, ring);
+  if (smem > kMaxDynSmem) return cudaErrorInvalidValue;
+  a.sk_ring = ring;
+  a.sk_flags = reinterpret_cast<unsigned int*>(workspace);
+  a.sk_partials = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) + (((size_t)sms * sizeof(unsigned int) + 255) / 256) * 256);
+  a.splits = 1;
+  W4Kernel kern = mt == 0 ? pick_sk_kernel<0>(upg) : (mt == 1 ? pick_sk_kernel<1>(upg) : pick_sk_kernel<2>(upg));
+
+  const int wk = 2, nt = 128;
+  alignas(64) CUtensorMap wmap, smap, zmap;
+  cudaError_t e = encode_2d(&wmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, a.qweight, (uint64_t)a.N, (uint64_t)a.qrows,
+                            (uint64_t)a.N * 4, 32, (uint32_t)(wk * 16), CU_TENSOR_MAP_SWIZZLE_128B);
+  if (e != cudaSuccess) return e;
+  e = encode_2d(&smap, CU_TENSOR_MAP_DATA_TYPE_UINT16, a.scales, (uint64_t)a.N, (uint64_t)a.groups, (uint64_t)a.N * 2,
+                (uint32_t)nt, (uint32_t)(wk * gpb), CU_TENSOR_MAP_SWIZZLE_NONE);
+  if (e != cudaSuccess) return e;
+  e = encode_2d(&zmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, a.qzeros, (uint64_t)a.zwords, (uint64_t)a.groups,
+                (uint64_t)a.zwords * 4, (uint32_t)(nt / 8), (uint32_t)(wk * gpb), CU_TENSOR_MAP_SWIZZLE_NONE);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
+  if (e != cudaSuccess) return e;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid, 1, 1);
+  cfg.blockDim = dim3(kW4Threads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attrs[1];
+  attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attrs[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, wmap, smap, zmap, a);
 }
 
 cudaError_t launch_gemv_generic(GemvArgs a, cudaStream_t stream) {

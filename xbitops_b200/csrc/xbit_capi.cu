@@ -75,8 +75,12 @@ int xbit_dequant_f16(const int32_t* qweight, const void* scales_f16, const int32
   return XBIT_OK;
 }
 
-size_t xbit_gemv_workspace_bytes(int, int, int, int, int) {
-  return 0;  // split-K is reduced through cluster shared memory: no global scratch
+size_t xbit_gemv_workspace_bytes(int M, int, int, int bits, int) {
+  // Optional: with this much zero-initialised scratch the W4 path runs the persistent, perfectly
+  // balanced stream-K schedule (partial tiles + ready flags; left zeroed after every call).
+  // Without it (NULL / too small) split-K is reduced through cluster shared memory instead.
+  if (bits != 4) return 0;
+  return xbit::gemv_w4_streamk_workspace_bytes(M > 16 ? 16 : (M < 1 ? 1 : M));
 }
 
 static int pick_family(const xbit::GemvArgs& a) {
@@ -96,9 +100,25 @@ static int pick_family(const xbit::GemvArgs& a) {
   return XBIT_GEMV_MMA;
 }
 
+static bool use_streamk(const xbit::GemvArgs& g, int family, void* workspace, size_t workspace_bytes) {
+  // Measured on B200 (profiles/r01_v4_streamk_vs_cluster_sweep.log): with the mma.sync / SIMT consumers
+  // one CTA per SM (8 consumer warps) cannot keep the legacy HMMA pipe busy, so the balanced
+  // schedule is slower than two cluster-path CTAs per SM.  It stays opt-in (XBIT_GEMV_STREAMK=1)
+  // until the consumer side is light enough (tcgen05 path).
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* v = getenv("XBIT_GEMV_STREAMK");
+    enabled = (v && *v == '1') ? 1 : 0;
+  }
+  if (!enabled || !workspace || (reinterpret_cast<uintptr_t>(workspace) & 255u)) return false;
+  if (workspace_bytes < xbit::gemv_w4_streamk_workspace_bytes(g.M)) return false;
+  return xbit::gemv_w4_streamk_applicable(g, family);
+}
+
 static int gemv_impl(const void* a_f16, const int32_t* qweight, const void* scales_f16, const int32_t* qzeros,
                      void* const* outs, int world, int M, int K, int N, int bits, int groupsize, int add_zero_bias,
-                     int64_t out_row_stride, int64_t col_offset, int family_and_flags, xbit_stream_t stream) {
+                     int64_t out_row_stride, int64_t col_offset, int family_and_flags, void* workspace,
+                     size_t workspace_bytes, xbit_stream_t stream) {
   g_err[0] = 0;
   if (int rc = check_common(qweight, scales_f16, qzeros, K, N, bits, groupsize, add_zero_bias)) return rc;
   if (!a_f16) return fail(XBIT_EINVAL, "null activation pointer");
@@ -141,14 +161,16 @@ static int gemv_impl(const void* a_f16, const int32_t* qweight, const void* scal
     cudaError_t e;
     switch (family) {
       case XBIT_GEMV_SIMT:
-        if (!xbit::gemv_w4_supported(g)) return fail(XBIT_EINVAL, "SIMT family needs bits=4, groupsize in {32, 64, 128*j}, K%%128=0, N%%8=0, 16-byte aligned pointers");
+        if (!xbit::gemv_w4_supported(g)) return fail(XBIT_EINVAL, "SIMT family needs bits=4, groupsize in {32, 64, 128}, K%%128=0, N%%32=0, 16-byte aligned pointers");
         slab = 1; g.M = 1;   // one activation row per launch (the GEMV kernel proper)
-        e = xbit::launch_gemv_w4_simt(g, st);
+        if (use_streamk(g, XBIT_GEMV_SIMT, workspace, workspace_bytes)) e = xbit::launch_gemv_w4_streamk(g, XBIT_GEMV_SIMT, workspace, workspace_bytes, st);
+        else e = xbit::launch_gemv_w4_simt(g, st);
         break;
       case XBIT_GEMV_MMA:
-        if (!xbit::gemv_w4_supported(g)) return fail(XBIT_EINVAL, "MMA family needs bits=4, groupsize in {32, 64, 128*j}, K%%128=0, N%%8=0, 16-byte aligned pointers");
+        if (!xbit::gemv_w4_supported(g)) return fail(XBIT_EINVAL, "MMA family needs bits=4, groupsize in {32, 64, 128}, K%%128=0, N%%32=0, 16-byte aligned pointers");
         slab = g.M > 16 ? 16 : g.M; g.M = slab;
-        e = xbit::launch_gemv_w4_mma(g, st);
+        if (use_streamk(g, XBIT_GEMV_MMA, workspace, workspace_bytes)) e = xbit::launch_gemv_w4_streamk(g, XBIT_GEMV_MMA, workspace, workspace_bytes, st);
+        else e = xbit::launch_gemv_w4_mma(g, st);
         break;
       case XBIT_GEMV_GENERIC:
         slab = g.M;
@@ -167,10 +189,9 @@ static int gemv_impl(const void* a_f16, const int32_t* qweight, const void* scal
 int xbit_gemv_f16_ex(const void* a_f16, const int32_t* qweight, const void* scales_f16, const int32_t* qzeros,
                      void* out_f16, int M, int K, int N, int bits, int groupsize, int add_zero_bias,
                      int64_t out_row_stride, void* workspace, size_t workspace_bytes, int family, xbit_stream_t stream) {
-  (void)workspace; (void)workspace_bytes;
   void* outs[1] = {out_f16};
   return gemv_impl(a_f16, qweight, scales_f16, qzeros, outs, 1, M, K, N, bits, groupsize, add_zero_bias, out_row_stride, 0,
-                   family, stream);
+                   family, workspace, workspace_bytes, stream);
 }
 
 int xbit_gemv_f16(const void* a_f16, const int32_t* qweight, const void* scales_f16, const int32_t* qzeros, void* out_f16,
@@ -191,9 +212,8 @@ int xbit_gemv_f16_peers_ex(const void* a_f16, const int32_t* qweight, const void
                            void* const* peer_out_host_array, int world, int M, int K, int N_local, int bits, int groupsize,
                            int add_zero_bias, int64_t out_row_stride, int64_t col_offset, void* workspace,
                            size_t workspace_bytes, int family, xbit_stream_t stream) {
-  (void)workspace; (void)workspace_bytes;
   return gemv_impl(a_f16, qweight, scales_f16, qzeros, peer_out_host_array, world, M, K, N_local, bits, groupsize,
-                   add_zero_bias, out_row_stride, col_offset, family, stream);
+                   add_zero_bias, out_row_stride, col_offset, family, workspace, workspace_bytes, stream);
 }
 
 int xbit_gemv_f16_peers(const void* a_f16, const int32_t* qweight, const void* scales_f16, const int32_t* qzeros,

@@ -34,6 +34,12 @@ struct GemvArgs {
   int splits;               // K splits = cluster size along grid.y
   int units_per_split;      // 32-k units per split
   int chunk_units;          // activation staging chunk, in 32-k units
+  // persistent stream-K schedule (gemv_w4_streamk_kernel)
+  float* sk_partials;       // [grid][M * 128] fp32 partial tiles (workspace)
+  unsigned int* sk_flags;   // [grid] "partial ready" flags, zero outside a launch (workspace)
+  int sk_stages_per_tile;   // ceil((K/128) / 2)
+  int sk_total_stages;      // tiles * stages_per_tile
+  int sk_ring;              // pipeline depth (stages)
 };
 
 struct GemvPlan {
@@ -52,6 +58,10 @@ cudaError_t launch_dequant(const DqArgs& a, cudaStream_t stream, int* path_taken
 bool gemv_w4_supported(const GemvArgs& a);
 cudaError_t launch_gemv_w4_simt(GemvArgs a, cudaStream_t stream);   // M <= 4
 cudaError_t launch_gemv_w4_mma(GemvArgs a, cudaStream_t stream);    // M <= 16
+// persistent, balanced stream-K variant of the two (needs workspace); false = not applicable here
+bool gemv_w4_streamk_applicable(const GemvArgs& a, int family);
+size_t gemv_w4_streamk_workspace_bytes(int M);
+cudaError_t launch_gemv_w4_streamk(GemvArgs a, int family, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 // any bits / groupsize / M / N
 cudaError_t launch_gemv_generic(GemvArgs a, cudaStream_t stream);
 

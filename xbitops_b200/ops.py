@@ -52,6 +52,22 @@ def _stream_handle() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+_WORKSPACES: dict = {}
+
+
+def gemv_workspace(device: torch.device) -> torch.Tensor:
+    """Zero-initialised scratch for the persistent stream-K GEMV schedule (include/xbitops_b200.h:
+    xbit_gemv_workspace_bytes), one per (device, stream): calls on one stream are ordered, calls on
+    different streams must not share it.  Every call leaves it zeroed again."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), _stream_handle())
+    ws = _WORKSPACES.get(key)
+    if ws is None:
+        nbytes = capi.load().xbit_gemv_workspace_bytes(16, 0, 0, 4, 128)
+        ws = torch.zeros(max(nbytes, 256), dtype=torch.uint8, device=device)
+        _WORKSPACES[key] = ws
+    return ws
+
+
 def dequant(qweight, scales, qzeros, groupsize, bits, in_features, add_zero_bias):
     """-> Tensor[in_features, out_features] in scales.dtype (i.e. W^T of nn.Linear.weight)."""
     _check_quant_args(qweight, scales, qzeros, groupsize, bits, in_features)
@@ -96,9 +112,11 @@ def gemv(input_a, qweight, scales, qzeros, groupsize, bits, in_features, add_zer
                 raise RuntimeError("out must be a contiguous float16 tensor of the result shape")
             out16 = out
         if m > 0:
+            ws = gemv_workspace(qweight.device)
             capi.check(lib.xbit_gemv_f16_ex(input_a.data_ptr(), qweight.data_ptr(), f16_scale.data_ptr(),
                                             qzeros.data_ptr(), out16.data_ptr(), m, in_features, n, bits, groupsize,
-                                            int(add_zero_bias), n, None, 0, int(family), _stream_handle()))
+                                            int(add_zero_bias), n, ws.data_ptr(), ws.numel(), int(family),
+                                            _stream_handle()))
         if scales.dtype == torch.bfloat16:
             return out16.to(torch.bfloat16)
     return out16

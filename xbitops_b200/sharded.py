@@ -44,13 +44,15 @@ def _device_gemv_into(x, qweight, scales, qzeros, groupsize, bits, in_features, 
                       peer_ptrs=None, family=capi.GEMV_AUTO):
     """Local shard GEMV through the C ABI, written into out_full[:, col_offset:col_offset+n]
     (and, with peer_ptrs, into every rank's buffer)."""
+    from .ops import gemv_workspace
     lib = capi.load()
     m, n = x.shape[0], qweight.shape[1]
     ptrs = peer_ptrs if peer_ptrs is not None else [out_full.data_ptr()]
     arr = (ctypes.c_void_p * len(ptrs))(*ptrs)
+    ws = gemv_workspace(x.device)
     capi.check(lib.xbit_gemv_f16_peers_ex(x.data_ptr(), qweight.data_ptr(), scales.data_ptr(), qzeros.data_ptr(), arr,
                                           len(ptrs), m, in_features, n, bits, groupsize, int(add_zero_bias),
-                                          out_full.shape[1], col_offset, None, 0, int(family),
+                                          out_full.shape[1], col_offset, ws.data_ptr(), ws.numel(), int(family),
                                           torch.cuda.current_stream().cuda_stream))
 
 
