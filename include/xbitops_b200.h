@@ -63,7 +63,8 @@ enum {
   XBIT_GEMV_SIMT = 1,     /* W4 SIMT GEMV: LOP3 magic-number unpack, half2 FMA, one row per launch  */
   XBIT_GEMV_MMA = 2,      /* W4 tensor-core kernel: register-level unpack straight into mma.sync
                              m16n8k16 fragments, fp32 accumulation, M <= 16                          */
-  XBIT_GEMV_GENERIC = 3   /* any bits 2..8, any groupsize >= 16, any M: SIMT, fp32 accumulation      */
+  XBIT_GEMV_GENERIC = 3,  /* any bits 2..8, any groupsize >= 16, any M: SIMT, fp32 accumulation      */
+  XBIT_GEMV_TCGEN05 = 4   /* W4 g128, M <= 16: tcgen05.mma with the unpacked weights in TMEM          */
 };
 
 /* Flags OR-ed into the `family` argument of xbit_gemv_f16_ex / xbit_gemv_f16_peers_ex. */

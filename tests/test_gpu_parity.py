@@ -141,7 +141,8 @@ def test_dequant_bf16_scales_and_full_size_properties(dev):
 
 # ------------------------------------------------------------------ gemv
 
-FAMILIES = [(capi.GEMV_SIMT, (1, 3)), (capi.GEMV_MMA, (1, 2, 7, 8, 9, 16)), (capi.GEMV_GENERIC, (1, 5))]
+FAMILIES = [(capi.GEMV_SIMT, (1, 3)), (capi.GEMV_MMA, (1, 2, 7, 8, 9, 16)), (capi.GEMV_GENERIC, (1, 5)),
+            (capi.GEMV_TCGEN05, (1, 2, 5, 8, 11, 16))]
 
 
 @pytest.mark.parametrize("family,Ms", FAMILIES)
@@ -152,6 +153,8 @@ def test_gemv_w4_families_vs_truth(family, Ms, dev, c_oracle):
             w = c_oracle.dequant(qw, s, qz, g, 4, K, bias)
             tq, ts, tz = ti(qw, dev), t16(s, dev), ti(qz, dev)
             for M in Ms:
+                if family == capi.GEMV_TCGEN05 and g != 128:
+                    continue                     # the tcgen05 family covers groupsize 128 (others: mma.sync family)
                 y64 = a[:M].astype(np.float64) @ w.astype(np.float64)
                 got = X.gemv(t16(a[:M], dev), tq, ts, tz, g, 4, K, bias, family=family).cpu().numpy()
                 assert got.shape == (M, N)
@@ -167,6 +170,26 @@ def test_gemv_other_bit_widths(bits, dev, c_oracle):
         y64, _ = c_oracle.gemv(a, qw, s, qz, g, bits, K, 1)
         got = X.gemv(t16(a, dev), ti(qw, dev), t16(s, dev), ti(qz, dev), g, bits, K, 1).cpu().numpy()
         assert_gemv_close(got, y64, f"bits={bits} M={M} K={K} N={N} g={g}")
+
+
+def test_gemv_streamk_schedule(dev, c_oracle, monkeypatch):
+    """The opt-in persistent stream-K schedule (XBIT_GEMV_STREAMK=1 + workspace): same results, and the
+    workspace is left zeroed (flags cleared) so that consecutive calls can share it."""
+    from xbitops_b200 import ops
+    monkeypatch.setenv("XBIT_GEMV_STREAMK", "1")
+    for (K, N, M) in ((4096, 4096, 1), (11008, 4096, 1), (4096, 11008, 2), (8192, 1024, 5)):
+        qw, s, qz, a = synth.make_inputs(K, N, 4, 128, M=M, seed=K + N + M)
+        w = c_oracle.dequant(qw, s, qz, 128, 4, K, 1)
+        y64 = a.astype(np.float64) @ w.astype(np.float64)
+        tq, ts, tz, ta = ti(qw, dev), t16(s, dev), ti(qz, dev), t16(a, dev)
+        for fam in (capi.GEMV_MMA, capi.GEMV_SIMT):
+            y1 = X.gemv(ta, tq, ts, tz, 128, 4, K, 1, family=fam)
+            y2 = X.gemv(ta, tq, ts, tz, 128, 4, K, 1, family=fam)
+            assert torch.equal(y1, y2)                       # deterministic, workspace reusable
+            assert_gemv_close(y1.cpu().numpy(), y64, f"stream-K {K}x{N} M={M} family {fam}")
+    torch.cuda.synchronize()
+    ws = ops.gemv_workspace(dev)
+    assert int(ws[: 148 * 4].view(torch.int32).abs().sum()) == 0      # ready flags cleared
 
 
 def test_gemv_shapes_dtypes_and_large_m(dev, c_oracle):
@@ -221,7 +244,7 @@ def test_gemv_full_size_properties(K, N, dev):
     a = torch.randn((4, K), device=dev, generator=gen).to(torch.float16)
     w = X.dequant(qw, s, qz, g, bits, K, 1)
     truth = (a.double() @ w.double()).cpu().numpy()
-    for fam in (capi.GEMV_SIMT, capi.GEMV_MMA):
+    for fam in (capi.GEMV_SIMT, capi.GEMV_MMA, capi.GEMV_TCGEN05):
         y = X.gemv(a, qw, s, qz, g, bits, K, 1, family=fam)
         assert_gemv_close(y.cpu().numpy(), truth, f"{K}x{N} family {fam}", floor_of(fam))
         y1 = X.gemv(a[2:3], qw, s, qz, g, bits, K, 1, family=fam)

@@ -72,25 +72,31 @@ def main():
     for (K, N) in shapes:
         R, qw, sc, qz, a, out, nbytes = make(K, N)
         print(f"== {K}x{N} {nbytes/1e6:.1f} MB R={R} roofline {nbytes/PEAK/1e3:.2f} us")
-        for fam, name in ((capi.GEMV_SIMT, "simt"), (capi.GEMV_MMA, "mma")):
-            row = f"   {name}:"
-            for label, use_ws, ring in (("cluster", False, 0), ("sk-auto", True, 0), ("sk-r3", True, 3), ("sk-r4", True, 4),
-                                        ("sk-r5", True, 5), ("sk-r6", True, 6), ("sk-r8", True, 8)):
-                for flags, fl in ((0, ""), (capi.GEMV_FLAG_STATIC_WEIGHTS, "p")):
-                    if not flags and label not in ("cluster", "sk-auto"):
-                        continue
-                    os.environ["XBIT_GEMV_RING"] = str(ring)
-                    wsp, wsn = (WS.data_ptr(), WS.numel()) if use_ws else (None, 0)
+        os.environ["XBIT_GEMV_STREAMK"] = "0"
+        for fam, name, hyb in ((capi.GEMV_SIMT, "simt      ", 0), (capi.GEMV_MMA, "mma hyb=0 ", 0), (capi.GEMV_MMA, "mma hyb=2 ", 2)):
+            os.environ["XBIT_GEMV_HYBRID"] = str(hyb)
+            for wc in (0, 2, 4, 8):
+                row = f"   {name} wc={wc if wc else 'A'}:"
+                for splits in ((0,) if wc == 0 else (1, 2, 4, 8)):
+                    os.environ["XBIT_GEMV_SPLITS"] = str(splits)
+                    os.environ["XBIT_GEMV_WC"] = str(wc)
+                    flags = capi.GEMV_FLAG_STATIC_WEIGHTS
 
                     def fn(i):
                         j = i % R
                         rc = lib.xbit_gemv_f16_ex(a.data_ptr(), qw[j].data_ptr(), sc[j].data_ptr(), qz[j].data_ptr(),
-                                                  out[j].data_ptr(), 1, K, N, 4, 128, 0, N, wsp, wsn,
+                                                  out[j].data_ptr(), 1, K, N, 4, 128, 0, N, None, 0,
                                                   fam | flags, torch.cuda.current_stream().cuda_stream)
                         assert rc == 0, capi.last_error()
-                    us = time_graph(fn, R)
-                    row += f"  {label}{fl} {us:6.2f}us {nbytes/us/1e3/PEAK*100:3.0f}%"
-            print(row, flush=True)
+                    try:
+                        us = time_graph(fn, R)
+                        row += f"  s{splits if splits else 'A'} {us:6.2f}us {nbytes/us/1e3/PEAK*100:3.0f}%"
+                    except AssertionError:
+                        row += f"  s{splits} n/a"
+                print(row, flush=True)
+        os.environ["XBIT_GEMV_WC"] = "0"
+        os.environ["XBIT_GEMV_SPLITS"] = "0"
+        os.environ["XBIT_GEMV_HYBRID"] = "0"
         os.environ["XBIT_GEMV_RING"] = "0"
         os.environ["XBIT_GEMV_WC"] = "0"
         os.environ["XBIT_GEMV_SPLITS"] = "0"

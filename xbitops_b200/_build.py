@@ -68,7 +68,7 @@ def build_torch_ext(force: bool = False) -> Path:
     inc = [f"-I{p}" for p in ce.include_paths("cuda")] + [f"-I{sysconfig.get_paths()['include']}"]
     libdirs = [f"-L{p}" for p in ce.library_paths("cuda")]
     abi = int(torch._C._GLIBCXX_USE_CXX11_ABI)
-    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-w", f"-D_GLIBCXX_USE_CXX11_ABI={abi}",
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-w", "-fvisibility=hidden", "-Wl,-Bsymbolic", f"-D_GLIBCXX_USE_CXX11_ABI={abi}",
            "-DTORCH_EXTENSION_NAME=XbitOps", "-DTORCH_API_INCLUDE_EXTENSION_H", "-DUSE_CUDA",
            *inc, str(src), "-o", str(out), *libdirs, f"-L{PKG}", "-lxbitops_b200",
            "-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch_cuda", "-ltorch", "-ltorch_python", "-lcudart",

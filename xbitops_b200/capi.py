@@ -9,7 +9,7 @@ from pathlib import Path
 from . import _build
 
 XBIT_OK = 0
-GEMV_AUTO, GEMV_SIMT, GEMV_MMA, GEMV_GENERIC = 0, 1, 2, 3
+GEMV_AUTO, GEMV_SIMT, GEMV_MMA, GEMV_GENERIC, GEMV_TCGEN05 = 0, 1, 2, 3, 4
 GEMV_FLAG_STATIC_WEIGHTS = 0x100
 
 _vp, _i, _i64, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_size_t

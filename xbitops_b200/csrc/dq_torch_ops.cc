@@ -21,9 +21,7 @@
 #include <torch/extension.h>
 
 #include <cstdint>
-#include <map>
-#include <mutex>
-#include <utility>
+#include <cstdlib>
 #include <vector>
 
 #include "../../include/xbitops_b200.h"
@@ -61,22 +59,16 @@ void check_quant_args(const torch::Tensor& qweight, const torch::Tensor& scales,
 
 void raise_if(int rc) { TORCH_CHECK(rc == XBIT_OK, "xbitops_b200: ", xbit_last_error()); }
 
-// Zero-initialised scratch for the persistent stream-K GEMV schedule, one per (device, stream):
-// calls on one stream are ordered, calls on different streams must not share it.
-at::Tensor& gemv_workspace(const at::Device& device, cudaStream_t stream) {
-  static std::mutex mu;
-  static std::map<std::pair<int, void*>, at::Tensor> cache;
-  std::lock_guard<std::mutex> lock(mu);
-  auto key = std::make_pair((int)device.index(), (void*)stream);
-  auto it = cache.find(key);
-  if (it == cache.end()) {
-    const int64_t nbytes = (int64_t)xbit_gemv_workspace_bytes(16, 0, 0, 4, 128);
-    it = cache.emplace(key, at::zeros({nbytes < 256 ? 256 : nbytes}, at::TensorOptions().dtype(at::kByte).device(device))).first;
-  }
-  return it->second;
+// The persistent stream-K schedule is opt-in (XBIT_GEMV_STREAMK=1) and needs zero-initialised scratch
+// (include/xbitops_b200.h: xbit_gemv_workspace_bytes).  It is allocated per call here -- no static
+// tensors in the shim -- so only opted-in calls pay for the memset.
+bool streamk_requested() {
+  const char* v = std::getenv("XBIT_GEMV_STREAMK");
+  return v && *v == '1';
 }
 
-}  // namespace
+// (internal linkage: the reference extension exports functions of the same names, and both modules
+// can live in one process -- the parity tests load them side by side)
 
 torch::Tensor dequant_any_bit(const torch::Tensor& qweight, const torch::Tensor& scales, const torch::Tensor& qzeros,
                               int groupsize, int bits, int in_features, uint8_t add_zero_bias) {
@@ -114,15 +106,26 @@ torch::Tensor op_gemv(const torch::Tensor& input_a, const torch::Tensor& qweight
   at::Tensor output = at::empty(outputshape, f16_scale.options());
   auto stream = at::cuda::getCurrentCUDAStream().stream();
   if (mat_m > 0) {
-    at::Tensor& ws = gemv_workspace(qweight.device(), stream);
+    at::Tensor ws;
+    void* ws_ptr = nullptr;
+    size_t ws_bytes = 0;
+    if (streamk_requested()) {
+      ws_bytes = xbit_gemv_workspace_bytes((int)mat_m, in_features, (int)qweight.size(1), bits, groupsize);
+      if (ws_bytes > 0) {
+        ws = at::zeros({(int64_t)ws_bytes}, at::TensorOptions().dtype(at::kByte).device(qweight.device()));
+        ws_ptr = ws.data_ptr();
+      }
+    }
     raise_if(xbit_gemv_f16(input_a.data_ptr(), qweight.data_ptr<int32_t>(), f16_scale.data_ptr(),
                            qzeros.data_ptr<int32_t>(), output.data_ptr(), (int)mat_m, in_features, (int)qweight.size(1),
-                           bits, groupsize, add_zero_bias, qweight.size(1), ws.data_ptr(), (size_t)ws.numel(),
+                           bits, groupsize, add_zero_bias, qweight.size(1), ws_ptr, ws_bytes,
                            reinterpret_cast<xbit_stream_t>(stream)));
   }
   if (ori_dtype == torch::kBFloat16) output = output.to(torch::kBFloat16);
   return output;
 }
+
+}  // namespace
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("dequant", &dequant_any_bit,

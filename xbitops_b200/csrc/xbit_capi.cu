@@ -97,6 +97,7 @@ static int pick_family(const xbit::GemvArgs& a) {
   if (forced == XBIT_GEMV_SIMT && a.M == 1) return XBIT_GEMV_SIMT;
   if (forced == XBIT_GEMV_MMA) return XBIT_GEMV_MMA;
   if (forced == XBIT_GEMV_GENERIC) return XBIT_GEMV_GENERIC;
+  if (forced == XBIT_GEMV_TCGEN05 && xbit::gemv_w4_tc5_supported(a)) return XBIT_GEMV_TCGEN05;
   return XBIT_GEMV_MMA;
 }
 
@@ -105,11 +106,8 @@ static bool use_streamk(const xbit::GemvArgs& g, int family, void* workspace, si
   // one CTA per SM (8 consumer warps) cannot keep the legacy HMMA pipe busy, so the balanced
   // schedule is slower than two cluster-path CTAs per SM.  It stays opt-in (XBIT_GEMV_STREAMK=1)
   // until the consumer side is light enough (tcgen05 path).
-  static int enabled = -1;
-  if (enabled < 0) {
-    const char* v = getenv("XBIT_GEMV_STREAMK");
-    enabled = (v && *v == '1') ? 1 : 0;
-  }
+  const char* v = getenv("XBIT_GEMV_STREAMK");
+  const bool enabled = v && *v == '1';
   if (!enabled || !workspace || (reinterpret_cast<uintptr_t>(workspace) & 255u)) return false;
   if (workspace_bytes < xbit::gemv_w4_streamk_workspace_bytes(g.M)) return false;
   return xbit::gemv_w4_streamk_applicable(g, family);
@@ -171,6 +169,11 @@ static int gemv_impl(const void* a_f16, const int32_t* qweight, const void* scal
         slab = g.M > 16 ? 16 : g.M; g.M = slab;
         if (use_streamk(g, XBIT_GEMV_MMA, workspace, workspace_bytes)) e = xbit::launch_gemv_w4_streamk(g, XBIT_GEMV_MMA, workspace, workspace_bytes, st);
         else e = xbit::launch_gemv_w4_mma(g, st);
+        break;
+      case XBIT_GEMV_TCGEN05:
+        slab = g.M > 16 ? 16 : g.M; g.M = slab;
+        if (!xbit::gemv_w4_tc5_supported(g)) return fail(XBIT_EINVAL, "TCGEN05 family needs bits=4, groupsize=128, K%%128=0, N%%32=0, 16-byte aligned pointers");
+        e = xbit::launch_gemv_w4_tc5(g, st);
         break;
       case XBIT_GEMV_GENERIC:
         slab = g.M;

@@ -40,6 +40,8 @@ struct GemvArgs {
   int sk_stages_per_tile;   // ceil((K/128) / 2)
   int sk_total_stages;      // tiles * stages_per_tile
   int sk_ring;              // pipeline depth (stages)
+  int ring;                 // pipeline depth of gemv_w4_kernel (stages, <= 8)
+  int debug_skip;           // tools/sweep.py only: 1 = consumers skip the math (feed ceiling), results are garbage
 };
 
 struct GemvPlan {
@@ -62,6 +64,9 @@ cudaError_t launch_gemv_w4_mma(GemvArgs a, cudaStream_t stream);    // M <= 16
 bool gemv_w4_streamk_applicable(const GemvArgs& a, int family);
 size_t gemv_w4_streamk_workspace_bytes(int M);
 cudaError_t launch_gemv_w4_streamk(GemvArgs a, int family, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+// tcgen05 + TMEM path (bits 4, groupsize 128, M <= 8)
+bool gemv_w4_tc5_supported(const GemvArgs& a);
+cudaError_t launch_gemv_w4_tc5(GemvArgs a, cudaStream_t stream);
 // any bits / groupsize / M / N
 cudaError_t launch_gemv_generic(GemvArgs a, cudaStream_t stream);
 
