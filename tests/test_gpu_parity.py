@@ -235,7 +235,7 @@ def test_gemv_full_size_properties(K, N, dev):
     (b) column sharding: gemv on a column slice agrees with the slice of the truth (the K-split chosen
         by the planner depends on N, so the fp32 summation order may differ from the unsharded call);
     (c) row m of an M-row call == the M=1 call on that row (same family), bit for bit;
-    (d) linearity: gemv(2a) == 2*gemv(a) exactly (power-of-two scaling is exact in fp16/fp32)."""
+    (d) linearity: gemv(2a) == 2*gemv(a) (power-of-two scaling is exact in fp16/fp32 except for subnormals)."""
     g, bits = 128, 4
     gen = torch.Generator(device=dev).manual_seed(K + N)
     qw = torch.randint(-2**31, 2**31 - 1, (K // 8, N), dtype=torch.int32, device=dev, generator=gen)
@@ -249,8 +249,12 @@ def test_gemv_full_size_properties(K, N, dev):
         assert_gemv_close(y.cpu().numpy(), truth, f"{K}x{N} family {fam}", floor_of(fam))
         y1 = X.gemv(a[2:3], qw, s, qz, g, bits, K, 1, family=fam)
         assert torch.equal(y1[0], y[2])
-        y2 = X.gemv(a[:1] * 2, qw, s, qz, g, bits, K, 1, family=fam)
-        assert torch.equal(y2, X.gemv(a[:1], qw, s, qz, g, bits, K, 1, family=fam) * 2)
+        y2 = X.gemv(a[:1] * 2, qw, s, qz, g, bits, K, 1, family=fam).double()
+        yd = X.gemv(a[:1], qw, s, qz, g, bits, K, 1, family=fam).double() * 2
+        # exact up to fp16 subnormal effects in the staged activations (a/16 and the low half of
+        # sum_k a_k lose bits below 2^-24, which does not scale): at most one fp16 ulp, and rarely
+        assert float((y2 - yd).abs().max()) <= 2.0 ** -10 * float(yd.abs().max())
+        assert float((y2 != yd).double().mean()) <= 0.02
         half = N // 2
         ysl = X.gemv(a[:1], qw[:, half:].contiguous(), s[:, half:].contiguous(), qz[:, half // 8:].contiguous(),
                      g, bits, K, 1, family=fam)

@@ -363,6 +363,147 @@ __device__ __forceinline__ W4Lane<MT> make_w4_lane(int lane, int wc, int wk, int
   return L;
 }
 
+// ------------------------------------------------------------------------------------------------
+// v2 block math (tensor-core path of both W4 kernels).  Same exact-product idea as
+// w4_consume_block, with fewer instructions per 128-k block -- instruction issue is what bounds an
+// SM here (tools/pipe_probe2.cu):
+//   * unpack = 2 PRMT + 2 LOP3 per word instead of IMAD.HI + 4 LOP3: the byte pairs (k0 + 16 k1) are
+//     themselves exact fp16 subnormals, so  k0 a0 + k1 a1 = k0 (a0 - a1/16) + (k0 + 16 k1) (a1/16)
+//     and only the low nibble needs a mask; the activations are staged as (a0 - a1/16, a1/16);
+//   * the zero point rides on the tensor core: one extra m16n8k16 per column pair and scale group
+//     with A = -(z + bias) * 64 * 2^-24 in k slots 0, 1 and B = (hi, lo) halves of sum_k a_k / 64, so the
+//     group accumulator already holds 2^-24 * sum_k a_k (w_k - z) and the epilogue is one FFMA per
+//     accumulator; the 2^24 is applied once per segment.
+template <int MT>
+struct W4Lane2 {
+  uint32_t w_x0;            // byte offset of this lane's 16-byte chunk for units with u%2 == 0 (odd units: ^ kOddXor)
+  uint32_t s_off, z_off;    // byte offsets of this lane's 4 scales / 4 zero nibbles (16 bits) inside a stage
+  uint32_t zmul, zadd;      // (z * zmul + zadd) = half2 bits of -(z + bias) * 64 * 2^-24, twice, in lanes r == 0; 0 elsewhere
+  int brow_off[MT];         // activation row offset (halves) of this lane's batch column(s)
+  int zt_off[MT];           // byte offset of this lane's (hi, lo) group-sum word inside a group's table row
+};
+
+template <int MT, int UPG, int WC>
+__device__ __forceinline__ W4Lane2<MT> make_w4_lane2(int lane, int wc, int wk, int M, int pitch, int zero_bias) {
+  using Cfg = W4Cfg<UPG, WC>;
+  W4Lane2<MT> L;
+  const int r = lane & 3, c8 = lane >> 2;
+  const int lane_row = w4_lane_row<UPG>(lane);
+  const int col_local = 32 * wc + 4 * c8;
+  L.w_x0 = (uint32_t)(wc * Cfg::kBoxBytes + (wk * 16 + lane_row) * 128 + ((c8 ^ lane_row) * 16));
+  L.s_off = (uint32_t)(Cfg::kWeights + wk * Cfg::GPB * (Cfg::NT * 2) + col_local * 2);
+  L.z_off = (uint32_t)(Cfg::kWeights + Cfg::kScales + wk * Cfg::GPB * (Cfg::NT / 2) + (col_local >> 2) * 2);
+  L.zmul = r == 0 ? 0x00400040u : 0u;
+  L.zadd = r == 0 ? (uint32_t)zero_bias * 0x00400040u + 0x80008000u : 0u;
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+    const int m = min(c8 + 8 * mt, M - 1);
+    L.brow_off[mt] = m * pitch;
+    L.zt_off[mt] = (m * 4 + r) * 4;
+  }
+  return L;
+}
+
+// activations [8 consecutive k] -> (a0 - a1/16, a4 - a5/16) (a1/16, a5/16) (a2 - a3/16, a6 - a7/16) (a3/16, a7/16)
+__device__ __forceinline__ uint4 permute_act8_v2(uint4 v) {
+  const __half2 sixteenth = u2h2(0x2C002C00u);   // 0.0625
+  uint4 o;
+  const __half2 p15 = __hmul2(u2h2(prmt(v.x, v.z, 0x7632)), sixteenth);
+  const __half2 p37 = __hmul2(u2h2(prmt(v.y, v.w, 0x7632)), sixteenth);
+  o.x = h22u(__hsub2(u2h2(prmt(v.x, v.z, 0x5410)), p15));
+  o.y = h22u(p15);
+  o.z = h22u(__hsub2(u2h2(prmt(v.y, v.w, 0x5410)), p37));
+  o.w = h22u(p37);
+  return o;
+}
+
+__device__ __forceinline__ void unpack_w4_bytes(uint32_t w, uint32_t (&e)[4]) {
+  e[1] = prmt(w, 0u, 0x4240);      // bytes 0, 2 zero-extended into the two halves
+  e[3] = prmt(w, 0u, 0x4341);      // bytes 1, 3
+  e[0] = e[1] & 0x000F000Fu;
+  e[2] = e[3] & 0x000F000Fu;
+}
+
+// One 128-k block: `st` = stage base, `ablk` = this lane's activations of the block, `zt_blk` = the
+// block's group-sum table ([GPB][M][4] words).  tot accumulates 2^-24 * y.
+template <int MT, int UPG, int WC>
+__device__ __forceinline__ void w4_consume_block_v2(const unsigned char* __restrict__ st, const __half* __restrict__ ablk,
+                                                    const unsigned char* __restrict__ zt_blk, int zt_group_bytes,
+                                                    const W4Lane2<MT>& L, float (&tot)[2 * MT][4]) {
+  using Cfg = W4Cfg<UPG, WC>;
+  constexpr int NT = Cfg::NT, GPB = Cfg::GPB;
+  constexpr uint32_t kOddXor = (UPG == 1) ? 64u : 16u;
+  auto unit_row = [](int u) constexpr { return (UPG == 1) ? 4 * u : 8 * (u >> 1) + (u & 1); };
+#pragma unroll
+  for (int q = 0; q < GPB; ++q) {
+    const uint2 sraw = *reinterpret_cast<const uint2*>(st + L.s_off + q * (NT * 2));
+    const uint32_t zraw = *reinterpret_cast<const unsigned short*>(st + L.z_off + q * (NT / 2));
+    // all shared-memory loads of the group first: the unpack / MMA chains below then never wait on LDS latency
+    uint4 wv[UPG], bfrag[UPG][MT];
+#pragma unroll
+    for (int uu = 0; uu < UPG; ++uu) {
+      const int u = q * UPG + uu;
+      wv[uu] = *reinterpret_cast<const uint4*>(st + ((u & 1) ? (L.w_x0 ^ kOddXor) : L.w_x0) + unit_row(u) * 128);
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+        bfrag[uu][mt] = *reinterpret_cast<const uint4*>(ablk + L.brow_off[mt] + unit_row(u) * 8);
+    }
+    uint32_t bz[MT];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) bz[mt] = *reinterpret_cast<const uint32_t*>(zt_blk + q * zt_group_bytes + L.zt_off[mt]);
+
+    // (splitting the dependent HMMA chains over two accumulator sets was measured: no gain, the loop is issue bound)
+    float grp[2 * MT][4];
+#pragma unroll
+    for (int uu = 0; uu < UPG; ++uu) {
+      const uint32_t w4[4] = {wv[uu].x, wv[uu].y, wv[uu].z, wv[uu].w};
+#pragma unroll
+      for (int tt = 0; tt < 2; ++tt) {
+        uint32_t ea[4], eb[4];
+        unpack_w4_bytes(w4[2 * tt], ea);
+        unpack_w4_bytes(w4[2 * tt + 1], eb);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          if (uu == 0) mma_m16n8k16_zero(grp[tt * MT + mt], ea[0], eb[0], ea[1], eb[1], bfrag[uu][mt].x, bfrag[uu][mt].y);
+          else         mma_m16n8k16(grp[tt * MT + mt], ea[0], eb[0], ea[1], eb[1], bfrag[uu][mt].x, bfrag[uu][mt].y);
+          mma_m16n8k16(grp[tt * MT + mt], ea[2], eb[2], ea[3], eb[3], bfrag[uu][mt].z, bfrag[uu][mt].w);
+        }
+      }
+    }
+    {
+      // zero point last (its operands come out of the longest scalar chain): -(z + bias) * sum_k a_k on the tensor core
+      uint32_t za[4];
+      za[0] = (zraw & 0xFu) * L.zmul + L.zadd;
+      za[1] = ((zraw >> 4) & 0xFu) * L.zmul + L.zadd;
+      za[2] = ((zraw >> 8) & 0xFu) * L.zmul + L.zadd;
+      za[3] = (zraw >> 12) * L.zmul + L.zadd;
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int tt = 0; tt < 2; ++tt) mma_m16n8k16(grp[tt * MT + mt], za[2 * tt], za[2 * tt + 1], 0u, 0u, bz[mt], 0u);
+    }
+    // grp = 2^-24 * sum_k a_k (w_k - z).  accumulators 0,1 belong to column 2*tt (rows m = 2r, 2r+1), 2,3 to column 2*tt+1.
+    const float2 s01 = __half22float2(u2h2(sraw.x));
+    const float2 s23 = __half22float2(u2h2(sraw.y));
+    const float sf[4] = {s01.x, s01.y, s23.x, s23.y};
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int tt = 0; tt < 2; ++tt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) tot[tt * MT + mt][i] = fmaf(sf[2 * tt + (i >> 1)], grp[tt * MT + mt][i], tot[tt * MT + mt][i]);
+  }
+}
+
+// tools/trace.py: wall-clock stamps of one CTA's phases (debug only; a.trace is null in production)
+__device__ __forceinline__ void trace_stamp(const GemvArgs& a, int slot) {
+  if (a.trace) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    a.trace[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + slot] = t;
+  }
+}
+
 // MT = 0: SIMT kernel, M == 1.  MT = 1, 2: mma.sync kernel, M <= 8 * MT.
 // UPG = 32-k units per scale group inside a 128-k block: 4 (groupsize 128), 2 (64), 1 (32).
 //
@@ -380,12 +521,17 @@ __device__ __forceinline__ W4Lane<MT> make_w4_lane(int lane, int wc, int wk, int
 // "empty" mbarrier and the producer refills it.  No global address arithmetic, bounds checks or
 // register landing buffers in the consumer loop; bytes in flight are bounded by shared memory
 // (4 stages x 17 KiB per CTA), not by registers.
+__device__ __forceinline__ void trace_value(const GemvArgs& a, int slot, unsigned long long v) {
+  if (a.trace) a.trace[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + slot] = v;
+}
+
 template <int MT, int UPG, int WC, int HYB>
 __global__ void __launch_bounds__(kW4Threads, 2)
 gemv_w4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap smap,
                const __grid_constant__ CUtensorMap zmap, const GemvArgs a) {
   using Cfg = W4Cfg<UPG, WC>;
   constexpr bool kMma = MT > 0;
+  constexpr bool kV2 = kMma && HYB == 0;            // v2 block math (see w4_consume_block_v2)
   constexpr int MROWS = kMma ? 8 * MT : 1;
   constexpr int WK = Cfg::WK, NT = Cfg::NT, GPB = Cfg::GPB;
   // lane-independent part of the word-row index of unit u
@@ -409,13 +555,14 @@ gemv_w4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_base + kStages * Cfg::kStageBytes);
   uint64_t* empty_bar = full_bar + kMaxStages;
   __half* act_sm = reinterpret_cast<__half*>(stage_base + kStages * Cfg::kStageBytes + 128);        // [M][pitch]
-  float* asum_sm = reinterpret_cast<float*>(act_sm + (size_t)a.M * pitch);                         // [ngroups][MROWS] (mma only)
-  float* red_sm = asum_sm + (kMma ? ngroups * MROWS : 0);                                          // [WK][M][NT]
+  float* asum_sm = reinterpret_cast<float*>(act_sm + (size_t)a.M * pitch);                         // v1 mma: [ngroups][MROWS] floats; v2: [ngroups][M][4] words
+  float* red_sm = asum_sm + (kV2 ? ngroups * a.M * 4 : (kMma ? ngroups * MROWS : 0));              // [WK][M][NT]
   float* clus_sm = red_sm + WK * a.M * NT;          // [splits][M][NT], only the cluster leader's is used
 
   const bool clustered = a.splits > 1;
   if (clustered) asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");   // "I have started"
   if (tid == 0) {
+    trace_stamp(a, 0);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 8);
@@ -449,9 +596,15 @@ gemv_w4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
       asm volatile("prefetch.tensormap [%0];" ::"l"(&wmap) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&smap) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&zmap) : "memory");
+      trace_stamp(a, 1);
+      int s = 0, ph = 0;                            // slot and the parity of its fill count, kept without divisions
+      long long pwait = 0;
       for (int t = 0; t < ntiles; ++t) {
-        const int s = t % kStages;
-        if (t >= kStages) mbar_wait(&empty_bar[s], ((t / kStages) - 1) & 1);
+        if (t >= kStages) {
+          const long long c0 = a.trace ? clock64() : 0;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          if (a.trace) pwait += clock64() - c0;
+        }
         const int blk = b0 + t * WK;
         unsigned char* st = stage_base + s * Cfg::kStageBytes;
         mbar_arrive_expect_tx(&full_bar[s], Cfg::kTxBytes);
@@ -459,7 +612,9 @@ gemv_w4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
         for (int c = 0; c < WC; ++c) tma_load_2d(st + c * Cfg::kBoxBytes, &wmap, n_cta + 32 * c, blk * 16, &full_bar[s], policy);
         tma_load_2d(st + Cfg::kWeights, &smap, n_cta, blk * GPB, &full_bar[s], policy);
         tma_load_2d(st + Cfg::kWeights + Cfg::kScales, &zmap, n_cta >> 3, blk * GPB, &full_bar[s], policy);
+        if (++s == kStages) { s = 0; ph ^= 1; }
       }
+      trace_value(a, 10, (unsigned long long)pwait);
     }
     __syncwarp();
   } else {
@@ -467,6 +622,7 @@ gemv_w4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
     // stage the activations of this CTA's K range (the only data that depends on the previous
     // kernel); the mma path also needs sum_k a_k per scale group for the folded zero point
     griddep_wait();
+    if (tid == 0) trace_stamp(a, 2);
     {
       const int k0 = b0 * 128;
       const int vecs_per_row = (b1 - b0) * 16;      // 8-half vectors; a scale group = 4*UPG consecutive vectors
@@ -477,7 +633,7 @@ gemv_w4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
         uint4 val = make_uint4(0, 0, 0, 0);
         if (ok) {
           val = __ldg(reinterpret_cast<const uint4*>(a.a + (size_t)m * a.K + k0) + v);
-          *reinterpret_cast<uint4*>(act_sm + (size_t)m * pitch + v * 8) = permute_act8<kMma>(val);
+          *reinterpret_cast<uint4*>(act_sm + (size_t)m * pitch + v * 8) = kV2 ? permute_act8_v2(val) : permute_act8<kMma>(val);
         }
         if constexpr (kMma) {
           const float2 f0 = __half22float2(u2h2(val.x)), f1 = __half22float2(u2h2(val.y));
@@ -486,28 +642,61 @@ gemv_w4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
           // vecs_per_row is a multiple of 16, so a group's 4*UPG vectors sit in 4*UPG consecutive lanes
 #pragma unroll
           for (int o = 1; o < 4 * UPG; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-          if (ok && (lane & (4 * UPG - 1)) == 0) asum_sm[(v / (4 * UPG)) * MROWS + m] = sum;
+          if (ok && (lane & (4 * UPG - 1)) == 0) {
+            if constexpr (kV2) {
+              // sum_k a_k / 64 as an fp16 (hi, lo) pair in the r == 0 slot, zeros in the other three
+              const float q64 = sum * 0.015625f;
+              const __half hi = __float2half_rn(q64);
+              const __half lo = __float2half_rn(q64 - __half2float(hi));
+              *reinterpret_cast<uint4*>(reinterpret_cast<uint32_t*>(asum_sm) + ((size_t)(v / (4 * UPG)) * a.M + m) * 4) =
+                  make_uint4((uint32_t)__half_as_ushort(hi) | ((uint32_t)__half_as_ushort(lo) << 16), 0u, 0u, 0u);
+            } else {
+              asum_sm[(v / (4 * UPG)) * MROWS + m] = sum;
+            }
+          }
         }
       }
     }
     asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");
+    if (tid == 0) trace_stamp(a, 3);
 
     const W4Lane<MT> L = make_w4_lane<MT, UPG, WC>(lane, wc, wk, a.M, pitch, a.zero_bias);
+    const W4Lane2<kMma ? MT : 1> L2 = make_w4_lane2<kMma ? MT : 1, UPG, WC>(lane, wc, wk, a.M, pitch, a.zero_bias);
+    const int zt_group_bytes = a.M * 16;
+    (void)L; (void)L2; (void)zt_group_bytes;
     const __half* aptr = act_sm + wk * 128 + w4_lane_row<UPG>(lane) * 8;   // this lane's word-row; + t * WK * 128 per stage
 
+    int s = 0, ph = 0;
+    long long cwait = 0;
+    const long long loop0 = a.trace ? clock64() : 0;
     for (int t = 0; t < ntiles; ++t) {
-      const int s = t % kStages;
-      mbar_wait(&full_bar[s], (t / kStages) & 1);
+      const long long c0 = a.trace ? clock64() : 0;
+      mbar_wait(&full_bar[s], ph);
+      if (a.trace) cwait += clock64() - c0;
+      if (tid == 0 && t == 0) trace_stamp(a, 4);
       const unsigned char* st = stage_base + s * Cfg::kStageBytes;
       const int blk_local = t * WK + wk;                          // block index inside this CTA's range
       if (b0 + blk_local < b1) {                                  // warp-uniform (the last stage may be partly empty)
-        if (!a.debug_skip) w4_consume_block<MT, UPG, WC, HYB>(st, aptr + t * (WK * 128), asum_sm + blk_local * GPB * MROWS, L, tot, tot_s);
+        if (!a.debug_skip) {
+          if constexpr (kV2)
+            w4_consume_block_v2<MT, UPG, WC>(st, aptr + t * (WK * 128), reinterpret_cast<const unsigned char*>(asum_sm) + blk_local * GPB * zt_group_bytes,
+                                             zt_group_bytes, L2, tot);
+          else
+            w4_consume_block<MT, UPG, WC, HYB>(st, aptr + t * (WK * 128), asum_sm + blk_local * GPB * MROWS, L, tot, tot_s);
+        }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bar[s]);
+      if (++s == kStages) { s = 0; ph ^= 1; }
+    }
+    if (tid == 0 && a.trace) {
+      trace_value(a, 8, (unsigned long long)(clock64() - loop0));
+      trace_value(a, 9, (unsigned long long)cwait);
+      trace_value(a, 11, (unsigned long long)ntiles);
     }
   }
 
+  if (tid == 0) trace_stamp(a, 5);
   // ---- split-K reduction: r-lanes (shuffle, SIMT only) -> K-slices (smem) -> cluster (DSMEM)
   if (warp < 8) {
     if constexpr (kMma && HYB != 0 && MT == 1) {
@@ -537,7 +726,7 @@ gemv_w4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
           for (int i = 0; i < 4; ++i) {
             const int m = 8 * mt + 2 * r + (i & 1);
             const int col = 32 * wc + 4 * c8 + 2 * tt + (i >> 1);
-            if (m < a.M) red_sm[(wk * a.M + m) * NT + col] = tot[tt * MT + mt][i];
+            if (m < a.M) red_sm[(wk * a.M + m) * NT + col] = kV2 ? tot[tt * MT + mt][i] * 16777216.f : tot[tt * MT + mt][i];
           }
     }
   }
@@ -555,6 +744,7 @@ gemv_w4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
       leader[split * nout + o] = v;
     }
     cluster.sync();
+    if (tid == 0) trace_stamp(a, 6);
     if (split != 0) return;
   }
   for (int o = tid; o < nout; o += kW4Threads) {
@@ -573,30 +763,38 @@ gemv_w4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
       for (int p = 1; p < a.world; ++p) a.out[p][off] = h;   // fused all-gather: NVLink peer stores
     }
   }
+  if (tid == 0) trace_stamp(a, 7);
 }
 
 // ------------------------------------------------------------------------------------------------
-// Persistent stream-K variant: one CTA per SM, perfectly balanced.
+// Persistent stream-K schedule: one CTA per SM that owns HALF an SM, perfectly balanced.
 //
-// Work = (128-column tile, stage of 2 x 128 k) items in tile-major order, W = tiles * stages_per_tile.
-// CTA c of G owns the contiguous range [W*c/G, W*(c+1)/G): at most the tail of one tile, some whole
-// tiles and the head of another.  Whole tiles are written directly.  For a tile shared by several
-// CTAs the one holding its LAST stage is the finisher: the others publish their fp32 partial tile in
-// the workspace (release flag), the finisher adds them in CTA order (deterministic, no atomics) after
-// it has finished all of its own streaming, and clears the flags.  Every CTA is resident (G <= #SMs),
-// contributors never wait on anybody, so the wait cannot deadlock.
-// Same producer / consumer pipeline and per-block math as gemv_w4_kernel (WC = 4, WK = 2); the
-// whole activation vector is staged once per CTA.
+// Why (tools/pipe_probe2.cu, tools/trace.py; profiles/r01_v5_*): on B200 an SM sub-partition retires
+// about one LOP3 / IMAD / FFMA per 2 cycles whatever the mix (the ALU and FMA pipes do not overlap)
+// and an HMMA per ~4, so the consumer instruction stream -- not HBM, not occupancy -- bounds an SM at
+// 2 KB per ~2 x (instructions per block) cycles: 8 warps already reach it, 16 add nothing.  What is
+// left to win is (a) balance: any (tiles x splits) grid leaves part of the SMs with half the work of
+// the others, and (b) between back-to-back calls only what already sits in shared memory when the
+// previous kernel retires is free.  So:
+//   * one CTA per SM (8 consumer warps + 1 TMA producer warp) using at most half of the SM's shared
+//     memory and registers: the NEXT launch's CTA is resident on the same SM and
+//     (XBIT_GEMV_FLAG_STATIC_WEIGHTS) fills its whole ring while this one computes;
+//   * work = (128-column tile, stage of 2 x 128 k) units in tile-major order, W = tiles * S_t; CTA c
+//     of G owns the contiguous range [W*c/G, W*(c+1)/G): the tail of one tile, whole tiles, the head
+//     of another.  Whole tiles are written directly.  For a shared tile the CTA holding its LAST
+//     stage is the finisher: the others publish fp32 partial tiles in the workspace (release flag);
+//     the finisher adds them in CTA order (deterministic, no atomics) and clears the flags.  Waits
+//     only ever target lower-numbered CTAs, which never wait themselves;
+//   * the activation rows are staged per CTA for exactly the k ranges its units touch.
 constexpr int kSkMaxRing = 8;
 
-template <int MT, int UPG, int HYB>
-__global__ void __launch_bounds__(kW4Threads, 1)
+template <int MT, int UPG>
+__global__ void __launch_bounds__(kW4Threads, MT == 2 ? 1 : 2)
 gemv_w4_streamk_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap smap,
                        const __grid_constant__ CUtensorMap zmap, const GemvArgs a) {
+  static_assert(MT == 1 || MT == 2, "tensor-core path only");
   constexpr int WC = 4;
   using Cfg = W4Cfg<UPG, WC>;
-  constexpr bool kMma = MT > 0;
-  constexpr int MROWS = kMma ? 8 * MT : 1;
   constexpr int WK = Cfg::WK, NT = Cfg::NT, GPB = Cfg::GPB;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
 
@@ -607,19 +805,26 @@ gemv_w4_streamk_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_co
   const int s_lo = (int)(W * c / G), s_hi = (int)(W * (c + 1) / G);
   const int nst = s_hi - s_lo;
   const int ring = a.sk_ring;
-  const int kpad = S_t * WK * 128;                  // K rounded up to whole stages
-  const int pitch = kpad + 32;                      // halves per staged activation row (+64 B: bank spread)
-  const int ngroups = S_t * WK * GPB;
+  const int act_units = a.sk_act_units;             // 256-k activation chunks staged per CTA
+  const bool act_abs = a.sk_act_abs != 0;           // chunk index = stage inside the tile (whole K staged) / unit index
+  const int pitch = act_units * (WK * 128) + 8;     // halves per staged activation row (+16 B: batch rows spread over banks)
+  const int tile0 = s_lo / S_t, stg0 = s_lo - tile0 * S_t;
+  // Processing order.  If the range starts with the tail of a tile somebody else began (this CTA is that
+  // tile's finisher) and goes on, that tail is processed LAST: the head of the last tile (a contribution to
+  // a higher-numbered CTA) is then published early, and by the time this CTA needs the contributions
+  // to its own first tile they are usually there.  Units [rot, nst) first, then [0, rot).
+  const int rot = (stg0 > 0 && S_t - stg0 < nst) ? S_t - stg0 : 0;
 
   unsigned char* stage_base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_base + ring * Cfg::kStageBytes);
   uint64_t* empty_bar = full_bar + kSkMaxRing;
   __half* act_sm = reinterpret_cast<__half*>(stage_base + ring * Cfg::kStageBytes + 128);          // [M][pitch]
-  float* asum_sm = reinterpret_cast<float*>(act_sm + (size_t)a.M * pitch);                         // [ngroups][MROWS] (mma only)
-  float* red_sm = asum_sm + (kMma ? ngroups * MROWS : 0);                                          // [WK][M][NT]
+  uint32_t* zt_sm = reinterpret_cast<uint32_t*>(act_sm + (size_t)a.M * pitch);                     // [act_units*WK*GPB][M][4]: (hi, lo) of sum_k a_k / 64, then 3 zero words
+  float* red_sm = reinterpret_cast<float*>(zt_sm + (size_t)act_units * WK * GPB * a.M * 4);         // [WK][M][NT]
   float* first_sm = red_sm + WK * a.M * NT;                                                        // [M][NT] deferred first tile
 
   if (tid == 0) {
+    trace_stamp(a, 0);
     for (int s = 0; s < ring; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 8);
@@ -638,161 +843,197 @@ gemv_w4_streamk_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_co
       asm volatile("prefetch.tensormap [%0];" ::"l"(&wmap) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&smap) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&zmap) : "memory");
-      int tile = s_lo / S_t, stg = s_lo - tile * S_t;
-      for (int it = 0; it < nst; ++it) {
-        const int s = it % ring;
-        if (it >= ring) mbar_wait(&empty_bar[s], ((it / ring) - 1) & 1);
-        unsigned char* st = stage_base + s * Cfg::kStageBytes;
-        const int n0 = tile * NT, blk = stg * WK;
-        mbar_arrive_expect_tx(&full_bar[s], Cfg::kTxBytes);
+      trace_stamp(a, 1);
+      int s = 0, ph = 0, issued = 0;
+      for (int pass = 0; pass < 2; ++pass) {
+        int tile = (pass == 0 && rot > 0) ? tile0 + 1 : tile0;
+        int stg = (pass == 0 && rot > 0) ? 0 : stg0;
+        const int count = pass == 0 ? nst - rot : rot;
+        for (int j = 0; j < count; ++j, ++issued) {
+          if (issued >= ring) mbar_wait(&empty_bar[s], ph ^ 1);
+          unsigned char* st = stage_base + s * Cfg::kStageBytes;
+          const int n0 = tile * NT, blk = stg * WK;
+          mbar_arrive_expect_tx(&full_bar[s], Cfg::kTxBytes);
 #pragma unroll
-        for (int cc = 0; cc < WC; ++cc) tma_load_2d(st + cc * Cfg::kBoxBytes, &wmap, n0 + 32 * cc, blk * 16, &full_bar[s], policy);
-        tma_load_2d(st + Cfg::kWeights, &smap, n0, blk * GPB, &full_bar[s], policy);
-        tma_load_2d(st + Cfg::kWeights + Cfg::kScales, &zmap, n0 >> 3, blk * GPB, &full_bar[s], policy);
-        if (++stg == S_t) { stg = 0; ++tile; }
+          for (int cc = 0; cc < WC; ++cc) tma_load_2d(st + cc * Cfg::kBoxBytes, &wmap, n0 + 32 * cc, blk * 16, &full_bar[s], policy);
+          tma_load_2d(st + Cfg::kWeights, &smap, n0, blk * GPB, &full_bar[s], policy);
+          tma_load_2d(st + Cfg::kWeights + Cfg::kScales, &zmap, n0 >> 3, blk * GPB, &full_bar[s], policy);
+          if (++stg == S_t) { stg = 0; ++tile; }
+          if (++s == ring) { s = 0; ph ^= 1; }
+        }
       }
     }
     __syncwarp();
-  } else {
-    // =========================== consumers ===========================
-    const int r = lane & 3, c8 = lane >> 2;
-    const int wc = warp & (WC - 1), wk = (warp / WC) & (WK - 1);
-    griddep_wait();
-    {
-      // whole activation vector, zero padded to kpad; mma path: sum_k a_k per scale group
-      const int vecs_per_row = kpad / 8, vecs_valid = a.K / 8;
-      for (int base = 0; base < a.M * vecs_per_row; base += kConsumerThreads) {
-        const int idx = base + tid;
-        const bool ok = idx < a.M * vecs_per_row;
-        const int m = ok ? idx / vecs_per_row : 0, v = ok ? idx - m * vecs_per_row : 0;
-        uint4 val = make_uint4(0, 0, 0, 0);
-        if (ok) {
-          if (v < vecs_valid) val = __ldg(reinterpret_cast<const uint4*>(a.a + (size_t)m * a.K) + v);
-          *reinterpret_cast<uint4*>(act_sm + (size_t)m * pitch + v * 8) = permute_act8<kMma>(val);
+    return;
+  }
+
+  // =========================== consumers ===========================
+  const int r = lane & 3, c8 = lane >> 2;
+  const int wc = warp & (WC - 1), wk = (warp / WC) & (WK - 1);
+  const W4Lane2<MT> L = make_w4_lane2<MT, UPG, WC>(lane, wc, wk, a.M, pitch, a.zero_bias);
+  const __half* aptr = act_sm + wk * 128 + w4_lane_row<UPG>(lane) * 8;     // + chunk * 256 per stage
+  const int zt_group_bytes = a.M * 16;
+  const unsigned char* zt_w = reinterpret_cast<const unsigned char*>(zt_sm) + wk * GPB * zt_group_bytes;   // + chunk * WK * GPB groups
+  const int nout = a.M * NT;
+  float tot[2 * MT][4];
+#pragma unroll
+  for (int v = 0; v < 2 * MT; ++v)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) tot[v][i] = 0.f;
+
+  griddep_wait();                                   // the activations are the only data produced by the previous kernel
+  if (tid == 0) trace_stamp(a, 2);
+  {
+    // activation chunk ci covers k in [256 * stage(ci), +256), zero padded past K; next to it,
+    // per scale group and batch row, sum_k a_k / 64 as an fp16 (hi, lo) pair for the zero-point MMA.
+    // Four independent loads per thread are in flight at a time (the L2 round trip is what costs).
+    // No divisions in here: the loop is instruction bound, not latency bound (tools/trace.py).
+    const int nchunks = act_abs ? S_t : nst;
+    const int row_vecs = nchunks * 32;              // 8-half vectors per staged row (a multiple of the warp size)
+    const int vecs_valid = a.K >> 3;
+    const int stage_add = act_abs ? 0 : stg0;
+    constexpr int kBatch = 4;
+    for (int m = 0; m < a.M; ++m) {
+      const uint4* arow = reinterpret_cast<const uint4*>(a.a + (size_t)m * a.K);
+      __half* srow = act_sm + (size_t)m * pitch;
+      for (int v0 = 0; v0 < row_vecs; v0 += kBatch * kConsumerThreads) {
+        uint4 val[kBatch];
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b) {
+          const int v = v0 + b * kConsumerThreads + tid;        // vector inside the staged row
+          int stage = stage_add + (v >> 5);
+          if (stage >= S_t) stage -= S_t;                       // relative chunks wrap into the next tile at most once
+          const int gv = stage * 32 + (v & 31);                 // vector inside the activation row
+          val[b] = make_uint4(0, 0, 0, 0);
+          if (v < row_vecs && gv < vecs_valid && a.debug_skip != 2) val[b] = __ldg(arow + gv);
         }
-        if constexpr (kMma) {
-          const float2 f0 = __half22float2(u2h2(val.x)), f1 = __half22float2(u2h2(val.y));
-          const float2 f2 = __half22float2(u2h2(val.z)), f3 = __half22float2(u2h2(val.w));
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b) {
+          const int v = v0 + b * kConsumerThreads + tid;
+          const bool ok = v < row_vecs;                         // warp-uniform
+          if (!ok) continue;
+          *reinterpret_cast<uint4*>(srow + v * 8) = permute_act8_v2(val[b]);
+          const float2 f0 = __half22float2(u2h2(val[b].x)), f1 = __half22float2(u2h2(val[b].y));
+          const float2 f2 = __half22float2(u2h2(val[b].z)), f3 = __half22float2(u2h2(val[b].w));
           float sum = ((f0.x + f0.y) + (f1.x + f1.y)) + ((f2.x + f2.y) + (f3.x + f3.y));
 #pragma unroll
           for (int o = 1; o < 4 * UPG; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-          if (ok && (lane & (4 * UPG - 1)) == 0) asum_sm[(v / (4 * UPG)) * MROWS + m] = sum;
-        }
-      }
-    }
-    asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");
-
-    const W4Lane<MT> L = make_w4_lane<MT, UPG, WC>(lane, wc, wk, a.M, pitch, a.zero_bias);
-    const __half* aptr = act_sm + w4_lane_row<UPG>(lane) * 8;     // + blk * 128 per block (blk includes this warp's K-slice)
-    const int nout = a.M * NT;
-    float tot[kMma ? 2 * MT : 1][4];
-    float tot_s[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int v = 0; v < (kMma ? 2 * MT : 1); ++v)
-#pragma unroll
-      for (int i = 0; i < 4; ++i) tot[v][i] = 0.f;
-
-    int tile = nst > 0 ? s_lo / S_t : 0;
-    int stg = nst > 0 ? s_lo - tile * S_t : 0;
-    int seg_lo = stg;
-    int first_tile = -1;                            // tile whose fix-up is deferred to the end
-
-    auto store_tile = [&](int tl, int o, float v) {
-      const int m = o / NT, col = o - m * NT;
-      const int n = tl * NT + col;
-      if (n < a.N) {
-        const __half h = __float2half_rn(v);
-        const size_t off = (size_t)m * a.ldo + a.col_offset + n;
-        a.out[0][off] = h;
-        for (int p = 1; p < a.world; ++p) a.out[p][off] = h;   // fused all-gather: NVLink peer stores
-      }
-    };
-
-    for (int it = 0; it < nst; ++it) {
-      const int s = it % ring;
-      mbar_wait(&full_bar[s], (it / ring) & 1);
-      const unsigned char* st = stage_base + s * Cfg::kStageBytes;
-      const int blk = stg * WK + wk;                // block index inside the tile's K range (past K: all zeros)
-      w4_consume_block<MT, UPG, WC, HYB>(st, aptr + blk * 128, asum_sm + blk * GPB * MROWS, L, tot, tot_s);
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty_bar[s]);
-      ++stg;
-      if (stg == S_t || it == nst - 1) {
-        // ---- end of a segment [seg_lo, stg) of `tile`: K-slices -> one fp32 partial tile
-        if constexpr (kMma && HYB != 0 && MT == 1) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float v = tot_s[j];
-            v += __shfl_xor_sync(0xffffffffu, v, 1);
-            v += __shfl_xor_sync(0xffffffffu, v, 2);
-            if (r == 0) tot[j >> 1][(j & 1) * 2] += v;
-            tot_s[j] = 0.f;
+          if (ok && (lane & (4 * UPG - 1)) == 0) {
+            const float q64 = sum * 0.015625f;
+            const __half hi = __float2half_rn(q64);
+            const __half lo = __float2half_rn(q64 - __half2float(hi));
+            *reinterpret_cast<uint4*>(zt_sm + ((size_t)(v / (4 * UPG)) * a.M + m) * 4) =
+                make_uint4((uint32_t)__half_as_ushort(hi) | ((uint32_t)__half_as_ushort(lo) << 16), 0u, 0u, 0u);
           }
         }
-        if constexpr (!kMma) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float v = tot[0][j];
-            v += __shfl_xor_sync(0xffffffffu, v, 1);
-            v += __shfl_xor_sync(0xffffffffu, v, 2);
-            if (r == 0) red_sm[wk * NT + 32 * wc + 4 * c8 + j] = v;
-            tot[0][j] = 0.f;
-          }
-        } else {
-#pragma unroll
-          for (int tt = 0; tt < 2; ++tt)
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int m = 8 * mt + 2 * r + (i & 1);
-                const int col = 32 * wc + 4 * c8 + 2 * tt + (i >> 1);
-                if (m < a.M) red_sm[(wk * a.M + m) * NT + col] = tot[tt * MT + mt][i];
-                tot[tt * MT + mt][i] = 0.f;
-              }
-        }
-        asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");
-        const bool whole = (seg_lo == 0 && stg == S_t);
-        const bool is_end = (stg == S_t);
-        for (int o = tid; o < nout; o += kConsumerThreads) {
-          float v = 0.f;
-#pragma unroll
-          for (int w = 0; w < WK; ++w) v += red_sm[w * nout + o];
-          if (whole) store_tile(tile, o, v);
-          else if (is_end) first_sm[o] = v;                          // finisher: add the other CTAs' parts at the end
-          else a.sk_partials[(size_t)c * nout + o] = v;              // contributor: publish
-        }
-        if (!whole && is_end) first_tile = tile;
-        if (!whole && !is_end) {
-          __threadfence();
-          asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");
-          if (tid == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.sk_flags + c), "r"(1u) : "memory");
-        }
-        asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");   // red_sm is reused by the next segment
-        seg_lo = 0;
-        if (stg == S_t) { stg = 0; ++tile; }
       }
-    }
-
-    if (first_tile >= 0) {
-      // contributors = the CTAs before this one whose ranges touch the tile, in order
-      const long long x = (long long)first_tile * S_t;                // first stage of the tile
-      const int c_first = (int)(((x + 1) * G + W - 1) / W) - 1;
-      for (int o = tid; o < nout; o += kConsumerThreads) {
-        float v = first_sm[o];
-        for (int cc = c_first; cc < c; ++cc) {
-          unsigned int f;
-          do {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(f) : "l"(a.sk_flags + cc) : "memory");
-          } while (f == 0u);
-          v += __ldcg(a.sk_partials + (size_t)cc * nout + o);
-        }
-        store_tile(first_tile, o, v);
-      }
-      asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");
-      for (int cc = c_first + tid; cc < c; cc += kConsumerThreads) a.sk_flags[cc] = 0u;   // leave the workspace clean
     }
   }
+  asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");
+  if (tid == 0) trace_stamp(a, 3);
+
+  auto store_tile = [&](int tl, int o, float v) {
+    const int m = o / NT, col = o - m * NT;
+    const int n = tl * NT + col;
+    if (n < a.N) {
+      const __half h = __float2half_rn(v);
+      const size_t off = (size_t)m * a.ldo + a.col_offset + n;
+      a.out[0][off] = h;
+      for (int p = 1; p < a.world; ++p) a.out[p][off] = h;   // fused all-gather: NVLink peer stores
+    }
+  };
+
+  int s = 0, ph = 0;                                // ring slot of the next unit and the parity of the slot's fill count
+  int first_tile = -1;                              // tile whose fix-up is deferred to the end
+  const long long loop0 = a.trace ? clock64() : 0;
+
+  for (int pass = 0; pass < 2; ++pass) {
+    int it = pass == 0 ? rot : 0;                   // next unit (relative to s_lo)
+    const int pass_end = pass == 0 ? nst : rot;
+    int tile = (pass == 0 && rot > 0) ? tile0 + 1 : tile0;
+    while (it < pass_end) {
+      const int seg_begin = it;
+      const int stg_first = seg_begin == 0 ? stg0 : 0;
+      const int seg_len = min(S_t - stg_first, pass_end - seg_begin);
+      const int seg_end = seg_begin + seg_len;
+      const int ci_off = act_abs ? stg_first - seg_begin : 0;     // activation chunk of unit it = it + ci_off
+      for (; it < seg_end; ++it) {
+        mbar_wait(&full_bar[s], ph);
+        if (a.trace && tid == 0 && it == rot) trace_stamp(a, 4);
+        const unsigned char* st = stage_base + s * Cfg::kStageBytes;
+        const int ci = it + ci_off;
+        // blocks past K inside the last stage are all-zero weights and scales (TMA zero fill)
+        if (a.debug_skip != 1) w4_consume_block_v2<MT, UPG, WC>(st, aptr + ci * (WK * 128), zt_w + ci * (WK * GPB) * zt_group_bytes, zt_group_bytes, L, tot);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[s]);
+        if (++s == ring) { s = 0; ph ^= 1; }
+      }
+      // ---- end of the segment [stg_first, stg_first + seg_len) of `tile`: K-slices -> one fp32 partial tile
+#pragma unroll
+      for (int tt = 0; tt < 2; ++tt)
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int m = 8 * mt + 2 * r + (i & 1);
+            const int col = 32 * wc + 4 * c8 + 2 * tt + (i >> 1);
+            if (m < a.M) red_sm[(wk * a.M + m) * NT + col] = tot[tt * MT + mt][i] * 16777216.f;
+            tot[tt * MT + mt][i] = 0.f;
+          }
+      asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");
+      const bool is_end = (stg_first + seg_len == S_t);
+      const bool whole = (stg_first == 0 && is_end);
+      for (int o = tid; o < nout; o += kConsumerThreads) {
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < WK; ++w) v += red_sm[w * nout + o];
+        if (whole) store_tile(tile, o, v);
+        else if (is_end) first_sm[o] = v;                          // finisher: add the other CTAs' parts at the end
+        else a.sk_partials[(size_t)c * nout + o] = v;              // contributor: publish
+      }
+      if (!whole && is_end) first_tile = tile;
+      if (!whole && !is_end) {
+        __threadfence();
+        asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");
+        if (tid == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.sk_flags + c), "r"(1u) : "memory");
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");   // red_sm is reused by the next segment
+      ++tile;
+    }
+  }
+  if (tid == 0 && a.trace) {
+    trace_value(a, 8, (unsigned long long)(clock64() - loop0));
+    trace_value(a, 11, (unsigned long long)nst);
+    trace_stamp(a, 5);
+  }
+
+  if (first_tile >= 0) {
+    // contributors = the CTAs before this one whose ranges touch the tile, in order
+    const long long x = (long long)first_tile * S_t;                // first stage of the tile
+    const int c_first = (int)(((x + 1) * G + W - 1) / W) - 1;
+    if (c_first + tid < c) {
+      unsigned int f;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(f) : "l"(a.sk_flags + c_first + tid) : "memory");
+      } while (f == 0u);
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");
+    if (tid == 0) trace_stamp(a, 6);
+    for (int o = tid; o < nout; o += kConsumerThreads) {
+      float v = first_sm[o];
+      // four contributors at a time: independent loads, summed in CTA order
+      for (int cc = c_first; cc < c; cc += 4) {
+        float p[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) p[j] = (cc + j < c) ? __ldcg(a.sk_partials + (size_t)(cc + j) * nout + o) : 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v += p[j];
+      }
+      store_tile(first_tile, o, v);
+    }
+    if (c_first + tid < c) a.sk_flags[c_first + tid] = 0u;          // leave the workspace clean
+  }
+  if (tid == 0) trace_stamp(a, 7);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1253,7 +1494,7 @@ static size_t w4_smem_bytes(int upg, int wc, int mt, int m, int blocks_per_split
   const size_t stage = ((size_t)(wc * wk * 16 * 128) + (size_t)wk * gpb * nt * 2 + (size_t)wk * gpb * (nt / 8) * 4 + 1023) / 1024 * 1024;
   return 1024 /* alignment slack */ + (size_t)ring * stage + 128                     // ring + mbarriers
          + (size_t)m * (blocks_per_split * 128 + 8) * sizeof(__half)                  // act_sm
-         + (size_t)(mt > 0 ? blocks_per_split * gpb * 8 * mt : 0) * sizeof(float)     // asum_sm
+         + (size_t)(mt > 0 ? blocks_per_split * gpb * (m * 4 > 8 * mt ? m * 4 : 8 * mt) : 0) * sizeof(float)   // asum_sm (v1) / group-sum table (v2)
          + (size_t)wk * m * nt * sizeof(float)                                        // red_sm
          + (size_t)(splits > 1 ? splits : 0) * m * nt * sizeof(float);                // clus_sm
 }
@@ -1286,6 +1527,11 @@ static bool plan_w4(GemvArgs& a, int mt, int upg, W4Plan& p) {
   if (ring < 2 || ring > kMaxStages) ring = 4;
   a.ring = ring;
   a.debug_skip = env_int("XBIT_GEMV_DEBUG_SKIP", 0);
+  a.trace = nullptr;
+  if (const char* tp = getenv("XBIT_GEMV_TRACE")) {   // tools/trace.py: device buffer of [launch][1024 CTAs][8] stamps
+    static int launches = 0;
+    a.trace = reinterpret_cast<unsigned long long*>(strtoull(tp, nullptr, 0)) + (size_t)(launches++ % 64) * 16384;
+  }
   auto smem_of = [&](int sp) { return w4_smem_bytes(upg, wc, mt, a.M, (nblocks + sp - 1) / sp, sp, ring); };
   while (splits < 8 && smem_of(splits) > kMaxDynSmem) splits *= 2;
   if (smem_of(splits) > kMaxDynSmem) return false;   // K too long for the staged-activation design at this M
@@ -1411,59 +1657,82 @@ size_t gemv_w4_streamk_workspace_bytes(int M) {
   return (size_t)sms * ((size_t)M * 128 * sizeof(float)) + (((size_t)sms * sizeof(unsigned int) + 255) / 256) * 256 + 256;
 }
 
+struct SkPlan {
+  int grid, ring, act_units, act_abs, stages_per_tile;
+  long long total;
+  size_t smem;
+};
 
-static size_t streamk_smem(int upg, int mt, int m, int K, int ring) {
+static size_t streamk_smem(int upg, int mt, int m, int act_units, int ring) {
   const int gpb = 4 / upg, wk = 2, nt = 128;
+  (void)mt;
   const size_t stage = ((size_t)(4 * wk * 16 * 128) + (size_t)wk * gpb * nt * 2 + (size_t)wk * gpb * (nt / 8) * 4 + 1023) / 1024 * 1024;
-  const int s_t = (K / 128 + wk - 1) / wk;
-  const int kpad = s_t * wk * 128;
-  return 1024 + (size_t)ring * stage + 128 + (size_t)m * (kpad + 32) * sizeof(__half)
-         + (size_t)(mt > 0 ? s_t * wk * gpb * 8 * mt : 0) * sizeof(float) + (size_t)(wk + 1) * m * nt * sizeof(float);
+  return 1024 + (size_t)ring * stage + 128 + (size_t)m * (act_units * 256 + 8) * sizeof(__half)
+         + (size_t)act_units * wk * gpb * m * 16 + (size_t)(wk + 1) * m * nt * sizeof(float);
+}
+
+static bool plan_streamk(const GemvArgs& a, int mt, SkPlan& p) {
+  const int sms = device_sm_count();
+  const int upg = upg_of(a.groupsize);
+  const int tiles = (a.N + 127) / 128;
+  p.stages_per_tile = (a.K / 128 + 1) / 2;
+  p.total = (long long)tiles * p.stages_per_tile;
+  p.grid = p.total < sms ? (int)p.total : sms;
+  const int per_cta = (int)((p.total + p.grid - 1) / p.grid);
+  p.act_abs = per_cta >= p.stages_per_tile;
+  p.act_units = p.act_abs ? p.stages_per_tile : per_cta;
+  // Half an SM (so that the next launch is resident while this one computes) when that still
+  // leaves a ring of 4 stages; otherwise whatever fits, up to 6
+  const size_t half = 113 * 1024;
+  int ring = env_int("XBIT_GEMV_RING", 0);
+  if (ring < 2 || ring > kSkMaxRing) {
+    ring = 6;
+    while (ring > 4 && streamk_smem(upg, mt, a.M, p.act_units, ring) > half) --ring;
+    while (ring > 2 && streamk_smem(upg, mt, a.M, p.act_units, ring) > kMaxDynSmem) --ring;
+  }
+  p.ring = ring;
+  p.smem = streamk_smem(upg, mt, a.M, p.act_units, ring);
+  return p.smem <= kMaxDynSmem;
 }
 
 bool gemv_w4_streamk_applicable(const GemvArgs& a, int family) {
   if (!gemv_w4_supported(a)) return false;
-  if (family == XBIT_GEMV_SIMT && a.M != 1) return false;
-  if (a.M > 16) return false;
-  const int mt = family == XBIT_GEMV_SIMT ? 0 : (a.M <= 8 ? 1 : 2);
-  const int tiles = (a.N + 127) / 128, s_t = (a.K / 128 + 1) / 2;
-  if ((long long)tiles * s_t < 2LL * device_sm_count()) return false;   // too little work to balance
-  return streamk_smem(upg_of(a.groupsize), mt, a.M, a.K, 3) <= kMaxDynSmem;
+  if (family != XBIT_GEMV_MMA || a.M > 16) return false;      // tensor-core block math only
+  const int mt = a.M <= 8 ? 1 : 2;
+  SkPlan p;
+  return plan_streamk(a, mt, p);
 }
 
-template <int MT, int HYB>
+template <int MT>
 static W4Kernel pick_sk_kernel(int upg) {
-  if (upg == 1) return gemv_w4_streamk_kernel<MT, 1, HYB>;
-  if (upg == 2) return gemv_w4_streamk_kernel<MT, 2, HYB>;
-  return gemv_w4_streamk_kernel<MT, 4, HYB>;
+  if (upg == 1) return gemv_w4_streamk_kernel<MT, 1>;
+  if (upg == 2) return gemv_w4_streamk_kernel<MT, 2>;
+  return gemv_w4_streamk_kernel<MT, 4>;
 }
 
 cudaError_t launch_gemv_w4_streamk(GemvArgs a, int family, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   const int sms = device_sm_count();
   const int upg = upg_of(a.groupsize), gpb = 4 / upg;
-  const int mt = family == XBIT_GEMV_SIMT ? 0 : (a.M <= 8 ? 1 : 2);
+  if (family != XBIT_GEMV_MMA) return cudaErrorInvalidValue;
+  const int mt = a.M <= 8 ? 1 : 2;
   if (workspace_bytes < gemv_w4_streamk_workspace_bytes(a.M) || (reinterpret_cast<uintptr_t>(workspace) & 255u)) return cudaErrorInvalidValue;
-  const int tiles = (a.N + 127) / 128;
-  a.sk_stages_per_tile = (a.K / 128 + 1) / 2;
-  a.sk_total_stages = tiles * a.sk_stages_per_tile;
-  const int grid = a.sk_total_stages < sms ? a.sk_total_stages : sms;
-  // deepest ring that leaves room for a second (next) kernel on the SM, at least 3, at most kSkMaxRing
-  int ring = env_int("XBIT_GEMV_RING", 0);
-  if (ring < 2 || ring > kSkMaxRing) {
-    ring = kSkMaxRing;
-    while (ring > 3 && streamk_smem(upg, mt, a.M, a.K, ring) > 112 * 1024) --ring;
-  }
-  while (ring > 2 && streamk_smem(upg, mt, a.M, a.K, ring) > kMaxDynSmem) --ring;
-  const size_t smem = streamk_smem(upg, mt, a.M, a.K, ring);
-  if (smem > kMaxDynSmem) return cudaErrorInvalidValue;
-  a.sk_ring = ring;
+  SkPlan p;
+  if (!plan_streamk(a, mt, p)) return cudaErrorInvalidValue;
+  a.sk_stages_per_tile = p.stages_per_tile;
+  a.sk_total_stages = (int)p.total;
+  a.sk_ring = p.ring;
+  a.sk_act_units = p.act_units;
+  a.sk_act_abs = p.act_abs;
   a.sk_flags = reinterpret_cast<unsigned int*>(workspace);
   a.sk_partials = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) + (((size_t)sms * sizeof(unsigned int) + 255) / 256) * 256);
   a.splits = 1;
-  const int hyb = a.M == 1 ? env_int("XBIT_GEMV_HYBRID", 0) : 0;
-  W4Kernel kern = mt == 0 ? pick_sk_kernel<0, 0>(upg)
-                          : (mt == 1 ? (hyb == 2 ? pick_sk_kernel<1, 2>(upg) : (hyb == 1 ? pick_sk_kernel<1, 1>(upg) : pick_sk_kernel<1, 0>(upg)))
-                                     : pick_sk_kernel<2, 0>(upg));
+  a.debug_skip = env_int("XBIT_GEMV_DEBUG_SKIP", 0);
+  a.trace = nullptr;
+  if (const char* tp = getenv("XBIT_GEMV_TRACE")) {
+    static int launches = 0;
+    a.trace = reinterpret_cast<unsigned long long*>(strtoull(tp, nullptr, 0)) + (size_t)(launches++ % 64) * 16384;
+  }
+  W4Kernel kern = mt == 1 ? pick_sk_kernel<1>(upg) : pick_sk_kernel<2>(upg);
 
   const int wk = 2, nt = 128;
   alignas(64) CUtensorMap wmap, smap, zmap;
@@ -1479,9 +1748,9 @@ cudaError_t launch_gemv_w4_streamk(GemvArgs a, int family, void* workspace, size
   e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)grid, 1, 1);
+  cfg.gridDim = dim3((unsigned)p.grid, 1, 1);
   cfg.blockDim = dim3(kW4Threads, 1, 1);
-  cfg.dynamicSmemBytes = smem;
+  cfg.dynamicSmemBytes = p.smem;
   cfg.stream = stream;
   cudaLaunchAttribute attrs[1];
   attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;

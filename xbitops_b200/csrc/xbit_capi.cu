@@ -125,7 +125,7 @@ static int gemv_impl(const void* a_f16, const int32_t* qweight, const void* scal
   if (col_offset < 0 || out_row_stride < col_offset + N)
     return fail(XBIT_EINVAL, "out_row_stride (%lld) must be >= col_offset + N (%lld)", (long long)out_row_stride,
                 (long long)(col_offset + N));
-  xbit::GemvArgs g;
+  xbit::GemvArgs g = {};
   memset(&g, 0, sizeof(g));
   for (int p = 0; p < world; ++p) {
     if (!outs || !outs[p]) return fail(XBIT_EINVAL, "null output pointer (rank %d)", p);
@@ -205,7 +205,7 @@ int xbit_gemv_f16(const void* a_f16, const int32_t* qweight, const void* scales_
 }
 
 int xbit_gemv_pick_family(int M, int K, int N, int bits, int groupsize) {
-  xbit::GemvArgs g;
+  xbit::GemvArgs g = {};
   memset(&g, 0, sizeof(g));
   g.M = M > 16 ? 16 : M; g.K = K; g.N = N; g.bits = bits; g.groupsize = groupsize;
   return pick_family(g);

@@ -40,7 +40,10 @@ struct GemvArgs {
   int sk_stages_per_tile;   // ceil((K/128) / 2)
   int sk_total_stages;      // tiles * stages_per_tile
   int sk_ring;              // pipeline depth (stages)
+  int sk_act_units;         // 256-k activation chunks staged per CTA
+  int sk_act_abs;           // 1: chunk index = stage inside the tile (whole K staged); 0: the CTA's own unit index
   int ring;                 // pipeline depth of gemv_w4_kernel (stages, <= 8)
+  unsigned long long* trace;   // tools/trace.py only: per-CTA globaltimer stamps [cta][8], null in production
   int debug_skip;           // tools/sweep.py only: 1 = consumers skip the math (feed ceiling), results are garbage
 };
 
