@@ -526,7 +526,7 @@ __device__ __forceinline__ void trace_value(const GemvArgs& a, int slot, unsigne
 }
 
 template <int MT, int UPG, int WC, int HYB>
-__global__ void __launch_bounds__(kW4Threads, 2)
+__global__ void __launch_bounds__(kW4Threads, 2)   // (a 72-register cap for a third CTA per SM was measured: the loop grows by 20 %, slower everywhere)
 gemv_w4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap smap,
                const __grid_constant__ CUtensorMap zmap, const GemvArgs a) {
   using Cfg = W4Cfg<UPG, WC>;
@@ -598,13 +598,8 @@ gemv_w4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
       asm volatile("prefetch.tensormap [%0];" ::"l"(&zmap) : "memory");
       trace_stamp(a, 1);
       int s = 0, ph = 0;                            // slot and the parity of its fill count, kept without divisions
-      long long pwait = 0;
       for (int t = 0; t < ntiles; ++t) {
-        if (t >= kStages) {
-          const long long c0 = a.trace ? clock64() : 0;
-          mbar_wait(&empty_bar[s], ph ^ 1);
-          if (a.trace) pwait += clock64() - c0;
-        }
+        if (t >= kStages) mbar_wait(&empty_bar[s], ph ^ 1);
         const int blk = b0 + t * WK;
         unsigned char* st = stage_base + s * Cfg::kStageBytes;
         mbar_arrive_expect_tx(&full_bar[s], Cfg::kTxBytes);
@@ -614,7 +609,6 @@ gemv_w4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
         tma_load_2d(st + Cfg::kWeights + Cfg::kScales, &zmap, n_cta >> 3, blk * GPB, &full_bar[s], policy);
         if (++s == kStages) { s = 0; ph ^= 1; }
       }
-      trace_value(a, 10, (unsigned long long)pwait);
     }
     __syncwarp();
   } else {
@@ -624,34 +618,36 @@ gemv_w4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
     griddep_wait();
     if (tid == 0) trace_stamp(a, 2);
     {
-      const int k0 = b0 * 128;
-      const int vecs_per_row = (b1 - b0) * 16;      // 8-half vectors; a scale group = 4*UPG consecutive vectors
-      for (int base = 0; base < a.M * vecs_per_row; base += kConsumerThreads) {
-        const int idx = base + tid;
-        const bool ok = idx < a.M * vecs_per_row;
-        const int m = ok ? idx / vecs_per_row : 0, v = ok ? idx - m * vecs_per_row : 0;
-        uint4 val = make_uint4(0, 0, 0, 0);
-        if (ok) {
-          val = __ldg(reinterpret_cast<const uint4*>(a.a + (size_t)m * a.K + k0) + v);
-          *reinterpret_cast<uint4*>(act_sm + (size_t)m * pitch + v * 8) = kV2 ? permute_act8_v2(val) : permute_act8<kMma>(val);
-        }
-        if constexpr (kMma) {
-          const float2 f0 = __half22float2(u2h2(val.x)), f1 = __half22float2(u2h2(val.y));
-          const float2 f2 = __half22float2(u2h2(val.z)), f3 = __half22float2(u2h2(val.w));
-          float sum = ((f0.x + f0.y) + (f1.x + f1.y)) + ((f2.x + f2.y) + (f3.x + f3.y));
-          // vecs_per_row is a multiple of 16, so a group's 4*UPG vectors sit in 4*UPG consecutive lanes
+      // no divisions in here: the loop is instruction bound, not latency bound (tools/trace.py)
+      const int vecs_per_row = (b1 - b0) * 16;      // 8-half vectors (a multiple of 16); a scale group = 4*UPG consecutive vectors
+      for (int m = 0; m < a.M; ++m) {
+        const uint4* arow = reinterpret_cast<const uint4*>(a.a + (size_t)m * a.K + b0 * 128);
+        __half* srow = act_sm + (size_t)m * pitch;
+        for (int v = tid; v - lane < vecs_per_row; v += kConsumerThreads) {      // warp-uniform trip count (shuffles below)
+          const bool ok = v < vecs_per_row;
+          uint4 val = make_uint4(0, 0, 0, 0);
+          if (ok) {
+            val = __ldg(arow + v);
+            *reinterpret_cast<uint4*>(srow + v * 8) = kV2 ? permute_act8_v2(val) : permute_act8<kMma>(val);
+          }
+          if constexpr (kMma) {
+            const float2 f0 = __half22float2(u2h2(val.x)), f1 = __half22float2(u2h2(val.y));
+            const float2 f2 = __half22float2(u2h2(val.z)), f3 = __half22float2(u2h2(val.w));
+            float sum = ((f0.x + f0.y) + (f1.x + f1.y)) + ((f2.x + f2.y) + (f3.x + f3.y));
+            // a group's 4*UPG vectors sit in 4*UPG consecutive lanes
 #pragma unroll
-          for (int o = 1; o < 4 * UPG; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-          if (ok && (lane & (4 * UPG - 1)) == 0) {
-            if constexpr (kV2) {
-              // sum_k a_k / 64 as an fp16 (hi, lo) pair in the r == 0 slot, zeros in the other three
-              const float q64 = sum * 0.015625f;
-              const __half hi = __float2half_rn(q64);
-              const __half lo = __float2half_rn(q64 - __half2float(hi));
-              *reinterpret_cast<uint4*>(reinterpret_cast<uint32_t*>(asum_sm) + ((size_t)(v / (4 * UPG)) * a.M + m) * 4) =
-                  make_uint4((uint32_t)__half_as_ushort(hi) | ((uint32_t)__half_as_ushort(lo) << 16), 0u, 0u, 0u);
-            } else {
-              asum_sm[(v / (4 * UPG)) * MROWS + m] = sum;
+            for (int o = 1; o < 4 * UPG; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            if (ok && (lane & (4 * UPG - 1)) == 0) {
+              if constexpr (kV2) {
+                // sum_k a_k / 64 as an fp16 (hi, lo) pair in the r == 0 slot, zeros in the other three
+                const float q64 = sum * 0.015625f;
+                const __half hi = __float2half_rn(q64);
+                const __half lo = __float2half_rn(q64 - __half2float(hi));
+                *reinterpret_cast<uint4*>(reinterpret_cast<uint32_t*>(asum_sm) + ((size_t)(v / (4 * UPG)) * a.M + m) * 4) =
+                    make_uint4((uint32_t)__half_as_ushort(hi) | ((uint32_t)__half_as_ushort(lo) << 16), 0u, 0u, 0u);
+              } else {
+                asum_sm[(v / (4 * UPG)) * MROWS + m] = sum;
+              }
             }
           }
         }
@@ -667,13 +663,10 @@ gemv_w4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
     const __half* aptr = act_sm + wk * 128 + w4_lane_row<UPG>(lane) * 8;   // this lane's word-row; + t * WK * 128 per stage
 
     int s = 0, ph = 0;
-    long long cwait = 0;
     const long long loop0 = a.trace ? clock64() : 0;
     for (int t = 0; t < ntiles; ++t) {
-      const long long c0 = a.trace ? clock64() : 0;
       mbar_wait(&full_bar[s], ph);
-      if (a.trace) cwait += clock64() - c0;
-      if (tid == 0 && t == 0) trace_stamp(a, 4);
+      if (a.trace && tid == 0 && t == 0) trace_stamp(a, 4);
       const unsigned char* st = stage_base + s * Cfg::kStageBytes;
       const int blk_local = t * WK + wk;                          // block index inside this CTA's range
       if (b0 + blk_local < b1) {                                  // warp-uniform (the last stage may be partly empty)
@@ -691,7 +684,6 @@ gemv_w4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
     }
     if (tid == 0 && a.trace) {
       trace_value(a, 8, (unsigned long long)(clock64() - loop0));
-      trace_value(a, 9, (unsigned long long)cwait);
       trace_value(a, 11, (unsigned long long)ntiles);
     }
   }
@@ -1499,48 +1491,61 @@ static size_t w4_smem_bytes(int upg, int wc, int mt, int m, int blocks_per_split
          + (size_t)(splits > 1 ? splits : 0) * m * nt * sizeof(float);                // clus_sm
 }
 
-// Decomposition.  The kernel is a pure stream: what matters is that every CTA is resident at once
-// (one wave, <= 2 CTAs per SM) and that enough bytes are in flight (CTAs x 4 stages x 17 KiB).
-// Prefer narrow tiles (more CTAs, no cross-CTA reduction); split K over a cluster only when the
-// column tiles alone cannot fill the machine.
+// Decomposition (measured: profiles/r01_v6_planner_sweep.log).  The consumer instruction stream
+// bounds an SM and a lone 8-warp CTA does not saturate it, so what counts is how close the CTA count
+// comes to two per SM in ONE wave; at equal counts fewer K splits win (no DSMEM reduction), tiles of
+// 128 columns win for long K slices (512-byte DRAM runs), and a CTA wants at least 1024 k (4 stages).
+// Ring depth: 3 stages when a CTA streams only a few (a third CTA slot per SM stays free, so more of
+// the NEXT launch's CTAs are resident early and prefetch), up to 5 for long streams.
 static bool plan_w4(GemvArgs& a, int mt, int upg, W4Plan& p) {
   const int sms = device_sm_count();
   const int nblocks = a.K / 128;
   const int cap = 2 * sms;
-  // Wide tiles first: the contiguous run per weight row (128 B x wc) is what decides DRAM efficiency
-  // (measured, profiles/r01_v3_tma_gemv_sweep.log: 512-byte runs beat 128-byte runs by up to 1.5x), and
-  // K is split over a cluster to get the CTA count up to about two per SM.
-  int wc = env_int("XBIT_GEMV_WC", 0);               // tuning knobs for tools/sweep.py
-  if (wc != 1 && wc != 2 && wc != 4 && wc != 8) {
-    wc = 4;
-    while (wc > 1 && a.N < 32 * wc) wc /= 2;
-  }
-  const int tiles = (a.N + 32 * wc - 1) / (32 * wc);
-  const int wk = 8 / wc;
-  int splits = env_int("XBIT_GEMV_SPLITS", 0);
-  if (splits < 1 || splits > 8 || (splits & (splits - 1))) {
-    splits = 1;
-    // up to two CTAs per SM in one wave; every CTA keeps at least two full stages
-    while (splits < 8 && tiles * splits * 2 <= cap && nblocks / (splits * 2) >= 2 * wk) splits *= 2;
-  }
-  int ring = env_int("XBIT_GEMV_RING", 0);
-  if (ring < 2 || ring > kMaxStages) ring = 4;
-  a.ring = ring;
+  const int env_wc = env_int("XBIT_GEMV_WC", 0);     // tuning knobs for tools/sweep.py
+  const int env_splits = env_int("XBIT_GEMV_SPLITS", 0);
+  const int env_ring = env_int("XBIT_GEMV_RING", 0);
   a.debug_skip = env_int("XBIT_GEMV_DEBUG_SKIP", 0);
   a.trace = nullptr;
-  if (const char* tp = getenv("XBIT_GEMV_TRACE")) {   // tools/trace.py: device buffer of [launch][1024 CTAs][8] stamps
+  if (const char* tp = getenv("XBIT_GEMV_TRACE")) {   // tools/trace.py: device buffer of [launch][1024 CTAs][16] stamps
     static int launches = 0;
     a.trace = reinterpret_cast<unsigned long long*>(strtoull(tp, nullptr, 0)) + (size_t)(launches++ % 64) * 16384;
   }
-  auto smem_of = [&](int sp) { return w4_smem_bytes(upg, wc, mt, a.M, (nblocks + sp - 1) / sp, sp, ring); };
-  while (splits < 8 && smem_of(splits) > kMaxDynSmem) splits *= 2;
-  if (smem_of(splits) > kMaxDynSmem) return false;   // K too long for the staged-activation design at this M
-  p.wc = wc;
-  p.splits = splits;
-  p.blocks_per_split = (nblocks + splits - 1) / splits;
-  p.smem = smem_of(splits);
-  p.grid = dim3((unsigned)tiles, (unsigned)splits, 1);
-  a.splits = splits;
+  double best = -1.0;
+  bool found = false;
+  for (int wc = 1; wc <= 8; wc *= 2) {
+    if (env_wc ? wc != env_wc : (wc == 1 && a.N >= 64)) continue;
+    if (a.N < 32 * wc && wc > 1) continue;
+    const int tiles = (a.N + 32 * wc - 1) / (32 * wc);
+    const int wk = 8 / wc;
+    for (int splits = 1; splits <= 8; splits *= 2) {
+      if (env_splits && splits != env_splits) continue;
+      const int bps = (nblocks + splits - 1) / splits;
+      if (splits > 1 && (splits - 1) * bps >= nblocks) continue;       // an empty split
+      const int stages = (bps + wk - 1) / wk;
+      const long long ctas = (long long)tiles * splits;
+      const long long waves = (ctas + cap - 1) / cap;
+      double score = (double)ctas / (double)(waves * cap);
+      if (waves > 1) score *= 0.75;                                      // every extra wave serialises a prologue and an epilogue
+      if (bps * 128 < 1024) score *= 0.8;
+      for (int sp = splits; sp > 1; sp >>= 1) score *= 0.98;
+      score *= wc == 4 ? 1.0 : (wc == 2 ? (bps * 128 >= 4096 ? 0.94 : 0.99) : 0.98);
+      int ring = env_ring >= 2 && env_ring <= kMaxStages ? env_ring : (stages >= 24 ? 5 : (stages >= 12 ? 4 : 3));
+      const size_t smem = w4_smem_bytes(upg, wc, mt, a.M, bps, splits, ring);
+      if (smem > kMaxDynSmem) continue;                                 // K slice too long for the staged activations at this M
+      if (score > best) {
+        best = score;
+        found = true;
+        p.wc = wc;
+        p.splits = splits;
+        p.blocks_per_split = bps;
+        p.smem = smem;
+        p.grid = dim3((unsigned)tiles, (unsigned)splits, 1);
+        a.ring = ring;
+      }
+    }
+  }
+  if (!found) return false;
+  a.splits = p.splits;
   a.units_per_split = p.blocks_per_split;
   a.chunk_units = 0;
   return true;
