@@ -337,7 +337,7 @@ def run_gpu_arm(args):
                        "calls_per_step": calls_per_step,
                        "l2_policy": "inputs larger than L2: every call reads a distinct weight set, >= 1 GiB rotated per shape",
                        "launch": "one CUDA graph per step, programmatic dependent launch" + (" off" if args.no_pdl else ""),
-                       "schedule": "cluster split-K" if args.no_streamk else "persistent stream-K (one CTA per SM) where applicable",
+                       "schedule": "cluster split-K" if args.no_streamk else "auto: cluster split-K; persistent stream-K where the cluster grid fills < 56 % of one wave and the matrix is >= 32 MB",
                        "combine": {"nccl": "nccl all_gather_into_tensor per call",
                                    "peers": "fused epilogue: NVLink peer stores into every rank's buffer + one symmetric-memory barrier per call",
                                    "none": "none"}[combine],

@@ -20,6 +20,10 @@
 #include <c10/cuda/CUDAGuard.h>
 #include <torch/extension.h>
 
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include <cstdint>
 #include <cstdlib>
 #include <vector>
@@ -59,12 +63,21 @@ void check_quant_args(const torch::Tensor& qweight, const torch::Tensor& scales,
 
 void raise_if(int rc) { TORCH_CHECK(rc == XBIT_OK, "xbitops_b200: ", xbit_last_error()); }
 
-// The persistent stream-K schedule is opt-in (XBIT_GEMV_STREAMK=1) and needs zero-initialised scratch
-// (include/xbitops_b200.h: xbit_gemv_workspace_bytes).  It is allocated per call here -- no static
-// tensors in the shim -- so only opted-in calls pay for the memset.
-bool streamk_requested() {
-  const char* v = std::getenv("XBIT_GEMV_STREAMK");
-  return v && *v == '1';
+// Scratch for the persistent stream-K schedule (include/xbitops_b200.h: xbit_gemv_workspace_bytes):
+// zero-initialised once, left zeroed by every call, one buffer per (device, stream) because calls on
+// one stream are ordered and calls on different streams must not share flags.  The map is leaked on
+// purpose: tensors must not be destroyed after the CUDA context at interpreter exit.
+at::Tensor gemv_workspace(const at::Device& device, cudaStream_t stream, size_t nbytes) {
+  static std::mutex mu;
+  static auto* cache = new std::map<std::pair<int, cudaStream_t>, at::Tensor>();
+  std::lock_guard<std::mutex> lock(mu);
+  auto key = std::make_pair((int)device.index(), stream);
+  auto it = cache->find(key);
+  if (it == cache->end() || (size_t)it->second.numel() < nbytes) {
+    at::Tensor t = at::zeros({(int64_t)nbytes}, at::TensorOptions().dtype(at::kByte).device(device));
+    it = cache->insert_or_assign(key, t).first;
+  }
+  return it->second;
 }
 
 // (internal linkage: the reference extension exports functions of the same names, and both modules
@@ -108,13 +121,10 @@ torch::Tensor op_gemv(const torch::Tensor& input_a, const torch::Tensor& qweight
   if (mat_m > 0) {
     at::Tensor ws;
     void* ws_ptr = nullptr;
-    size_t ws_bytes = 0;
-    if (streamk_requested()) {
-      ws_bytes = xbit_gemv_workspace_bytes((int)mat_m, in_features, (int)qweight.size(1), bits, groupsize);
-      if (ws_bytes > 0) {
-        ws = at::zeros({(int64_t)ws_bytes}, at::TensorOptions().dtype(at::kByte).device(qweight.device()));
-        ws_ptr = ws.data_ptr();
-      }
+    const size_t ws_bytes = xbit_gemv_workspace_bytes((int)(mat_m > 16 ? 16 : mat_m), in_features, (int)qweight.size(1), bits, groupsize);
+    if (ws_bytes > 0) {
+      ws = gemv_workspace(qweight.device(), stream, ws_bytes);
+      ws_ptr = ws.data_ptr();
     }
     raise_if(xbit_gemv_f16(input_a.data_ptr(), qweight.data_ptr<int32_t>(), f16_scale.data_ptr(),
                            qzeros.data_ptr<int32_t>(), output.data_ptr(), (int)mat_m, in_features, (int)qweight.size(1),

@@ -39,6 +39,13 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <string.h>
+
+#include <map>
+#include <mutex>
+#include <set>
+#include <tuple>
+#include <utility>
 
 #include "unpack.cuh"
 #include "xbit_internal.h"
@@ -1491,25 +1498,29 @@ static size_t w4_smem_bytes(int upg, int wc, int mt, int m, int blocks_per_split
          + (size_t)(splits > 1 ? splits : 0) * m * nt * sizeof(float);                // clus_sm
 }
 
+// developer knobs of one launch: tools/sweep.py (skip the math) and tools/trace.py (phase stamps)
+static void apply_debug_knobs(GemvArgs& a) {
+  a.debug_skip = env_int("XBIT_GEMV_DEBUG_SKIP", 0);
+  a.trace = nullptr;
+  if (const char* tp = getenv("XBIT_GEMV_TRACE")) {   // device buffer of [launch % 64][1024 CTAs][16] stamps
+    static int launches = 0;
+    a.trace = reinterpret_cast<unsigned long long*>(strtoull(tp, nullptr, 0)) + (size_t)(launches++ % 64) * 16384;
+  }
+}
+
 // Decomposition (measured: profiles/r01_v6_planner_sweep.log).  The consumer instruction stream
 // bounds an SM and a lone 8-warp CTA does not saturate it, so what counts is how close the CTA count
 // comes to two per SM in ONE wave; at equal counts fewer K splits win (no DSMEM reduction), tiles of
 // 128 columns win for long K slices (512-byte DRAM runs), and a CTA wants at least 1024 k (4 stages).
 // Ring depth: 3 stages when a CTA streams only a few (a third CTA slot per SM stays free, so more of
 // the NEXT launch's CTAs are resident early and prefetch), up to 5 for long streams.
-static bool plan_w4(GemvArgs& a, int mt, int upg, W4Plan& p) {
+static bool plan_w4(GemvArgs& a, int mt, int upg, W4Plan& p, double* score_out = nullptr) {
   const int sms = device_sm_count();
   const int nblocks = a.K / 128;
   const int cap = 2 * sms;
   const int env_wc = env_int("XBIT_GEMV_WC", 0);     // tuning knobs for tools/sweep.py
   const int env_splits = env_int("XBIT_GEMV_SPLITS", 0);
   const int env_ring = env_int("XBIT_GEMV_RING", 0);
-  a.debug_skip = env_int("XBIT_GEMV_DEBUG_SKIP", 0);
-  a.trace = nullptr;
-  if (const char* tp = getenv("XBIT_GEMV_TRACE")) {   // tools/trace.py: device buffer of [launch][1024 CTAs][16] stamps
-    static int launches = 0;
-    a.trace = reinterpret_cast<unsigned long long*>(strtoull(tp, nullptr, 0)) + (size_t)(launches++ % 64) * 16384;
-  }
   double best = -1.0;
   bool found = false;
   for (int wc = 1; wc <= 8; wc *= 2) {
@@ -1545,6 +1556,7 @@ static bool plan_w4(GemvArgs& a, int mt, int upg, W4Plan& p) {
     }
   }
   if (!found) return false;
+  if (score_out) *score_out = best;
   a.splits = p.splits;
   a.units_per_split = p.blocks_per_split;
   a.chunk_units = 0;
@@ -1567,8 +1579,22 @@ static EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
+// Host-side cost matters for the per-call (e2e) figure: cuTensorMapEncodeTiled is a pure function of
+// its arguments, so the encoded maps are kept in a small cache keyed by all of them.
 static cudaError_t encode_2d(CUtensorMap* map, CUtensorMapDataType dt, const void* base, uint64_t inner, uint64_t outer,
                              uint64_t row_bytes, uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle sw) {
+  using Key = std::tuple<int, const void*, uint64_t, uint64_t, uint64_t, uint32_t, uint32_t, int>;
+  static std::mutex mu;
+  static auto* cache = new std::map<Key, CUtensorMap>();
+  const Key key((int)dt, base, inner, outer, row_bytes, box_inner, box_outer, (int)sw);
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache->find(key);
+    if (it != cache->end()) {
+      memcpy(map, &it->second, sizeof(CUtensorMap));
+      return cudaSuccess;
+    }
+  }
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return cudaErrorNotSupported;
   const cuuint64_t dims[2] = {inner, outer};
@@ -1577,7 +1603,25 @@ static cudaError_t encode_2d(CUtensorMap* map, CUtensorMapDataType dt, const voi
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = enc(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+  if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+  std::lock_guard<std::mutex> lock(mu);
+  if (cache->size() >= 8192) cache->clear();
+  (*cache)[key] = *map;
+  return cudaSuccess;
+}
+
+// opt in to large dynamic shared memory once per (device, kernel); not a stream operation
+static cudaError_t ensure_max_dyn_smem(const void* kern) {
+  static std::mutex mu;
+  static auto* done = new std::set<std::pair<int, const void*>>();
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lock(mu);
+  if (done->count({dev, kern})) return cudaSuccess;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
+  if (e == cudaSuccess) done->insert({dev, kern});
+  return e;
 }
 
 using W4Kernel = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemvArgs);
@@ -1599,8 +1643,7 @@ static cudaError_t launch_w4(W4Kernel kern, const GemvArgs& a, const W4Plan& p, 
   e = encode_2d(&zmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, a.qzeros, (uint64_t)a.zwords, (uint64_t)a.groups,
                 (uint64_t)a.zwords * 4, (uint32_t)(nt / 8), (uint32_t)(wk * gpb), CU_TENSOR_MAP_SWIZZLE_NONE);
   if (e != cudaSuccess) return e;
-  // opt in to large dynamic shared memory (idempotent, not a stream operation)
-  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
+  e = ensure_max_dyn_smem(reinterpret_cast<const void*>(kern));
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = p.grid;
@@ -1640,6 +1683,7 @@ cudaError_t launch_gemv_w4_simt(GemvArgs a, cudaStream_t stream) {
   const int upg = upg_of(a.groupsize);
   W4Plan p;
   if (!plan_w4(a, 0, upg, p)) return cudaErrorInvalidValue;
+  apply_debug_knobs(a);
   W4Kernel k = pick_w4_kernel<0, 0>(upg, p.wc);
   return k ? launch_w4(k, a, p, upg, stream) : cudaErrorInvalidValue;
 }
@@ -1649,6 +1693,7 @@ cudaError_t launch_gemv_w4_mma(GemvArgs a, cudaStream_t stream) {
   const int upg = upg_of(a.groupsize);
   W4Plan p;
   if (!plan_w4(a, mt, upg, p)) return cudaErrorInvalidValue;
+  apply_debug_knobs(a);
   // M == 1: hybrid HMMA + FHFMA consumer (XBIT_GEMV_HYBRID=0 forces pure HMMA, for the sweep)
   const int hyb = a.M == 1 ? env_int("XBIT_GEMV_HYBRID", 0) : 0;
   W4Kernel k = mt == 1 ? (hyb == 2 ? pick_w4_kernel<1, 2>(upg, p.wc) : (hyb == 1 ? pick_w4_kernel<1, 1>(upg, p.wc) : pick_w4_kernel<1, 0>(upg, p.wc)))
@@ -1708,6 +1753,19 @@ bool gemv_w4_streamk_applicable(const GemvArgs& a, int family) {
   return plan_streamk(a, mt, p);
 }
 
+// AUTO policy (profiles/r01_v6_cluster_vs_streamk.log): the cluster split-K kernel wins wherever its grid
+// fills the CTA slots of one wave reasonably; when it cannot (e.g. N = 5120: 160 of 296 slots) and the
+// matrix is large enough to amortise the stream-K fix-up, the balanced persistent schedule is faster.
+bool gemv_w4_prefers_streamk(const GemvArgs& a, int family) {
+  if (!gemv_w4_streamk_applicable(a, family)) return false;
+  GemvArgs probe = a;
+  W4Plan p;
+  double score = 1.0;
+  if (!plan_w4(probe, a.M <= 8 ? 1 : 2, upg_of(a.groupsize), p, &score)) return true;   // the cluster kernel cannot stage this K at this M
+  const double weight_bytes = (double)a.K * a.N * 0.5;
+  return score < 0.56 && weight_bytes >= 32e6;
+}
+
 template <int MT>
 static W4Kernel pick_sk_kernel(int upg) {
   if (upg == 1) return gemv_w4_streamk_kernel<MT, 1>;
@@ -1731,12 +1789,7 @@ cudaError_t launch_gemv_w4_streamk(GemvArgs a, int family, void* workspace, size
   a.sk_flags = reinterpret_cast<unsigned int*>(workspace);
   a.sk_partials = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) + (((size_t)sms * sizeof(unsigned int) + 255) / 256) * 256);
   a.splits = 1;
-  a.debug_skip = env_int("XBIT_GEMV_DEBUG_SKIP", 0);
-  a.trace = nullptr;
-  if (const char* tp = getenv("XBIT_GEMV_TRACE")) {
-    static int launches = 0;
-    a.trace = reinterpret_cast<unsigned long long*>(strtoull(tp, nullptr, 0)) + (size_t)(launches++ % 64) * 16384;
-  }
+  apply_debug_knobs(a);
   W4Kernel kern = mt == 1 ? pick_sk_kernel<1>(upg) : pick_sk_kernel<2>(upg);
 
   const int wk = 2, nt = 128;
@@ -1750,7 +1803,7 @@ cudaError_t launch_gemv_w4_streamk(GemvArgs a, int family, void* workspace, size
   e = encode_2d(&zmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, a.qzeros, (uint64_t)a.zwords, (uint64_t)a.groups,
                 (uint64_t)a.zwords * 4, (uint32_t)(nt / 8), (uint32_t)(wk * gpb), CU_TENSOR_MAP_SWIZZLE_NONE);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
+  e = ensure_max_dyn_smem(reinterpret_cast<const void*>(kern));
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)p.grid, 1, 1);
@@ -1809,7 +1862,7 @@ cudaError_t launch_gemv_w4_tc5(GemvArgs a, cudaStream_t stream) {
   e = encode_2d(&zmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, a.qzeros, (uint64_t)a.zwords, (uint64_t)a.groups, (uint64_t)a.zwords * 4, 16, 2,
                 CU_TENSOR_MAP_SWIZZLE_NONE);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
+  e = ensure_max_dyn_smem(reinterpret_cast<const void*>(kern));
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)tiles, (unsigned)splits, 1);

@@ -102,15 +102,14 @@ static int pick_family(const xbit::GemvArgs& a) {
 }
 
 static bool use_streamk(const xbit::GemvArgs& g, int family, void* workspace, size_t workspace_bytes) {
-  // Measured on B200 (profiles/r01_v4_streamk_vs_cluster_sweep.log): with the mma.sync / SIMT consumers
-  // one CTA per SM (8 consumer warps) cannot keep the legacy HMMA pipe busy, so the balanced
-  // schedule is slower than two cluster-path CTAs per SM.  It stays opt-in (XBIT_GEMV_STREAMK=1)
-  // until the consumer side is light enough (tcgen05 path).
-  const char* v = getenv("XBIT_GEMV_STREAMK");
-  const bool enabled = v && *v == '1';
-  if (!enabled || !workspace || (reinterpret_cast<uintptr_t>(workspace) & 255u)) return false;
+  // The persistent stream-K schedule needs the caller's workspace.  XBIT_GEMV_STREAMK=1 forces it on
+  // wherever it applies, =0 off; otherwise the measured policy of gemv_w4_prefers_streamk decides.
+  if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255u)) return false;
   if (workspace_bytes < xbit::gemv_w4_streamk_workspace_bytes(g.M)) return false;
-  return xbit::gemv_w4_streamk_applicable(g, family);
+  const char* v = getenv("XBIT_GEMV_STREAMK");
+  if (v && *v == '0') return false;
+  if (v && *v == '1') return xbit::gemv_w4_streamk_applicable(g, family);
+  return xbit::gemv_w4_prefers_streamk(g, family);
 }
 
 static int gemv_impl(const void* a_f16, const int32_t* qweight, const void* scales_f16, const int32_t* qzeros,

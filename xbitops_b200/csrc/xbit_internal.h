@@ -65,6 +65,7 @@ cudaError_t launch_gemv_w4_simt(GemvArgs a, cudaStream_t stream);   // M <= 4
 cudaError_t launch_gemv_w4_mma(GemvArgs a, cudaStream_t stream);    // M <= 16
 // persistent, balanced stream-K variant of the two (needs workspace); false = not applicable here
 bool gemv_w4_streamk_applicable(const GemvArgs& a, int family);
+bool gemv_w4_prefers_streamk(const GemvArgs& a, int family);      // AUTO policy: cluster grid fills the machine badly
 size_t gemv_w4_streamk_workspace_bytes(int M);
 cudaError_t launch_gemv_w4_streamk(GemvArgs a, int family, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 // tcgen05 + TMEM path (bits 4, groupsize 128, M <= 8)
