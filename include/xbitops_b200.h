@@ -87,9 +87,10 @@ XBIT_API int xbit_dequant_f16(const int32_t* qweight, const void* scales_f16, co
                               xbit_stream_t stream);
 
 /* Bytes of OPTIONAL scratch for xbit_gemv_f16 (0 when none is useful).  With a workspace of at
- * least this size the W4 path runs a persistent, perfectly balanced stream-K schedule (fp32
- * partial tiles + ready flags); without one (NULL / smaller) split-K is reduced through cluster
- * shared memory.  The scratch must be 256-byte aligned, ZERO-INITIALISED before its first use
+ * least this size the W4 path MAY run a persistent, perfectly balanced stream-K schedule (fp32
+ * partial tiles + ready flags) where that is measured to be faster (large matrices whose column
+ * tiles fill the SMs badly; env XBIT_GEMV_STREAMK=0/1 forces it off/on); without one (NULL /
+ * smaller) split-K is always reduced through cluster shared memory.  The scratch must be 256-byte aligned, ZERO-INITIALISED before its first use
  * (every call leaves it zeroed again), and must not be shared by calls that can run concurrently
  * (calls ordered on one stream may share it). */
 XBIT_API size_t xbit_gemv_workspace_bytes(int M, int K, int N, int bits, int groupsize);
