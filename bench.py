@@ -231,14 +231,25 @@ def run_gpu_arm(args):
     peak, peak_src = measured_peak_gbs()
 
     combine = args.combine if world > 1 else "none"
-    if combine == "peers":
+    sig = None
+    if combine in ("peers", "signal"):
         try:
             for ss in sets:
                 ss.make_symmetric(torch, dist)
+            if combine == "signal":
+                import torch.distributed._symmetric_memory as symm_mem
+                sflags = symm_mem.empty((64,), dtype=torch.int32, device=dev)
+                sflags.zero_()
+                fhdl = symm_mem.rendezvous(sflags, dist.group.WORLD.group_name)
+                state = torch.zeros(4, dtype=torch.int32, device=dev)
+                torch.cuda.synchronize()
+                dist.barrier()
+                sig = (sflags, [int(p) for p in fhdl.buffer_ptrs], state)
         except Exception as ex:  # noqa: BLE001
             if rank == 0:
                 print(f"[bench] symmetric memory unavailable ({ex}); falling back to nccl all-gather", file=sys.stderr)
             combine = "nccl"
+            sig = None
 
     def launch(ss: ShapeSet, j: int, mode: str = None):
         mode = mode or combine
@@ -254,6 +265,20 @@ def run_gpu_arm(args):
                 raise RuntimeError(capi.last_error())
             hdl.barrier()          # every rank's slice has landed in every buffer
             return
+        if mode == "signal":
+            buf, hdl, bases = ss.symm
+            off = j * ss.N_total * 2
+            arr = (ctypes.c_void_p * world)(*[b + off for b in bases])
+            sflags, fptrs, state = sig
+            farr = (ctypes.c_void_p * world)(*fptrs)
+            # the gather of call i is awaited inside call i + 1 (as in a decode chain, where call i + 1 reads
+            # call i's gathered output); finish_chain() awaits the last one
+            rc = lib.xbit_gemv_f16_peers_signal(ss.a.data_ptr(), ss.qw[j].data_ptr(), ss.sc[j].data_ptr(), ss.qz[j].data_ptr(),
+                                                arr, farr, state.data_ptr(), world, rank, 1, ss.K, ss.N, BITS, GROUP, 0,
+                                                ss.N_total, ss.col0, family | flags | (0 if os.environ.get("BENCH_SIGNAL_NOWAIT") else capi.GEMV_FLAG_WAIT_PEERS), st)
+            if rc != 0:
+                raise RuntimeError(capi.last_error())
+            return
         out = ss.out[j]
         rc = lib.xbit_gemv_f16_peers_ex(ss.a.data_ptr(), ss.qw[j].data_ptr(), ss.sc[j].data_ptr(), ss.qz[j].data_ptr(),
                                         (ctypes.c_void_p * 1)(out.data_ptr()), 1, 1, ss.K, ss.N, BITS, GROUP, 0,
@@ -263,12 +288,20 @@ def run_gpu_arm(args):
         if mode == "nccl":
             dist.all_gather_into_tensor(out.view(-1), out[:, ss.col0:ss.col0 + ss.N].reshape(-1))
 
+    def finish_chain(mode: str = None):
+        if (mode or combine) == "signal":
+            sflags, fptrs, state = sig
+            rc = lib.xbit_peers_wait(fptrs[rank], world, rank, state.data_ptr() + 12, torch.cuda.current_stream().cuda_stream)
+            if rc != 0:
+                raise RuntimeError(capi.last_error())
+
     def capture(set_list, mode=None):
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):          # warm outside capture (module load, NCCL channels)
             for ss in set_list:
                 launch(ss, 0, mode)
+            finish_chain(mode)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
@@ -278,6 +311,7 @@ def run_gpu_arm(args):
                 for j in range(ss.R):
                     launch(ss, j, mode)
                     n += 1
+            finish_chain(mode)
         return g, n
 
     def sync_all():
@@ -322,14 +356,16 @@ def run_gpu_arm(args):
             "rotating_sets": ss.R, "family": lib.xbit_gemv_pick_family(1, ss.K, ss.N, BITS, GROUP) if family == 0 else family}
         del g1
         if world > 1:
-            for mode in ("none", "nccl", "peers"):
-                if mode == combine or (mode == "peers" and ss.symm is None):
+            for mode in ("none", "nccl", "peers", "signal"):
+                if mode == combine or (mode in ("peers", "signal") and ss.symm is None) or (mode == "signal" and sig is None):
                     continue
                 g2, n2 = capture([ss], mode)
                 ms2 = timed(g2, max(3, args.steps // 4), 3) / max(3, args.steps // 4)
                 per_shape[f"{ss.K}x{ss.N_total}"][f"us_per_call_{'kernel_only' if mode == 'none' else mode}"] = round(ms2 * 1e3 / n2, 3)
                 del g2
 
+    if sig is not None and int(sig[2][3].item()) != 0:
+        raise RuntimeError("xbit_peers_wait timed out: a rank never published its completion flag")
     line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms_per_step, 5), "higher_is_better": True,
             "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
@@ -338,11 +374,13 @@ def run_gpu_arm(args):
                        "l2_policy": "inputs larger than L2: every call reads a distinct weight set, >= 1 GiB rotated per shape",
                        "launch": "one CUDA graph per step, programmatic dependent launch" + (" off" if args.no_pdl else ""),
                        "schedule": "cluster split-K" if args.no_streamk else "auto: cluster split-K; persistent stream-K where the cluster grid fills < 56 % of one wave and the matrix is >= 32 MB",
-                       "combine": {"nccl": "nccl all_gather_into_tensor per call",
+                       "combine": {"signal": "fused: the kernel's epilogue stores its slice into every rank's buffer over NVLink and raises a per-rank completion flag; the next call's kernel awaits the flags before it reads its activations (one wait kernel at the end of a step)",
+                                   "nccl": "nccl all_gather_into_tensor per call",
                                    "peers": "fused epilogue: NVLink peer stores into every rank's buffer + one symmetric-memory barrier per call",
                                    "none": "none"}[combine],
                        "parallelism": f"n-split x{world}" if world > 1 else "single"},
-            "per_shape": per_shape, "clocks": clk.summary(), "gpu_launches": calls_per_step * args.steps}
+            "per_shape": per_shape, "clocks": clk.summary(),
+            "gpu_launches": (calls_per_step + (1 if combine == "signal" else 0)) * args.steps}
 
     if rank == 0:
         # roofline of the dominant (only) kernel family over the timed region
@@ -464,8 +502,9 @@ def main():
     ap.add_argument("--workload", default=None, choices=[None, *WORKLOADS])
     ap.add_argument("--family", default="auto", choices=["auto", "simt", "mma"])
     ap.add_argument("--no-pdl", action="store_true", help="do not assert static weights (no prefetch before griddepcontrol.wait)")
-    ap.add_argument("--combine", default="peers", choices=["peers", "nccl", "none"],
-                    help="N>1: how output slices are combined (fused NVLink peer stores | NCCL all-gather | kernel only)")
+    ap.add_argument("--combine", default="peers", choices=["peers", "signal", "nccl", "none"],
+                    help="N>1: how output slices are combined (fused NVLink peer stores + symmetric-memory barrier | peer stores "
+                         "+ in-kernel completion flags awaited by the next call | NCCL all-gather | kernel only)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-streamk", action="store_true", help="no workspace: cluster split-K kernel instead of the persistent stream-K schedule")
     ap.add_argument("--no-single", action="store_true")

@@ -11,6 +11,8 @@
  *   xbit_gemv_f16_peers   <-  no reference counterpart (the reference is single-GPU):
  *                             N-split GEMV whose epilogue stores each finished output slice into
  *                             every rank's output buffer over NVLink peer mappings.
+ *   xbit_gemv_f16_peers_signal / xbit_peers_wait  <-  none either: the same with the rank
+ *                             synchronisation fused into the kernel (flag per rank, no barrier launch).
  *
  * The reference's own `extern "C" int QbitGemv(SampleData*)` (src/gemv.cuh:22) is a benchmark
  * harness entry, not an operator ABI, and is deliberately not mirrored.
@@ -74,6 +76,10 @@ enum {
    * loop).  The kernel may then prefetch weights while that previous kernel is still running
    * (programmatic dependent launch); activations are still read only after it has finished. */
   XBIT_GEMV_FLAG_STATIC_WEIGHTS = 0x100,
+  /* xbit_gemv_f16_peers_signal only: before it reads its activations the kernel waits until
+   * every rank has published as many calls as this rank has (i.e. the previous N-split call is
+   * complete everywhere): the gather of call i is awaited inside call i+1, no wait launch. */
+  XBIT_GEMV_FLAG_WAIT_PEERS = 0x200,
   XBIT_GEMV_FAMILY_MASK = 0xFF
 };
 
@@ -135,6 +141,31 @@ XBIT_API int xbit_gemv_f16_peers_ex(const void* a_f16, const int32_t* qweight, c
                                     int64_t out_row_stride, int64_t col_offset,
                                     void* workspace, size_t workspace_bytes, int family,
                                     xbit_stream_t stream);
+
+/* As xbit_gemv_f16_peers_ex, with the rank synchronisation fused into the kernel: no barrier
+ * launch.  peer_flags[r] is rank r's flag array (world x uint32, zero-initialised once, in the
+ * same kind of peer-mapped memory as the outputs) as mapped in THIS process; local_state is two
+ * zero-initialised uint32 in ordinary device memory of this rank.  When the last column tile of
+ * this rank's slice has been stored into every buffer, the kernel publishes its call number
+ * (local_state[1] + 1) in slot `rank` of every rank's flag array (system-scope fence, then the
+ * flag stores).  A rank may read its output buffer after xbit_peers_wait on the same stream, or
+ * inside the next xbit_gemv_f16_peers_signal call issued with XBIT_GEMV_FLAG_WAIT_PEERS (whose
+ * activations are then typically that buffer).  Call numbers live in device memory, so a captured
+ * CUDA graph can be replayed.  Every rank must issue the same sequence of calls.  Restrictions:
+ * the W4 fast path (bits 4, groupsize 32/64/128, K%128 = 0, N_local%32 = 0) and M <= 16;
+ * XBIT_EINVAL otherwise (use the barrier form). */
+XBIT_API int xbit_gemv_f16_peers_signal(const void* a_f16, const int32_t* qweight, const void* scales_f16,
+                                        const int32_t* qzeros, void* const* peer_out_host_array,
+                                        void* const* peer_flags_host_array, void* local_state,
+                                        int world, int rank, int M, int K, int N_local, int bits,
+                                        int groupsize, int add_zero_bias, int64_t out_row_stride,
+                                        int64_t col_offset, int family, xbit_stream_t stream);
+
+/* Enqueues a one-warp kernel that returns once every rank has published as many calls as this
+ * rank (local_flags = this rank's own flag array).  timeout_flag (device uint32, may be NULL) is
+ * set to 1 if a peer did not arrive within about 2 s -- the kernel never hangs. */
+XBIT_API int xbit_peers_wait(const void* local_flags, int world, int rank, void* timeout_flag,
+                             xbit_stream_t stream);
 
 /* Host-buffer convenience used for end-to-end measurement: activations come from (pinned) host
  * memory and the result goes back to host memory; weights stay resident on the device.

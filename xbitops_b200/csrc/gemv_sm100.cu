@@ -502,6 +502,30 @@ __device__ __forceinline__ void w4_consume_block_v2(const unsigned char* __restr
   }
 }
 
+// Fused gather wait: ONE lane per CTA polls this rank's flag array until every rank's slot has reached
+// this rank's own published call count (relaxed system-scope polls with a back-off, one fence at the
+// end).  Thousands of threads polling one L2 sector delay the very NVLink write they wait for: with
+// all 8 warps of every CTA polling, the wait cost 14 us per call (profiles/r01_v6_bench_n2_*).  ~2 s guard.
+__device__ __forceinline__ bool peers_poll(const unsigned int* flags, int world, int rank, int lane) {
+  bool ok = true;
+  if (lane == 0) {
+    unsigned int expected, f;
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(expected) : "l"(flags + rank) : "memory");
+    const long long c0 = clock64();
+    for (int p = 0; p < world; ++p) {
+      for (unsigned int n = 1;; ++n) {
+        asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(f) : "l"(flags + p) : "memory");
+        if ((int)(f - expected) >= 0) break;
+        if ((n & 255u) == 0 && clock64() - c0 > 4000000000ll) { ok = false; break; }
+        __nanosleep(200);
+      }
+    }
+    __threadfence_system();
+  }
+  __syncwarp();
+  return ok;
+}
+
 // tools/trace.py: wall-clock stamps of one CTA's phases (debug only; a.trace is null in production)
 __device__ __forceinline__ void trace_stamp(const GemvArgs& a, int slot) {
   if (a.trace) {
@@ -623,6 +647,10 @@ gemv_w4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
     // stage the activations of this CTA's K range (the only data that depends on the previous
     // kernel); the mma path also needs sum_k a_k per scale group for the folded zero point
     griddep_wait();
+    if (a.sig_wait) {                               // the previous N-split call has landed here (warp 0 polls, the others wait for it)
+      if (warp == 0) peers_poll(a.sig_flags[a.sig_rank], a.world, a.sig_rank, lane);
+      asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");
+    }
     if (tid == 0) trace_stamp(a, 2);
     {
       // no divisions in here: the loop is instruction bound, not latency bound (tools/trace.py)
@@ -634,7 +662,7 @@ gemv_w4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
           const bool ok = v < vecs_per_row;
           uint4 val = make_uint4(0, 0, 0, 0);
           if (ok) {
-            val = __ldg(arow + v);
+            val = __ldcg(arow + v);                 // L2 only: the row may just have been written by peer GPUs
             *reinterpret_cast<uint4*>(srow + v * 8) = kV2 ? permute_act8_v2(val) : permute_act8<kMma>(val);
           }
           if constexpr (kMma) {
@@ -760,6 +788,28 @@ gemv_w4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
       const size_t off = (size_t)m * a.ldo + a.col_offset + n_cta + col;
       a.out[0][off] = h;
       for (int p = 1; p < a.world; ++p) a.out[p][off] = h;   // fused all-gather: NVLink peer stores
+    }
+  }
+  if (a.sig_state != nullptr) {
+    // Fused completion signal: the column tile that finishes LAST on this GPU tells every rank
+    // "rank sig_rank's slice of call #epoch has landed in your buffer".  Stores of every tile are made
+    // visible system-wide (one fence per CTA, after the CTA barrier) before its count; the last one fences
+    // again before the flags.
+    __syncthreads();
+    if (tid == 0) {
+      // one thread, cumulative over the CTA's stores ordered by the barrier.  GPU scope here (a system
+      // fence per CTA was measured at +8 us per call); the CTA that arrives last issues the one
+      // system-scope fence, which is cumulative over everything it has observed through the counter.
+      __threadfence();
+      const unsigned int done = atomicAdd(a.sig_state, 1u);
+      if (done == gridDim.x - 1) {
+        a.sig_state[0] = 0u;
+        const unsigned int epoch = a.sig_state[1] + 1u;
+        a.sig_state[1] = epoch;
+        __threadfence_system();
+        for (int p = 0; p < a.world; ++p)
+          asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(a.sig_flags[p] + a.sig_rank), "r"(epoch) : "memory");
+      }
     }
   }
   if (tid == 0) trace_stamp(a, 7);
@@ -1894,6 +1944,27 @@ cudaError_t launch_gemv_generic(GemvArgs a, cudaStream_t stream) {
     if (e != cudaSuccess) return e;
   }
   return cudaSuccess;
+}
+
+
+// ---- explicit consumer side of the fused completion signal (end of a chain): one warp
+__global__ void peers_wait_kernel(const unsigned int* flags, int world, int rank, unsigned int* timeout_flag) {
+  griddep_launch_dependents();
+  griddep_wait();                                   // this rank's own call has completed: its flag holds the call count
+  if (!peers_poll(flags, world, rank, threadIdx.x) && timeout_flag) *timeout_flag = 1u;
+}
+
+cudaError_t launch_peers_wait(const unsigned int* flags, int world, int rank, unsigned int* timeout_flag, cudaStream_t stream) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(1, 1, 1);
+  cfg.blockDim = dim3(32, 1, 1);
+  cfg.stream = stream;
+  cudaLaunchAttribute attrs[1];
+  attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // resident before the GEMV retires: no launch gap
+  attrs[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, peers_wait_kernel, flags, world, rank, timeout_flag);
 }
 
 }  // namespace xbit

@@ -112,10 +112,16 @@ static bool use_streamk(const xbit::GemvArgs& g, int family, void* workspace, si
   return xbit::gemv_w4_prefers_streamk(g, family);
 }
 
+struct PeerSignal {
+  void* const* flags;   // world peer-mapped flag arrays
+  void* state;          // local uint32[3]
+  int rank;
+};
+
 static int gemv_impl(const void* a_f16, const int32_t* qweight, const void* scales_f16, const int32_t* qzeros,
                      void* const* outs, int world, int M, int K, int N, int bits, int groupsize, int add_zero_bias,
                      int64_t out_row_stride, int64_t col_offset, int family_and_flags, void* workspace,
-                     size_t workspace_bytes, xbit_stream_t stream) {
+                     size_t workspace_bytes, xbit_stream_t stream, const PeerSignal* sig = nullptr) {
   g_err[0] = 0;
   if (int rc = check_common(qweight, scales_f16, qzeros, K, N, bits, groupsize, add_zero_bias)) return rc;
   if (!a_f16) return fail(XBIT_EINVAL, "null activation pointer");
@@ -140,8 +146,26 @@ static int gemv_impl(const void* a_f16, const int32_t* qweight, const void* scal
   g.zwords = ceil_div((long long)N * bits, 32);
   g.groups = ceil_div(K, groupsize);
   g.static_weights = (family_and_flags & XBIT_GEMV_FLAG_STATIC_WEIGHTS) ? 1 : 0;
-  const int family_req = family_and_flags & XBIT_GEMV_FAMILY_MASK;
+  int family_req = family_and_flags & XBIT_GEMV_FAMILY_MASK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (sig) {
+    // the signal is raised by the cluster split-K kernel of the tensor-core family, one launch per call
+    if (!sig->flags || !sig->state || sig->rank < 0 || sig->rank >= world) return fail(XBIT_EINVAL, "bad peer signal arguments");
+    if (family_req != XBIT_GEMV_AUTO && family_req != XBIT_GEMV_MMA) return fail(XBIT_EINVAL, "the fused signal needs the AUTO or MMA family");
+    g.M = M;
+    if (M > 16 || !xbit::gemv_w4_supported(g))
+      return fail(XBIT_EINVAL, "the fused signal needs the W4 fast path (bits 4, groupsize 32/64/128, K%%128=0, N%%32=0) and M <= 16");
+    family_req = XBIT_GEMV_MMA;
+    workspace = nullptr;          // no stream-K here: its tiles are not stored by one CTA each
+    workspace_bytes = 0;
+    for (int p = 0; p < world; ++p) {
+      if (!sig->flags[p]) return fail(XBIT_EINVAL, "null flag pointer (rank %d)", p);
+      g.sig_flags[p] = reinterpret_cast<unsigned int*>(sig->flags[p]);
+    }
+    g.sig_state = reinterpret_cast<unsigned int*>(sig->state);
+    g.sig_rank = sig->rank;
+    g.sig_wait = (family_and_flags & XBIT_GEMV_FLAG_WAIT_PEERS) ? 1 : 0;
+  }
 
   // rows are processed in slabs the chosen family can take (weights are re-read per slab only
   // beyond M = 16; the reference re-reads them for every row, gemv_w4a16_pt.cu:158)
@@ -225,6 +249,26 @@ int xbit_gemv_f16_peers(const void* a_f16, const int32_t* qweight, const void* s
   return xbit_gemv_f16_peers_ex(a_f16, qweight, scales_f16, qzeros, peer_out_host_array, world, M, K, N_local, bits,
                                 groupsize, add_zero_bias, out_row_stride, col_offset, workspace, workspace_bytes,
                                 XBIT_GEMV_AUTO, stream);
+}
+
+int xbit_gemv_f16_peers_signal(const void* a_f16, const int32_t* qweight, const void* scales_f16, const int32_t* qzeros,
+                               void* const* peer_out_host_array, void* const* peer_flags_host_array, void* local_state,
+                               int world, int rank, int M, int K, int N_local, int bits, int groupsize, int add_zero_bias,
+                               int64_t out_row_stride, int64_t col_offset, int family, xbit_stream_t stream) {
+  const PeerSignal sig = {peer_flags_host_array, local_state, rank};
+  return gemv_impl(a_f16, qweight, scales_f16, qzeros, peer_out_host_array, world, M, K, N_local, bits, groupsize,
+                   add_zero_bias, out_row_stride, col_offset, family, nullptr, 0, stream, &sig);
+}
+
+int xbit_peers_wait(const void* local_flags, int world, int rank, void* timeout_flag, xbit_stream_t stream) {
+  g_err[0] = 0;
+  if (!local_flags) return fail(XBIT_EINVAL, "null flag pointer");
+  if (world < 1 || world > xbit::kMaxPeers || rank < 0 || rank >= world)
+    return fail(XBIT_EINVAL, "need 1 <= world <= %d and 0 <= rank < world, got world %d rank %d", xbit::kMaxPeers, world, rank);
+  const cudaError_t e = xbit::launch_peers_wait(reinterpret_cast<const unsigned int*>(local_flags), world, rank,
+                                                reinterpret_cast<unsigned int*>(timeout_flag), reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "xbit_peers_wait launch");
+  return XBIT_OK;
 }
 
 int xbit_gemv_f16_host(const void* a_f16_host, void* out_f16_host, void* d_a_staging, void* d_out_staging,

@@ -30,6 +30,11 @@ struct GemvArgs {
   long long col_offset;     // first output column of this shard
   int qrows, zwords, groups;
   int static_weights;       // XBIT_GEMV_FLAG_STATIC_WEIGHTS: weights may be read before griddepcontrol.wait
+  // fused completion signal of the N-split epilogue (xbit_gemv_f16_peers_signal); null = none
+  unsigned int* sig_flags[kMaxPeers];   // rank r's flag array [world] as mapped here; this rank writes slot sig_rank
+  unsigned int* sig_state;              // local: [0] tiles stored so far, [1] calls published
+  int sig_rank;
+  int sig_wait;                         // XBIT_GEMV_FLAG_WAIT_PEERS: wait for the previous call before reading activations
   // decomposition (filled by the planner)
   int splits;               // K splits = cluster size along grid.y
   int units_per_split;      // 32-k units per split
@@ -75,5 +80,6 @@ cudaError_t launch_gemv_w4_tc5(GemvArgs a, cudaStream_t stream);
 cudaError_t launch_gemv_generic(GemvArgs a, cudaStream_t stream);
 
 int device_sm_count();
+cudaError_t launch_peers_wait(const unsigned int* flags, int world, int rank, unsigned int* timeout_flag, cudaStream_t stream);
 
 }  // namespace xbit

@@ -56,6 +56,26 @@ def _device_gemv_into(x, qweight, scales, qzeros, groupsize, bits, in_features, 
                                           torch.cuda.current_stream().cuda_stream))
 
 
+def _device_gemv_signal(x, qweight, scales, qzeros, groupsize, bits, in_features, add_zero_bias, out_view, col_offset,
+                        peer_ptrs, flag_ptrs, state, rank, family=capi.GEMV_AUTO) -> bool:
+    """Shard GEMV whose epilogue stores the slice into every rank's buffer AND raises the per-rank
+    completion flag (xbit_gemv_f16_peers_signal), followed by the one-warp wait.  False = this shape is not
+    covered by the fused signal (the caller falls back to the barrier form)."""
+    lib = capi.load()
+    m, n = x.shape[0], qweight.shape[1]
+    if m > 16 or bits != 4 or groupsize not in (32, 64, 128) or in_features % 128 or n % 32:
+        return False
+    world = len(peer_ptrs)
+    outs = (ctypes.c_void_p * world)(*peer_ptrs)
+    flags = (ctypes.c_void_p * world)(*flag_ptrs)
+    st = torch.cuda.current_stream().cuda_stream
+    capi.check(lib.xbit_gemv_f16_peers_signal(x.data_ptr(), qweight.data_ptr(), scales.data_ptr(), qzeros.data_ptr(), outs,
+                                              flags, state.data_ptr(), world, rank, m, in_features, n, bits, groupsize,
+                                              int(add_zero_bias), out_view.shape[1], col_offset, int(family), st))
+    capi.check(lib.xbit_peers_wait(flag_ptrs[rank], world, rank, state.data_ptr() + 12, st))
+    return True
+
+
 class ShardedQLinear:
     """y = x @ DQ(W) with W split by output columns over the ranks of `group`.
 
@@ -75,7 +95,7 @@ class ShardedQLinear:
         self.n_local = out_features // self.world
         if qweight_shard.shape[1] != self.n_local:
             raise ValueError(f"qweight shard has {qweight_shard.shape[1]} columns, expected {self.n_local}")
-        if combine not in ("nccl", "peers", "none"):
+        if combine not in ("nccl", "peers", "signal", "none"):
             raise ValueError(combine)
         self.combine = combine
         self._local = local_gemv
@@ -92,25 +112,44 @@ class ShardedQLinear:
 
     # -- symmetric memory for the fused epilogue -------------------------------------------------
     def _symm_buffer(self, m: int, device):
-        if self._symm is not None and self._symm[0].shape[0] >= m:
+        """Two [m, out_features] result buffers (used alternately: a rank publishes call e+1 only after it has
+        consumed result e on the same stream, so whoever has seen all flags of e+1 may overwrite buffer e%2)
+        and a flag array, all in symmetric memory; the call counters live in ordinary device memory."""
+        if self._symm is not None and self._symm[0].shape[1] >= m:
             return self._symm
         import torch.distributed._symmetric_memory as symm_mem
-        buf = symm_mem.empty((m, self.out_features), dtype=torch.float16, device=device)
-        hdl = symm_mem.rendezvous(buf, self.group.group_name if self.group is not None else dist.group.WORLD.group_name)
-        ptrs = [int(p) for p in hdl.buffer_ptrs]
-        self._symm = (buf, hdl, ptrs)
+        name = self.group.group_name if self.group is not None else dist.group.WORLD.group_name
+        buf = symm_mem.empty((2, m, self.out_features), dtype=torch.float16, device=device)
+        hdl = symm_mem.rendezvous(buf, name)
+        flags = symm_mem.empty((64,), dtype=torch.int32, device=device)
+        flags.zero_()
+        fhdl = symm_mem.rendezvous(flags, name)
+        state = torch.zeros(4, dtype=torch.int32, device=device)   # tiles done, send epoch, wait epoch, timeout
+        torch.cuda.synchronize(device)
+        hdl.barrier()                                              # every rank's flags are zero before anyone signals
+        self._symm = (buf, hdl, [int(p) for p in hdl.buffer_ptrs], flags, [int(p) for p in fhdl.buffer_ptrs], state)
+        self._calls = 0
         return self._symm
 
     # -- forward -----------------------------------------------------------------------------------
     def forward(self, x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
         """x [M, K] fp16 (replicated on every rank) -> [M, out_features] fp16 on every rank."""
         m = x.shape[0]
-        if self.combine == "peers" and self.world > 1:
-            buf, hdl, ptrs = self._symm_buffer(m, x.device)
+        if self.combine in ("peers", "signal") and self.world > 1:
+            buf, hdl, ptrs, flags, fptrs, state = self._symm_buffer(m, x.device)
+            k = self._calls & 1
+            self._calls += 1
+            view = buf[k, :m]
+            off = k * buf.shape[1] * buf.shape[2] * 2
+            kptrs = [p + off for p in ptrs]
+            if self.combine == "signal" and self._local is None and _device_gemv_signal(x, self.qweight, self.scales, self.qzeros, self.groupsize, self.bits,
+                                                           self.in_features, self.add_zero_bias, view, self.rank * self.n_local,
+                                                           kptrs, fptrs, state, self.rank):
+                return view                    # synchronisation fused into the kernel + a one-warp wait
             hdl.barrier()                      # everyone has consumed the previous result
-            self._local_gemv(x, buf[:m], ptrs)
+            self._local_gemv(x, view, kptrs)
             hdl.barrier()                      # every slice has landed everywhere
-            return buf[:m]
+            return view
         if out is None:
             out = torch.empty((m, self.out_features), dtype=torch.float16, device=x.device)
         self._local_gemv(x, out)
