@@ -177,16 +177,26 @@ def test_gemv_streamk_schedule(dev, c_oracle, monkeypatch):
     workspace is left zeroed (flags cleared) so that consecutive calls can share it."""
     from xbitops_b200 import ops
     monkeypatch.setenv("XBIT_GEMV_STREAMK", "1")
-    for (K, N, M) in ((4096, 4096, 1), (11008, 4096, 1), (4096, 11008, 2), (8192, 1024, 5)):
-        qw, s, qz, a = synth.make_inputs(K, N, 4, 128, M=M, seed=K + N + M)
-        w = c_oracle.dequant(qw, s, qz, 128, 4, K, 1)
+    # (K, N, M, g, bias): whole tiles per CTA and tiles shared by several CTAs, a half-empty last stage
+    # (K = 4224 = 33 blocks), a partial last tile (N = 4128), fewer units than SMs (N = 96), every
+    # groupsize of the fast path, both tensor-core tile heights (M <= 8, M <= 16)
+    cases = ((4096, 4096, 1, 128, 1), (11008, 4096, 1, 128, 1), (4096, 11008, 2, 128, 0), (8192, 1024, 5, 128, 1),
+             (4224, 4128, 1, 128, 1), (1024, 96, 3, 64, 0), (2048, 2048, 8, 32, 1), (4096, 512, 13, 128, 1),
+             (8192, 8192, 16, 64, 0))
+    for (K, N, M, g, bias) in cases:
+        qw, s, qz, a = synth.make_inputs(K, N, 4, g, M=M, seed=K + N + M)
+        w = c_oracle.dequant(qw, s, qz, g, 4, K, bias)
         y64 = a.astype(np.float64) @ w.astype(np.float64)
         tq, ts, tz, ta = ti(qw, dev), t16(s, dev), ti(qz, dev), t16(a, dev)
-        for fam in (capi.GEMV_MMA, capi.GEMV_SIMT):
-            y1 = X.gemv(ta, tq, ts, tz, 128, 4, K, 1, family=fam)
-            y2 = X.gemv(ta, tq, ts, tz, 128, 4, K, 1, family=fam)
-            assert torch.equal(y1, y2)                       # deterministic, workspace reusable
-            assert_gemv_close(y1.cpu().numpy(), y64, f"stream-K {K}x{N} M={M} family {fam}")
+        y1 = X.gemv(ta, tq, ts, tz, g, 4, K, bias, family=capi.GEMV_MMA)
+        y2 = X.gemv(ta, tq, ts, tz, g, 4, K, bias, family=capi.GEMV_MMA)
+        assert torch.equal(y1, y2)                           # deterministic, workspace reusable
+        assert_gemv_close(y1.cpu().numpy(), y64, f"stream-K {K}x{N} M={M} g={g}")
+        monkeypatch.setenv("XBIT_GEMV_STREAMK", "0")         # the cluster split-K kernel on the same inputs
+        y3 = X.gemv(ta, tq, ts, tz, g, 4, K, bias, family=capi.GEMV_MMA)
+        monkeypatch.setenv("XBIT_GEMV_STREAMK", "1")
+        assert_gemv_close(y3.cpu().numpy(), y64, f"cluster {K}x{N} M={M} g={g}")
+        assert float((y1.double() - y3.double()).abs().max()) <= 2e-3 * float(np.abs(y64).max())
     torch.cuda.synchronize()
     ws = ops.gemv_workspace(dev)
     assert int(ws[: 148 * 4].view(torch.int32).abs().sum()) == 0      # ready flags cleared
