@@ -170,7 +170,11 @@ XBIT_API int xbit_peers_wait(const void* local_flags, int world, int rank, void*
 /* Host-buffer convenience used for end-to-end measurement: activations come from (pinned) host
  * memory and the result goes back to host memory; weights stay resident on the device.
  * d_a_staging / d_out_staging are device scratch of M*K*2 and M*N*2 bytes.  Enqueues
- * H2D copy -> gemv -> D2H copy on `stream`; the caller synchronises. */
+ * H2D copy -> gemv -> D2H copy on `stream`; the caller synchronises.  With page-locked,
+ * device-mapped host memory (cudaHostAlloc / cudaHostRegister) no copy nodes are enqueued: a
+ * small kernel pulls the activation rows over PCIe and the GEMV stores its result straight into
+ * out_f16_host.  The weights must not be written by the operation that precedes this call in
+ * `stream` (they are prefetched under programmatic dependent launch). */
 XBIT_API int xbit_gemv_f16_host(const void* a_f16_host, void* out_f16_host, void* d_a_staging,
                                 void* d_out_staging, const int32_t* qweight, const void* scales_f16,
                                 const int32_t* qzeros, int M, int K, int N, int bits, int groupsize,

@@ -333,7 +333,13 @@ def test_host_buffer_entry_point(dev, c_oracle):
     capi.check(lib.xbit_gemv_f16_host(ha.data_ptr(), ho.data_ptr(), da.data_ptr(), do.data_ptr(), tq.data_ptr(),
                                       ts.data_ptr(), tz.data_ptr(), 1, K, N, 4, g, 0, None, 0, st))
     torch.cuda.synchronize()
-    assert_gemv_close(ho.numpy().view(np.float16), y64, "host entry")
+    assert_gemv_close(ho.numpy().view(np.float16), y64, "host entry")          # pinned result: stored by the kernel itself
+    assert not bool(torch.equal(do.view(torch.int16).cpu(), ho))                  # ... the staging buffer was not used
+    hp = np.zeros((1, N), dtype=np.int16)                                          # pageable result: staged + D2H copy
+    capi.check(lib.xbit_gemv_f16_host(ha.data_ptr(), hp.ctypes.data, da.data_ptr(), do.data_ptr(), tq.data_ptr(),
+                                      ts.data_ptr(), tz.data_ptr(), 1, K, N, 4, g, 0, None, 0, st))
+    torch.cuda.synchronize()
+    assert np.array_equal(hp, ho.numpy())
 
 
 def test_peer_entry_point_single_process(dev, c_oracle):

@@ -1967,4 +1967,28 @@ cudaError_t launch_peers_wait(const unsigned int* flags, int world, int rank, un
   return cudaLaunchKernelEx(&cfg, peers_wait_kernel, flags, world, rank, timeout_flag);
 }
 
+// ---- host-buffer entry: pull activation rows out of page-locked host memory with a kernel instead of a
+// copy node, so that the chain  pull -> gemv  stays on programmatic dependent launches (a copy node in
+// front of the GEMV costs ~10 us of copy-engine latency per call; measured in bench.py's e2e leg)
+__global__ void pull_rows_kernel(const uint4* __restrict__ src_host, uint4* __restrict__ dst, size_t nvec) {
+  griddep_launch_dependents();                      // the GEMV behind may start streaming its weights
+  griddep_wait();                                   // the previous GEMV has finished reading dst
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) dst[i] = src_host[i];
+}
+
+cudaError_t launch_pull_rows(const void* src_host_devptr, void* dst, size_t bytes, cudaStream_t stream) {
+  const size_t nvec = bytes / 16;
+  cudaLaunchConfig_t cfg = {};
+  const unsigned blocks = (unsigned)((nvec + 255) / 256);
+  cfg.gridDim = dim3(blocks < 1 ? 1 : (blocks > 64 ? 64 : blocks), 1, 1);
+  cfg.blockDim = dim3(256, 1, 1);
+  cfg.stream = stream;
+  cudaLaunchAttribute attrs[1];
+  attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attrs[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, pull_rows_kernel, reinterpret_cast<const uint4*>(src_host_devptr), reinterpret_cast<uint4*>(dst), nvec);
+}
+
 }  // namespace xbit

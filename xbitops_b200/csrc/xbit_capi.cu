@@ -278,14 +278,42 @@ int xbit_gemv_f16_host(const void* a_f16_host, void* out_f16_host, void* d_a_sta
   if (!a_f16_host || !out_f16_host || !d_a_staging || !d_out_staging) return fail(XBIT_EINVAL, "null host/staging pointer");
   if (M < 1 || K < 1 || N < 1) return fail(XBIT_EINVAL, "bad shape M=%d K=%d N=%d", M, K, N);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  cudaError_t e = cudaMemcpyAsync(d_a_staging, a_f16_host, (size_t)M * K * 2, cudaMemcpyHostToDevice, st);
-  if (e != cudaSuccess) return cuda_fail(e, "xbit_gemv_f16_host H2D");
-  // the H2D copy is not a kernel: the weights are untouched by it, so the static-weights prefetch is safe
-  int rc = xbit_gemv_f16_ex(d_a_staging, qweight, scales_f16, qzeros, d_out_staging, M, K, N, bits, groupsize, add_zero_bias,
-                            N, workspace, workspace_bytes, XBIT_GEMV_AUTO, stream);
+  cudaError_t e;
+  const size_t a_bytes = (size_t)M * K * 2;
+  const void* a_dev = nullptr;
+  {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, a_f16_host) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
+      a_dev = attr.devicePointer;
+    else
+      cudaGetLastError();
+  }
+  if (a_dev && a_bytes % 16 == 0 && ((reinterpret_cast<uintptr_t>(a_dev) | reinterpret_cast<uintptr_t>(d_a_staging)) & 15u) == 0) {
+    // page-locked activations: pulled over PCIe by a small kernel (keeps the chain on programmatic launches)
+    e = xbit::launch_pull_rows(a_dev, d_a_staging, a_bytes, st);
+    if (e != cudaSuccess) return cuda_fail(e, "xbit_gemv_f16_host pull");
+  } else {
+    e = cudaMemcpyAsync(d_a_staging, a_f16_host, a_bytes, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return cuda_fail(e, "xbit_gemv_f16_host H2D");
+  }
+  // Pinned (page-locked, device-mapped) result buffer: the kernel's epilogue stores straight into it over
+  // PCIe -- M*N*2 bytes of posted writes, no copy node behind the kernel.  Pageable memory: staged + D2H copy.
+  void* out_dev = nullptr;
+  {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, out_f16_host) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
+      out_dev = attr.devicePointer;
+    else
+      cudaGetLastError();                           // unregistered host memory is reported as an error by older runtimes
+  }
+  // neither the copy nor the pull kernel touches the weights: the static-weights prefetch is safe
+  int rc = xbit_gemv_f16_ex(d_a_staging, qweight, scales_f16, qzeros, out_dev ? out_dev : d_out_staging, M, K, N, bits, groupsize,
+                            add_zero_bias, N, workspace, workspace_bytes, XBIT_GEMV_AUTO | XBIT_GEMV_FLAG_STATIC_WEIGHTS, stream);
   if (rc != XBIT_OK) return rc;
-  e = cudaMemcpyAsync(out_f16_host, d_out_staging, (size_t)M * N * 2, cudaMemcpyDeviceToHost, st);
-  if (e != cudaSuccess) return cuda_fail(e, "xbit_gemv_f16_host D2H");
+  if (!out_dev) {
+    e = cudaMemcpyAsync(out_f16_host, d_out_staging, (size_t)M * N * 2, cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) return cuda_fail(e, "xbit_gemv_f16_host D2H");
+  }
   return XBIT_OK;
 }
 

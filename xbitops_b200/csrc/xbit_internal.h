@@ -80,6 +80,7 @@ cudaError_t launch_gemv_w4_tc5(GemvArgs a, cudaStream_t stream);
 cudaError_t launch_gemv_generic(GemvArgs a, cudaStream_t stream);
 
 int device_sm_count();
+cudaError_t launch_pull_rows(const void* src_host_devptr, void* dst, size_t bytes, cudaStream_t stream);
 cudaError_t launch_peers_wait(const unsigned int* flags, int world, int rank, unsigned int* timeout_flag, cudaStream_t stream);
 
 }  // namespace xbit
