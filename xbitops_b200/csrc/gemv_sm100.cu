@@ -1584,15 +1584,20 @@ static bool plan_w4(GemvArgs& a, int mt, int upg, W4Plan& p, double* score_out =
       if (splits > 1 && (splits - 1) * bps >= nblocks) continue;       // an empty split
       const int stages = (bps + wk - 1) / wk;
       const long long ctas = (long long)tiles * splits;
-      const long long waves = (ctas + cap - 1) / cap;
-      double score = (double)ctas / (double)(waves * cap);
+      const int ring = env_ring >= 2 && env_ring <= kMaxStages ? env_ring : (stages >= 24 ? 5 : (stages >= 12 ? 4 : 3));
+      const size_t smem = w4_smem_bytes(upg, wc, mt, a.M, bps, splits, ring);
+      if (smem > kMaxDynSmem) continue;                                 // K slice too long for the staged activations at this M
+      // staged activations grow with M: above half an SM only one CTA is resident and the SM runs at
+      // about half its rate (a lone 8-warp CTA does not saturate the issue slots)
+      const bool two_per_sm = smem <= 113 * 1024;
+      const long long slots = two_per_sm ? cap : cap / 2;
+      const long long waves = (ctas + slots - 1) / slots;
+      double score = (double)ctas / (double)(waves * slots);
+      if (!two_per_sm) score *= 0.6;
       if (waves > 1) score *= 0.75;                                      // every extra wave serialises a prologue and an epilogue
       if (bps * 128 < 1024) score *= 0.8;
       for (int sp = splits; sp > 1; sp >>= 1) score *= 0.98;
       score *= wc == 4 ? 1.0 : (wc == 2 ? (bps * 128 >= 4096 ? 0.94 : 0.99) : 0.98);
-      int ring = env_ring >= 2 && env_ring <= kMaxStages ? env_ring : (stages >= 24 ? 5 : (stages >= 12 ? 4 : 3));
-      const size_t smem = w4_smem_bytes(upg, wc, mt, a.M, bps, splits, ring);
-      if (smem > kMaxDynSmem) continue;                                 // K slice too long for the staged activations at this M
       if (score > best) {
         best = score;
         found = true;
