@@ -92,10 +92,14 @@ __global__ void __launch_bounds__(128)
 dq_block32_kernel(const uint32_t* __restrict__ qweight, const __half* __restrict__ scales,
                   const uint32_t* __restrict__ qzeros, __half* __restrict__ out,
                   int K, int N, int groupsize, int zero_bias, int qrows, int zwords, int rblocks) {
+  // programmatic dependent launch: the next kernel in the stream may become resident while this one
+  // drains; nothing is read before the previous kernel has completed
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int octets = N >> 3;
   const long long t = (long long)blockIdx.x * 128 + threadIdx.x;
   const int cx = (int)(t % octets);
   const int rb = (int)(t / octets);
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   if (rb >= rblocks) return;
   const int k0 = rb * 32;
   const int n0 = cx * 8;
@@ -170,9 +174,17 @@ static cudaError_t launch_block32(const DqArgs& a, cudaStream_t stream) {
   const int rblocks = (a.K + 31) / 32;
   const long long threads = (long long)rblocks * (a.N >> 3);
   const unsigned grid = (unsigned)((threads + 127) / 128);
-  dq_block32_kernel<B><<<grid, 128, 0, stream>>>(a.qweight, a.scales, a.qzeros, a.out, a.K, a.N, a.groupsize,
-                                                  a.zero_bias, a.qrows, a.zwords, rblocks);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid, 1, 1);
+  cfg.blockDim = dim3(128, 1, 1);
+  cfg.stream = stream;
+  cudaLaunchAttribute attrs[1];
+  attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attrs[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, dq_block32_kernel<B>, a.qweight, a.scales, a.qzeros, a.out, a.K, a.N, a.groupsize,
+                            a.zero_bias, a.qrows, a.zwords, rblocks);
 }
 
 cudaError_t launch_dequant(const DqArgs& a, cudaStream_t stream, int* path_taken) {
