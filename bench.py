@@ -232,6 +232,24 @@ def run_gpu_arm(args):
 
     combine = args.combine if world > 1 else "none"
     sig = None
+    llctx = None
+    if combine == "ll":
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            max_n = max(ss.N_total for ss in sets)
+            llbuf = symm_mem.empty((2, max_n), dtype=torch.int32, device=dev)     # two alternating LL buffers, 8 bytes per result pair
+            llbuf.zero_()
+            lhdl = symm_mem.rendezvous(llbuf, dist.group.WORLD.group_name)
+            lstate = torch.zeros(4, dtype=torch.int32, device=dev)
+            lplain = torch.empty((max_n,), dtype=torch.float16, device=dev)
+            torch.cuda.synchronize()
+            dist.barrier()
+            llctx = {"buf": llbuf, "ptrs": [int(p) for p in lhdl.buffer_ptrs], "state": lstate, "plain": lplain,
+                     "stride": max_n * 4, "calls": 0, "last_n": 0}
+        except Exception as ex:  # noqa: BLE001
+            if rank == 0:
+                print(f"[bench] symmetric memory unavailable ({ex}); falling back to nccl all-gather", file=sys.stderr)
+            combine = "nccl"
     if combine in ("peers", "signal"):
         try:
             for ss in sets:
@@ -265,6 +283,22 @@ def run_gpu_arm(args):
                 raise RuntimeError(capi.last_error())
             hdl.barrier()          # every rank's slice has landed in every buffer
             return
+        if mode == "ll":
+            # dependent chain: this call's activations are the previous call's gathered result, read from the LL
+            # buffer slot by slot as the ranks deliver them; its own result goes into the other LL buffer
+            c = llctx["calls"]
+            chained = c > 0 and llctx["last_n"] == ss.K
+            src = (llctx["ptrs"][rank] + ((c - 1) & 1) * llctx["stride"]) if chained else ss.a.data_ptr()
+            outs = (ctypes.c_void_p * world)(*[b + (c & 1) * llctx["stride"] for b in llctx["ptrs"]])
+            rc = lib.xbit_gemv_f16_peers_ll(src, ss.qw[j].data_ptr(), ss.sc[j].data_ptr(), ss.qz[j].data_ptr(), outs,
+                                            llctx["state"].data_ptr(), world, rank, 1, ss.K, ss.N, BITS, GROUP, 0, ss.N_total,
+                                            ss.col0, family | flags | (capi.GEMV_FLAG_A_IS_LL if chained else 0), st)
+            if rc != 0:
+                raise RuntimeError(capi.last_error())
+            if not chained and c > 0:
+                raise RuntimeError("LL chain broken: the bench order must feed every call from the previous one")
+            llctx["calls"], llctx["last_n"] = c + 1, ss.N_total
+            return
         if mode == "signal":
             buf, hdl, bases = ss.symm
             off = j * ss.N_total * 2
@@ -289,6 +323,14 @@ def run_gpu_arm(args):
             dist.all_gather_into_tensor(out.view(-1), out[:, ss.col0:ss.col0 + ss.N].reshape(-1))
 
     def finish_chain(mode: str = None):
+        if (mode or combine) == "ll":
+            c = llctx["calls"]
+            rc = lib.xbit_ll_unpack_f16(llctx["ptrs"][rank] + ((c - 1) & 1) * llctx["stride"], llctx["plain"].data_ptr(),
+                                        llctx["last_n"], llctx["state"].data_ptr(), llctx["state"].data_ptr() + 12,
+                                        torch.cuda.current_stream().cuda_stream)
+            if rc != 0:
+                raise RuntimeError(capi.last_error())
+            llctx["calls"], llctx["last_n"] = 0, 0      # the next chain starts from plain activations
         if (mode or combine) == "signal":
             sflags, fptrs, state = sig
             rc = lib.xbit_peers_wait(fptrs[rank], world, rank, state.data_ptr() + 12, torch.cuda.current_stream().cuda_stream)
@@ -306,11 +348,17 @@ def run_gpu_arm(args):
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         n = 0
+        order = [(ss, j) for ss in set_list for j in range(ss.R)]
+        if (mode or combine) == "ll" and len(set_list) > 1:
+            # every weight set once, ordered as a dependent chain: cycles (8192x8192 -> 8192x28672 -> 28672x8192),
+            # whose output width is the next call's K, then the remaining square calls (which chain with themselves)
+            cyc = min(ss.R for ss in set_list)
+            order = [(ss, j) for j in range(cyc) for ss in set_list]
+            order += [(ss, j) for ss in set_list for j in range(cyc, ss.R)]
         with torch.cuda.graph(g):
-            for ss in set_list:
-                for j in range(ss.R):
-                    launch(ss, j, mode)
-                    n += 1
+            for ss, j in order:
+                launch(ss, j, mode)
+                n += 1
             finish_chain(mode)
         return g, n
 
@@ -346,7 +394,10 @@ def run_gpu_arm(args):
     # ---- per-shape breakdown (separate graphs; same protocol) -- explains the aggregate
     per_shape = {}
     for ss in sets:
-        g1, n1 = capture([ss])
+        # (flag-in-data mode needs a dependent chain: only a square shape chains with itself; the others are
+        # timed kernel-only here and appear with their exchange in the aggregate)
+        solo_mode = "none" if (combine == "ll" and ss.K != ss.N_total) else None
+        g1, n1 = capture([ss], solo_mode)
         ms1 = timed(g1, max(3, args.steps // 4), 3) / max(3, args.steps // 4)
         us = ms1 * 1e3 / n1
         gbs = ss.bytes_call / us / 1e3
@@ -354,10 +405,14 @@ def run_gpu_arm(args):
             "us_per_call": round(us, 3), "GBps": round(gbs, 1), "frac_of_measured_peak": round(gbs / (peak * world), 4),
             "frac_of_8TBps_nominal": round(gbs / (8000.0 * world), 4), "algorithmic_bytes": ss.bytes_call,
             "rotating_sets": ss.R, "family": lib.xbit_gemv_pick_family(1, ss.K, ss.N, BITS, GROUP) if family == 0 else family}
+        if solo_mode:
+            per_shape[f"{ss.K}x{ss.N_total}"]["us_per_call_is"] = "kernel only (this shape cannot chain with itself)"
         del g1
         if world > 1:
             for mode in ("none", "nccl", "peers", "signal"):
-                if mode == combine or (mode in ("peers", "signal") and ss.symm is None) or (mode == "signal" and sig is None):
+                if mode == (solo_mode or combine) or (mode in ("peers", "signal") and ss.symm is None) or (mode == "signal" and sig is None):
+                    continue
+                if combine == "ll" and mode in ("peers", "signal"):
                     continue
                 g2, n2 = capture([ss], mode)
                 ms2 = timed(g2, max(3, args.steps // 4), 3) / max(3, args.steps // 4)
@@ -366,6 +421,8 @@ def run_gpu_arm(args):
 
     if sig is not None and int(sig[2][3].item()) != 0:
         raise RuntimeError("xbit_peers_wait timed out: a rank never published its completion flag")
+    if llctx is not None and int(llctx["state"][3].item()) != 0:
+        raise RuntimeError("xbit_ll_unpack_f16 timed out: a rank never delivered its slice")
     line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms_per_step, 5), "higher_is_better": True,
             "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
@@ -374,13 +431,14 @@ def run_gpu_arm(args):
                        "l2_policy": "inputs larger than L2: every call reads a distinct weight set, >= 1 GiB rotated per shape",
                        "launch": "one CUDA graph per step, programmatic dependent launch" + (" off" if args.no_pdl else ""),
                        "schedule": "cluster split-K" if args.no_streamk else "auto: cluster split-K; persistent stream-K where the cluster grid fills < 56 % of one wave and the matrix is >= 32 MB",
-                       "combine": {"signal": "fused: the kernel's epilogue stores its slice into every rank's buffer over NVLink and raises a per-rank completion flag; the next call's kernel awaits the flags before it reads its activations (one wait kernel at the end of a step)",
+                       "combine": {"ll": "fused, flag-in-data: the kernel's epilogue stores every pair of results into every rank's buffer over NVLink as one 8-byte {results, call number} store; the next call of the dependent chain spins on the slots it needs while staging its activations (no barrier, no fence, no wait launch; one unpack kernel at the end of a step)",
+                                   "signal": "fused: the kernel's epilogue stores its slice into every rank's buffer over NVLink and raises a per-rank completion flag; the next call's kernel awaits the flags before it reads its activations (one wait kernel at the end of a step)",
                                    "nccl": "nccl all_gather_into_tensor per call",
                                    "peers": "fused epilogue: NVLink peer stores into every rank's buffer + one symmetric-memory barrier per call",
                                    "none": "none"}[combine],
                        "parallelism": f"n-split x{world}" if world > 1 else "single"},
             "per_shape": per_shape, "clocks": clk.summary(),
-            "gpu_launches": (calls_per_step + (1 if combine == "signal" else 0)) * args.steps}
+            "gpu_launches": (calls_per_step + (1 if combine in ("signal", "ll") else 0)) * args.steps}
 
     if rank == 0:
         # roofline of the dominant (only) kernel family over the timed region
@@ -519,9 +577,10 @@ def main():
     ap.add_argument("--workload", default=None, choices=[None, *WORKLOADS])
     ap.add_argument("--family", default="auto", choices=["auto", "simt", "mma"])
     ap.add_argument("--no-pdl", action="store_true", help="do not assert static weights (no prefetch before griddepcontrol.wait)")
-    ap.add_argument("--combine", default="peers", choices=["peers", "signal", "nccl", "none"],
-                    help="N>1: how output slices are combined (fused NVLink peer stores + symmetric-memory barrier | peer stores "
-                         "+ in-kernel completion flags awaited by the next call | NCCL all-gather | kernel only)")
+    ap.add_argument("--combine", default="ll", choices=["ll", "peers", "signal", "nccl", "none"],
+                    help="N>1: how output slices are combined (fused NVLink peer stores + symmetric-memory barrier | flag-in-data "
+                         "8-byte stores consumed by the next call of a dependent chain | peer stores + in-kernel completion flags "
+                         "awaited by the next call | NCCL all-gather | kernel only)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-streamk", action="store_true", help="no workspace: cluster split-K kernel instead of the persistent stream-K schedule")
     ap.add_argument("--no-single", action="store_true")

@@ -13,6 +13,8 @@
  *                             every rank's output buffer over NVLink peer mappings.
  *   xbit_gemv_f16_peers_signal / xbit_peers_wait  <-  none either: the same with the rank
  *                             synchronisation fused into the kernel (flag per rank, no barrier launch).
+ *   xbit_gemv_f16_peers_ll / xbit_ll_unpack_f16   <-  none either: flag-in-data exchange (8-byte
+ *                             {results, call number} stores), consumed by the next call's staging.
  *
  * The reference's own `extern "C" int QbitGemv(SampleData*)` (src/gemv.cuh:22) is a benchmark
  * harness entry, not an operator ABI, and is deliberately not mirrored.
@@ -80,6 +82,9 @@ enum {
    * every rank has published as many calls as this rank has (i.e. the previous N-split call is
    * complete everywhere): the gather of call i is awaited inside call i+1, no wait launch. */
   XBIT_GEMV_FLAG_WAIT_PEERS = 0x200,
+  /* xbit_gemv_f16_peers_ll only: a_f16 is not a plain fp16 matrix but the LL buffer that the
+   * previous xbit_gemv_f16_peers_ll call of every rank filled ([M][K/2] 8-byte slots). */
+  XBIT_GEMV_FLAG_A_IS_LL = 0x400,
   XBIT_GEMV_FAMILY_MASK = 0xFF
 };
 
@@ -166,6 +171,27 @@ XBIT_API int xbit_gemv_f16_peers_signal(const void* a_f16, const int32_t* qweigh
  * set to 1 if a peer did not arrive within about 2 s -- the kernel never hangs. */
 XBIT_API int xbit_peers_wait(const void* local_flags, int world, int rank, void* timeout_flag,
                              xbit_stream_t stream);
+
+/* Flag-in-data ("LL") form of the N-split exchange, for chains of dependent GEMVs (a decode
+ * step): no barrier, no fence, no wait launch.  peer_ll_out[r] is rank r's LL result buffer as
+ * mapped in THIS process: M * out_row_stride / 2 slots of 8 bytes, slot = {two fp16 results,
+ * call number}, in peer-mapped memory, zero-initialised once.  The epilogue stores every pair of
+ * this rank's results into every rank's buffer with one 8-byte store each; local_state (two
+ * zero-initialised uint32 in ordinary device memory) counts this rank's calls.  The consumer is
+ * either the next xbit_gemv_f16_peers_ll call with XBIT_GEMV_FLAG_A_IS_LL (its activation staging
+ * spins on exactly the slots it needs, as they arrive from the ranks) or xbit_ll_unpack_f16.
+ * Use two LL buffers alternately along a chain; every rank must issue the same sequence of calls.
+ * Same restrictions as xbit_gemv_f16_peers_signal; out_row_stride and col_offset must be even. */
+XBIT_API int xbit_gemv_f16_peers_ll(const void* a_f16_or_ll, const int32_t* qweight, const void* scales_f16,
+                                    const int32_t* qzeros, void* const* peer_ll_out_host_array,
+                                    void* local_state, int world, int rank, int M, int K, int N_local,
+                                    int bits, int groupsize, int add_zero_bias, int64_t out_row_stride,
+                                    int64_t col_offset, int family, xbit_stream_t stream);
+
+/* LL buffer -> plain fp16 [n_elems] once every slot carries this rank's current call number
+ * (local_state[1]).  n_elems must be even.  timeout_flag as in xbit_peers_wait. */
+XBIT_API int xbit_ll_unpack_f16(const void* ll_in, void* out_f16, int64_t n_elems, const void* local_state,
+                                void* timeout_flag, xbit_stream_t stream);
 
 /* Host-buffer convenience used for end-to-end measurement: activations come from (pinned) host
  * memory and the result goes back to host memory; weights stay resident on the device.

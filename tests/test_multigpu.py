@@ -73,6 +73,59 @@ def _chain(rank, world, dev, X):
     return not why
 
 
+def _chain_ll(rank, world, dev, X):
+    """Three dependent N-split calls in the flag-in-data form: every call stores {results, call number} slots
+    into every rank's LL buffer, the next call's activation staging spins on the slots it needs; two LL
+    buffers alternate; the last result is unpacked to plain fp16."""
+    import ctypes
+    import torch.distributed._symmetric_memory as symm_mem
+    from xbitops_b200 import capi
+    from xbitops_b200.sharded import shard_columns
+    lib = capi.load()
+    K = N = 4096
+    qw, s, qz, a = synth.make_inputs(K, N, 4, 128, M=2, seed=78)
+    d = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)  # noqa: E731
+    tq, ts, tz = d(qw), d((s.view(np.int16))).view(torch.float16) * 0.02, d(qz)
+    ta = d(a.view(np.int16)).view(torch.float16)
+    M = ta.shape[0]
+    ref = ta
+    for _ in range(3):
+        ref = X.gemv(ref, tq, ts, tz, 128, 4, K, 1)
+    q, sc, z = shard_columns(tq, ts, tz, 4, world, rank)
+    name = dist.group.WORLD.group_name
+    ll = symm_mem.empty((2, M, N), dtype=torch.int32, device=dev)       # 8-byte slot per pair of results
+    ll.zero_()
+    hdl = symm_mem.rendezvous(ll, name)
+    state = torch.zeros(4, dtype=torch.int32, device=dev)
+    out = torch.empty((M, N), dtype=torch.float16, device=dev)
+    torch.cuda.synchronize()
+    hdl.barrier()
+    st = torch.cuda.current_stream().cuda_stream
+    n_local = N // world
+    bufsz = M * N * 4
+    src, flag = ta.data_ptr(), 0
+    for call in range(3):
+        k = call & 1
+        outs = (ctypes.c_void_p * world)(*[int(p) + k * bufsz for p in hdl.buffer_ptrs])
+        capi.check(lib.xbit_gemv_f16_peers_ll(src, q.data_ptr(), sc.data_ptr(), z.data_ptr(), outs, state.data_ptr(), world, rank,
+                                              M, K, n_local, 4, 128, 1, N, rank * n_local, capi.GEMV_AUTO | flag, st))
+        src, flag = int(hdl.buffer_ptrs[rank]) + k * bufsz, capi.GEMV_FLAG_A_IS_LL
+    capi.check(lib.xbit_ll_unpack_f16(src, out.data_ptr(), M * N, state.data_ptr(), state.data_ptr() + 12, st))
+    torch.cuda.synchronize()
+    why = []
+    if int(state[3].item()) != 0:
+        why.append("unpack timed out")
+    if int(state[1].item()) != 3:
+        why.append(f"call counter {int(state[1].item())}")
+    e = float((out.double() - ref.double()).abs().max()) / float(ref.double().abs().max())
+    if not e < 6e-3:
+        why.append(f"chain error {e:.3e}")
+    hdl.barrier()
+    if why:
+        print(f"[rank {rank}] LL chain test: " + "; ".join(why), flush=True)
+    return not why
+
+
 def _worker(rank, world, port, combine, ret):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
@@ -81,6 +134,9 @@ def _worker(rank, world, port, combine, ret):
     try:
         import xbitops_b200 as X
         from xbitops_b200.sharded import ShardedQLinear, shard_columns
+        if combine == "ll":
+            ret[rank] = _chain_ll(rank, world, dev, X)
+            return
         ok = True
         for (K, N, M) in ((8192, 8192, 1), (4096, 1024, 3)):
             qw, s, qz, a = synth.make_inputs(K, N, 4, 128, M=M, seed=K + M)
@@ -109,7 +165,7 @@ def _worker(rank, world, port, combine, ret):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("combine", ("nccl", "peers", "signal"))
+@pytest.mark.parametrize("combine", ("nccl", "peers", "signal", "ll"))
 def test_sharded_gemv_two_gpus(combine):
     if not torch.cuda.is_available():
         pytest.fail("gpu-marked test without a CUDA device")

@@ -12,6 +12,7 @@ XBIT_OK = 0
 GEMV_AUTO, GEMV_SIMT, GEMV_MMA, GEMV_GENERIC, GEMV_TCGEN05 = 0, 1, 2, 3, 4
 GEMV_FLAG_STATIC_WEIGHTS = 0x100
 GEMV_FLAG_WAIT_PEERS = 0x200
+GEMV_FLAG_A_IS_LL = 0x400
 
 _vp, _i, _i64, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_size_t
 
@@ -31,6 +32,9 @@ SIGNATURES = {
     "xbit_gemv_f16_peers_signal": (_i, [_vp, _vp, _vp, _vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp), _vp, _i, _i, _i, _i, _i,
                                         _i, _i, _i, _i64, _i64, _i, _vp]),
     "xbit_peers_wait": (_i, [_vp, _i, _i, _vp, _vp]),
+    "xbit_gemv_f16_peers_ll": (_i, [_vp, _vp, _vp, _vp, ctypes.POINTER(_vp), _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i64, _i64,
+                                    _i, _vp]),
+    "xbit_ll_unpack_f16": (_i, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "xbit_gemv_f16_host": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
 }
 

@@ -526,6 +526,24 @@ __device__ __forceinline__ bool peers_poll(const unsigned int* flags, int world,
   return ok;
 }
 
+// Flag-in-data ("LL") exchange helpers.  A slot is 8 bytes {two fp16 results, call number}, written with
+// ONE 8-byte store (atomic on NVLink), so the flag validates its own data and nobody needs a fence.
+__device__ __forceinline__ void ll_store(unsigned long long* slot, uint32_t data, uint32_t epoch) {
+  asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(slot), "r"(data), "r"(epoch) : "memory");
+}
+// 8 consecutive halves = 4 slots = 32 bytes; spins until all four carry `epoch` (~2 s guard, then garbage)
+__device__ __forceinline__ uint4 ll_load8(const unsigned long long* slots, uint32_t epoch) {
+  uint4 q0, q1;
+  const long long c0 = clock64();
+  for (unsigned int n = 1;; ++n) {
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q0.x), "=r"(q0.y), "=r"(q0.z), "=r"(q0.w) : "l"(slots) : "memory");
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q1.x), "=r"(q1.y), "=r"(q1.z), "=r"(q1.w) : "l"(slots + 2) : "memory");
+    if (q0.y == epoch && q0.w == epoch && q1.y == epoch && q1.w == epoch) break;
+    if ((n & 1023u) == 0 && clock64() - c0 > 4000000000ll) break;
+  }
+  return make_uint4(q0.x, q0.z, q1.x, q1.z);
+}
+
 // tools/trace.py: wall-clock stamps of one CTA's phases (debug only; a.trace is null in production)
 __device__ __forceinline__ void trace_stamp(const GemvArgs& a, int slot) {
   if (a.trace) {
@@ -657,12 +675,16 @@ gemv_w4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
       const int vecs_per_row = (b1 - b0) * 16;      // 8-half vectors (a multiple of 16); a scale group = 4*UPG consecutive vectors
       for (int m = 0; m < a.M; ++m) {
         const uint4* arow = reinterpret_cast<const uint4*>(a.a + (size_t)m * a.K + b0 * 128);
+        // LL form: row m of the previous call's result, 2 halves per 8-byte slot; its call number = calls completed so far
+        const unsigned long long* ll_row = reinterpret_cast<const unsigned long long*>(a.a) + (((size_t)m * a.K + b0 * 128) >> 1);
+        const uint32_t ll_epoch = a.a_is_ll ? a.sig_state[1] : 0u;
         __half* srow = act_sm + (size_t)m * pitch;
         for (int v = tid; v - lane < vecs_per_row; v += kConsumerThreads) {      // warp-uniform trip count (shuffles below)
           const bool ok = v < vecs_per_row;
           uint4 val = make_uint4(0, 0, 0, 0);
           if (ok) {
-            val = __ldcg(arow + v);                 // L2 only: the row may just have been written by peer GPUs
+            if (a.a_is_ll) val = ll_load8(ll_row + 4 * (size_t)v, ll_epoch);   // arrives slot by slot from every rank
+            else           val = __ldcg(arow + v);                            // L2 only: may just have been written by peer GPUs
             *reinterpret_cast<uint4*>(srow + v * 8) = kV2 ? permute_act8_v2(val) : permute_act8<kMma>(val);
           }
           if constexpr (kMma) {
@@ -774,8 +796,7 @@ gemv_w4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
     if (tid == 0) trace_stamp(a, 6);
     if (split != 0) return;
   }
-  for (int o = tid; o < nout; o += kW4Threads) {
-    const int m = o / NT, col = o - m * NT;
+  auto tile_sum = [&](int o) {
     float v = 0.f;
     if (clustered) {
       for (int s = 0; s < a.splits; ++s) v += clus_sm[s * nout + o];
@@ -783,6 +804,30 @@ gemv_w4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
 #pragma unroll
       for (int w = 0; w < WK; ++w) v += red_sm[w * nout + o];
     }
+    return v;
+  };
+  if (a.ll_out) {
+    // flag-in-data all-gather: each pair of results goes to every rank as one {half2, call number} store
+    const uint32_t epoch = a.sig_state[1] + 1u;     // stable until the last tile of this call bumps it below
+    for (int o2 = tid; o2 < (nout >> 1); o2 += kW4Threads) {
+      const int m = o2 / (NT / 2), col = 2 * (o2 - m * (NT / 2));
+      if (col < cw) {
+        const __half2 h2 = __floats2half2_rn(tile_sum(m * NT + col), tile_sum(m * NT + col + 1));
+        const size_t slot = ((size_t)m * a.ldo + a.col_offset + n_cta + col) >> 1;
+        for (int p = 0; p < a.world; ++p) ll_store(reinterpret_cast<unsigned long long*>(a.out[p]) + slot, h22u(h2), epoch);
+      }
+    }
+    __syncthreads();
+    if (tid == 0 && atomicAdd(a.sig_state, 1u) == gridDim.x - 1) {   // last tile: the call is complete on this rank
+      a.sig_state[0] = 0u;
+      a.sig_state[1] = epoch;
+    }
+    if (tid == 0) trace_stamp(a, 7);
+    return;
+  }
+  for (int o = tid; o < nout; o += kW4Threads) {
+    const int m = o / NT, col = o - m * NT;
+    const float v = tile_sum(o);
     if (col < cw) {
       const __half h = __float2half_rn(v);
       const size_t off = (size_t)m * a.ldo + a.col_offset + n_cta + col;
@@ -1970,6 +2015,43 @@ cudaError_t launch_peers_wait(const unsigned int* flags, int world, int rank, un
   cfg.attrs = attrs;
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, peers_wait_kernel, flags, world, rank, timeout_flag);
+}
+
+// ---- LL buffer -> plain fp16 (the consumer at the end of a chain): spins on each slot's call number
+__global__ void ll_unpack_kernel(const unsigned long long* __restrict__ ll, uint32_t* __restrict__ out, long long n_pairs,
+                                 const unsigned int* __restrict__ state, unsigned int* timeout_flag) {
+  griddep_launch_dependents();
+  griddep_wait();                                   // this rank's own call has completed: state[1] is its number
+  const uint32_t epoch = state[1];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_pairs; i += (long long)gridDim.x * blockDim.x) {
+    uint32_t d, f;
+    const long long c0 = clock64();
+    for (unsigned int n = 1;; ++n) {
+      asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(d), "=r"(f) : "l"(ll + i) : "memory");
+      if (f == epoch) break;
+      if ((n & 1023u) == 0 && clock64() - c0 > 4000000000ll) {
+        if (timeout_flag) *timeout_flag = 1u;
+        break;
+      }
+    }
+    out[i] = d;
+  }
+}
+
+cudaError_t launch_ll_unpack(const void* ll_in, void* out_f16, long long n_pairs, const unsigned int* state, unsigned int* timeout_flag,
+                             cudaStream_t stream) {
+  cudaLaunchConfig_t cfg = {};
+  const long long blocks = (n_pairs + 255) / 256;
+  cfg.gridDim = dim3((unsigned)(blocks < 1 ? 1 : (blocks > 128 ? 128 : blocks)), 1, 1);
+  cfg.blockDim = dim3(256, 1, 1);
+  cfg.stream = stream;
+  cudaLaunchAttribute attrs[1];
+  attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attrs[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, ll_unpack_kernel, reinterpret_cast<const unsigned long long*>(ll_in),
+                            reinterpret_cast<uint32_t*>(out_f16), n_pairs, state, timeout_flag);
 }
 
 // ---- host-buffer entry: pull activation rows out of page-locked host memory with a kernel instead of a

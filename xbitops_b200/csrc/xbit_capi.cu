@@ -113,9 +113,10 @@ static bool use_streamk(const xbit::GemvArgs& g, int family, void* workspace, si
 }
 
 struct PeerSignal {
-  void* const* flags;   // world peer-mapped flag arrays
-  void* state;          // local uint32[3]
+  void* const* flags;   // world peer-mapped flag arrays (null in the LL form)
+  void* state;          // local uint32 counters
   int rank;
+  bool ll;              // flag-in-data form: outs are LL buffers
 };
 
 static int gemv_impl(const void* a_f16, const int32_t* qweight, const void* scales_f16, const int32_t* qzeros,
@@ -150,7 +151,8 @@ static int gemv_impl(const void* a_f16, const int32_t* qweight, const void* scal
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (sig) {
     // the signal is raised by the cluster split-K kernel of the tensor-core family, one launch per call
-    if (!sig->flags || !sig->state || sig->rank < 0 || sig->rank >= world) return fail(XBIT_EINVAL, "bad peer signal arguments");
+    if ((!sig->ll && !sig->flags) || !sig->state || sig->rank < 0 || sig->rank >= world) return fail(XBIT_EINVAL, "bad peer signal arguments");
+    if (sig->ll && ((out_row_stride | col_offset) & 1)) return fail(XBIT_EINVAL, "the LL form needs even out_row_stride and col_offset");
     if (family_req != XBIT_GEMV_AUTO && family_req != XBIT_GEMV_MMA) return fail(XBIT_EINVAL, "the fused signal needs the AUTO or MMA family");
     g.M = M;
     if (M > 16 || !xbit::gemv_w4_supported(g))
@@ -158,13 +160,15 @@ static int gemv_impl(const void* a_f16, const int32_t* qweight, const void* scal
     family_req = XBIT_GEMV_MMA;
     workspace = nullptr;          // no stream-K here: its tiles are not stored by one CTA each
     workspace_bytes = 0;
-    for (int p = 0; p < world; ++p) {
+    for (int p = 0; p < world && !sig->ll; ++p) {
       if (!sig->flags[p]) return fail(XBIT_EINVAL, "null flag pointer (rank %d)", p);
       g.sig_flags[p] = reinterpret_cast<unsigned int*>(sig->flags[p]);
     }
     g.sig_state = reinterpret_cast<unsigned int*>(sig->state);
     g.sig_rank = sig->rank;
-    g.sig_wait = (family_and_flags & XBIT_GEMV_FLAG_WAIT_PEERS) ? 1 : 0;
+    g.sig_wait = (!sig->ll && (family_and_flags & XBIT_GEMV_FLAG_WAIT_PEERS)) ? 1 : 0;
+    g.ll_out = sig->ll ? 1 : 0;
+    g.a_is_ll = (sig->ll && (family_and_flags & XBIT_GEMV_FLAG_A_IS_LL)) ? 1 : 0;
   }
 
   // rows are processed in slabs the chosen family can take (weights are re-read per slab only
@@ -255,9 +259,29 @@ int xbit_gemv_f16_peers_signal(const void* a_f16, const int32_t* qweight, const 
                                void* const* peer_out_host_array, void* const* peer_flags_host_array, void* local_state,
                                int world, int rank, int M, int K, int N_local, int bits, int groupsize, int add_zero_bias,
                                int64_t out_row_stride, int64_t col_offset, int family, xbit_stream_t stream) {
-  const PeerSignal sig = {peer_flags_host_array, local_state, rank};
+  const PeerSignal sig = {peer_flags_host_array, local_state, rank, false};
   return gemv_impl(a_f16, qweight, scales_f16, qzeros, peer_out_host_array, world, M, K, N_local, bits, groupsize,
                    add_zero_bias, out_row_stride, col_offset, family, nullptr, 0, stream, &sig);
+}
+
+int xbit_gemv_f16_peers_ll(const void* a_f16_or_ll, const int32_t* qweight, const void* scales_f16, const int32_t* qzeros,
+                           void* const* peer_ll_out_host_array, void* local_state, int world, int rank, int M, int K,
+                           int N_local, int bits, int groupsize, int add_zero_bias, int64_t out_row_stride, int64_t col_offset,
+                           int family, xbit_stream_t stream) {
+  const PeerSignal sig = {nullptr, local_state, rank, true};
+  return gemv_impl(a_f16_or_ll, qweight, scales_f16, qzeros, peer_ll_out_host_array, world, M, K, N_local, bits, groupsize,
+                   add_zero_bias, out_row_stride, col_offset, family, nullptr, 0, stream, &sig);
+}
+
+int xbit_ll_unpack_f16(const void* ll_in, void* out_f16, int64_t n_elems, const void* local_state, void* timeout_flag,
+                       xbit_stream_t stream) {
+  g_err[0] = 0;
+  if (!ll_in || !out_f16 || !local_state) return fail(XBIT_EINVAL, "null pointer");
+  if (n_elems < 2 || (n_elems & 1)) return fail(XBIT_EINVAL, "n_elems must be even and >= 2, got %lld", (long long)n_elems);
+  const cudaError_t e = xbit::launch_ll_unpack(ll_in, out_f16, n_elems / 2, reinterpret_cast<const unsigned int*>(local_state),
+                                               reinterpret_cast<unsigned int*>(timeout_flag), reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "xbit_ll_unpack_f16 launch");
+  return XBIT_OK;
 }
 
 int xbit_peers_wait(const void* local_flags, int world, int rank, void* timeout_flag, xbit_stream_t stream) {
