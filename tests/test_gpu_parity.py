@@ -342,6 +342,51 @@ def test_host_buffer_entry_point(dev, c_oracle):
     assert np.array_equal(hp, ho.numpy())
 
 
+def test_flag_in_data_chain_single_gpu(dev):
+    """xbit_gemv_f16_peers_ll / xbit_ll_unpack_f16 with world = 1: two dependent calls, the second one reads the
+    first one's {results, call number} slots while staging its activations (the 2-GPU version is in
+    test_multigpu.py); and the signal form with its wait kernel."""
+    import ctypes
+    K = N = 2048
+    M = 3
+    qw, s, qz, a = synth.make_inputs(K, N, 4, 128, M=M, seed=5)
+    tq, ts, tz, ta = ti(qw, dev), t16(s, dev) * 0.05, ti(qz, dev), t16(a, dev)
+    y1 = X.gemv(ta, tq, ts, tz, 128, 4, K, 1)
+    y2 = X.gemv(y1, tq, ts, tz, 128, 4, K, 1)
+    lib = capi.load()
+    st = torch.cuda.current_stream().cuda_stream
+    ll = torch.zeros((2, M, N), dtype=torch.int32, device=dev)
+    state = torch.zeros(4, dtype=torch.int32, device=dev)
+    out = torch.empty((M, N), dtype=torch.float16, device=dev)
+    for call, (src, flag) in enumerate(((ta.data_ptr(), 0), (ll[0].data_ptr(), capi.GEMV_FLAG_A_IS_LL))):
+        outs = (ctypes.c_void_p * 1)(ll[call].data_ptr())
+        capi.check(lib.xbit_gemv_f16_peers_ll(src, tq.data_ptr(), ts.data_ptr(), tz.data_ptr(), outs, state.data_ptr(), 1, 0, M, K, N,
+                                              4, 128, 1, N, 0, capi.GEMV_AUTO | flag, st))
+    capi.check(lib.xbit_ll_unpack_f16(ll[1].data_ptr(), out.data_ptr(), M * N, state.data_ptr(), state.data_ptr() + 12, st))
+    torch.cuda.synchronize()
+    assert state.tolist() == [0, 2, 0, 0]                        # tile counter reset, two calls counted, no timeout
+    slots = ll[0].view(M, N // 2, 2)
+    assert bool((slots[..., 1] == 1).all()) and bool((ll[1].view(M, N // 2, 2)[..., 1] == 2).all())
+    assert torch.equal(slots[..., 0].contiguous().view(torch.float16).view(M, N), y1)      # same kernel, same sums
+    assert torch.equal(out, y2)
+    # restrictions are reported, not executed
+    rc = lib.xbit_gemv_f16_peers_ll(ta.data_ptr(), tq.data_ptr(), ts.data_ptr(), tz.data_ptr(), (ctypes.c_void_p * 1)(ll[0].data_ptr()),
+                                    state.data_ptr(), 1, 0, M, K, N, 3, 128, 1, N, 0, capi.GEMV_AUTO, st)
+    assert rc == -1 and "bits" in capi.last_error()          # XBIT_EINVAL
+    # signal form, world = 1: the flag carries the call count, the wait kernel returns at once
+    flags = torch.zeros(8, dtype=torch.int32, device=dev)
+    state2 = torch.zeros(4, dtype=torch.int32, device=dev)
+    y = torch.empty((M, N), dtype=torch.float16, device=dev)
+    for _ in range(2):
+        capi.check(lib.xbit_gemv_f16_peers_signal(ta.data_ptr(), tq.data_ptr(), ts.data_ptr(), tz.data_ptr(),
+                                                  (ctypes.c_void_p * 1)(y.data_ptr()), (ctypes.c_void_p * 1)(flags.data_ptr()),
+                                                  state2.data_ptr(), 1, 0, M, K, N, 4, 128, 1, N, 0,
+                                                  capi.GEMV_AUTO | capi.GEMV_FLAG_WAIT_PEERS, st))
+    capi.check(lib.xbit_peers_wait(flags.data_ptr(), 1, 0, state2.data_ptr() + 12, st))
+    torch.cuda.synchronize()
+    assert int(flags[0]) == 2 and state2.tolist() == [0, 2, 0, 0] and torch.equal(y, y1)
+
+
 def test_peer_entry_point_single_process(dev, c_oracle):
     """xbit_gemv_f16_peers with world=2 emulated inside one process: two 'rank' buffers on the same
     device, each shard's epilogue stores its slice into both (multi-process NVLink is in test_multigpu)."""
