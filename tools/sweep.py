@@ -82,7 +82,7 @@ def main():
             os.environ["XBIT_GEMV_HYBRID"] = str(hyb)
             for wc in (0, 2, 4, 8):
                 row = f"   {name} wc={wc if wc else 'A'}:"
-                for splits in ((0,) if wc == 0 else (1, 2, 4, 8)):
+                for splits in ((0,) if wc == 0 else (1, 2, 3, 4, 5, 6, 7, 8)):
                     os.environ["XBIT_GEMV_SPLITS"] = str(splits)
                     os.environ["XBIT_GEMV_WC"] = str(wc)
                     flags = capi.GEMV_FLAG_STATIC_WEIGHTS

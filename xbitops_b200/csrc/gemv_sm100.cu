@@ -39,6 +39,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <math.h>
 #include <string.h>
 
 #include <map>
@@ -1603,66 +1604,6 @@ static void apply_debug_knobs(GemvArgs& a) {
   }
 }
 
-// Decomposition (measured: profiles/r01_v6_planner_sweep.log).  The consumer instruction stream
-// bounds an SM and a lone 8-warp CTA does not saturate it, so what counts is how close the CTA count
-// comes to two per SM in ONE wave; at equal counts fewer K splits win (no DSMEM reduction), tiles of
-// 128 columns win for long K slices (512-byte DRAM runs), and a CTA wants at least 1024 k (4 stages).
-// Ring depth: 3 stages when a CTA streams only a few (a third CTA slot per SM stays free, so more of
-// the NEXT launch's CTAs are resident early and prefetch), up to 5 for long streams.
-static bool plan_w4(GemvArgs& a, int mt, int upg, W4Plan& p, double* score_out = nullptr) {
-  const int sms = device_sm_count();
-  const int nblocks = a.K / 128;
-  const int cap = 2 * sms;
-  const int env_wc = env_int("XBIT_GEMV_WC", 0);     // tuning knobs for tools/sweep.py
-  const int env_splits = env_int("XBIT_GEMV_SPLITS", 0);
-  const int env_ring = env_int("XBIT_GEMV_RING", 0);
-  double best = -1.0;
-  bool found = false;
-  for (int wc = 1; wc <= 8; wc *= 2) {
-    if (env_wc ? wc != env_wc : (wc == 1 && a.N >= 64)) continue;
-    if (a.N < 32 * wc && wc > 1) continue;
-    const int tiles = (a.N + 32 * wc - 1) / (32 * wc);
-    const int wk = 8 / wc;
-    for (int splits = 1; splits <= 8; splits *= 2) {
-      if (env_splits && splits != env_splits) continue;
-      const int bps = (nblocks + splits - 1) / splits;
-      if (splits > 1 && (splits - 1) * bps >= nblocks) continue;       // an empty split
-      const int stages = (bps + wk - 1) / wk;
-      const long long ctas = (long long)tiles * splits;
-      const int ring = env_ring >= 2 && env_ring <= kMaxStages ? env_ring : (stages >= 24 ? 5 : (stages >= 12 ? 4 : 3));
-      const size_t smem = w4_smem_bytes(upg, wc, mt, a.M, bps, splits, ring);
-      if (smem > kMaxDynSmem) continue;                                 // K slice too long for the staged activations at this M
-      // staged activations grow with M: above half an SM only one CTA is resident and the SM runs at
-      // about half its rate (a lone 8-warp CTA does not saturate the issue slots)
-      const bool two_per_sm = smem <= 113 * 1024;
-      const long long slots = two_per_sm ? cap : cap / 2;
-      const long long waves = (ctas + slots - 1) / slots;
-      double score = (double)ctas / (double)(waves * slots);
-      if (!two_per_sm) score *= 0.6;
-      if (waves > 1) score *= 0.75;                                      // every extra wave serialises a prologue and an epilogue
-      if (bps * 128 < 1024) score *= 0.8;
-      for (int sp = splits; sp > 1; sp >>= 1) score *= 0.98;
-      score *= wc == 4 ? 1.0 : (wc == 2 ? (bps * 128 >= 4096 ? 0.94 : 0.99) : 0.98);
-      if (score > best) {
-        best = score;
-        found = true;
-        p.wc = wc;
-        p.splits = splits;
-        p.blocks_per_split = bps;
-        p.smem = smem;
-        p.grid = dim3((unsigned)tiles, (unsigned)splits, 1);
-        a.ring = ring;
-      }
-    }
-  }
-  if (!found) return false;
-  if (score_out) *score_out = best;
-  a.splits = p.splits;
-  a.units_per_split = p.blocks_per_split;
-  a.chunk_units = 0;
-  return true;
-}
-
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1777,6 +1718,146 @@ static W4Kernel pick_w4_kernel(int upg, int wc) {
 #undef XBIT_W4_CASE
   return nullptr;
 }
+
+// CTA slots the device really offers to clusters of `splits` CTAs of this kernel (cached per kernel, cluster size and
+// shared-memory size): clusters are placed inside one GPC, so the answer is below 2 * #SMs for awkward sizes.
+static long long max_active_cluster_ctas(W4Kernel kern, int splits, size_t smem) {
+  using Key = std::tuple<int, const void*, int, size_t>;
+  static std::mutex mu;
+  static auto* cache = new std::map<Key, long long>();
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  const Key key(dev, reinterpret_cast<const void*>(kern), splits, smem);
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache->find(key);
+    if (it != cache->end()) return it->second;
+  }
+  long long result = -1;
+  if (ensure_max_dyn_smem(reinterpret_cast<const void*>(kern)) == cudaSuccess) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(1, (unsigned)splits, 1);
+    cfg.blockDim = dim3(kW4Threads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = (unsigned)splits;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&clusters, reinterpret_cast<const void*>(kern), &cfg) == cudaSuccess) result = (long long)clusters * splits;
+    else cudaGetLastError();
+  }
+  std::lock_guard<std::mutex> lock(mu);
+  (*cache)[key] = result;
+  return result;
+}
+
+// Decomposition (measured: profiles/r01_v6_planner_sweep.log).  The consumer instruction stream
+// bounds an SM and a lone 8-warp CTA does not saturate it, so what counts is how close the CTA count
+// comes to two per SM in ONE wave; at equal counts fewer K splits win (no DSMEM reduction), tiles of
+// 128 columns win for long K slices (512-byte DRAM runs), and a CTA wants at least 1024 k (4 stages).
+// Ring depth: 3 stages when a CTA streams only a few (a third CTA slot per SM stays free, so more of
+// the NEXT launch's CTAs are resident early and prefetch), up to 5 for long streams.
+struct W4PlanEntry {
+  W4Plan plan;
+  int ring;
+  double score;
+  bool ok;
+};
+
+static bool plan_w4(GemvArgs& a, int mt, int upg, W4Plan& p, double* score_out = nullptr) {
+  const int sms = device_sm_count();
+  const int nblocks = a.K / 128;
+  const int cap = 2 * sms;
+  const int env_wc = env_int("XBIT_GEMV_WC", 0);     // tuning knobs for tools/sweep.py
+  const int env_splits = env_int("XBIT_GEMV_SPLITS", 0);
+  const int env_ring = env_int("XBIT_GEMV_RING", 0);
+  // the decomposition is a pure function of these: computed once per shape
+  using Key = std::tuple<int, int, int, int, int, int, int, int, int>;
+  static std::mutex mu;
+  static auto* cache = new std::map<Key, W4PlanEntry>();
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const Key key(dev, a.M, a.K, a.N, upg, mt, env_wc, env_splits, env_ring);
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache->find(key);
+    if (it != cache->end()) {
+      const W4PlanEntry& e = it->second;
+      if (!e.ok) return false;
+      p = e.plan;
+      a.ring = e.ring;
+      a.splits = p.splits;
+      a.units_per_split = p.blocks_per_split;
+      a.chunk_units = 0;
+      if (score_out) *score_out = e.score;
+      return true;
+    }
+  }
+  double best = -1.0;
+  bool found = false;
+  for (int wc = 1; wc <= 8; wc *= 2) {
+    if (env_wc ? wc != env_wc : (wc == 1 && a.N >= 64)) continue;
+    if (a.N < 32 * wc && wc > 1) continue;
+    const int tiles = (a.N + 32 * wc - 1) / (32 * wc);
+    const int wk = 8 / wc;
+    for (int splits = 1; splits <= 8; ++splits) {
+      // cluster sizes 1, 2, 3, 4, 8: 3 fills shapes like N = 11008 (86 tiles -> 258 CTAs) that powers of two leave
+      // at 58 %; 5, 6 and 7 were measured slower than their CTA count suggests (profiles/r01_v6_planner_sweep_odd_splits.log)
+      if (env_splits ? splits != env_splits : (splits >= 5 && splits <= 7)) continue;
+      const int bps = (nblocks + splits - 1) / splits;
+      if (splits > 1 && (splits - 1) * bps >= nblocks) continue;       // an empty split
+      const int stages = (bps + wk - 1) / wk;
+      const long long ctas = (long long)tiles * splits;
+      const int ring = env_ring >= 2 && env_ring <= kMaxStages ? env_ring : (stages >= 24 ? 5 : (stages >= 12 ? 4 : 3));
+      const size_t smem = w4_smem_bytes(upg, wc, mt, a.M, bps, splits, ring);
+      if (smem > kMaxDynSmem) continue;                                 // K slice too long for the staged activations at this M
+      // staged activations grow with M: above half an SM only one CTA is resident and the SM runs at
+      // about half its rate (a lone 8-warp CTA does not saturate the issue slots).  Clusters must be
+      // co-scheduled inside a GPC: the driver's occupancy query gives the real number of CTA slots
+      // (odd cluster sizes fragment the GPCs: e.g. 5-CTA clusters of 7168x7168 ran in two waves).
+      const bool two_per_sm = smem <= 113 * 1024;
+      long long slots = two_per_sm ? cap : cap / 2;
+      if (splits > 1) {
+        const W4Kernel kern = mt == 0 ? pick_w4_kernel<0, 0>(upg, wc) : (mt == 1 ? pick_w4_kernel<1, 0>(upg, wc) : pick_w4_kernel<2, 0>(upg, wc));
+        const long long real = max_active_cluster_ctas(kern, splits, smem);
+        if (real > 0 && real < slots) slots = real;
+      }
+      const long long waves = (ctas + slots - 1) / slots;
+      double score = (double)ctas / (double)(waves * slots) * ((double)slots / (double)cap);   // fill of the whole machine
+      if (!two_per_sm) score *= 1.2;                                                            // (cap/2 slots already halve it)
+      if (waves > 1) score *= 0.75;                                      // every extra wave serialises a prologue and an epilogue
+      if (bps * 128 < 1024) score *= 0.8;
+      score *= 1.0 - 0.02 * log2((double)splits);                        // at equal fill fewer splits win (smaller DSMEM reduction)
+      score *= wc == 4 ? 1.0 : (wc == 2 ? (bps * 128 >= 4096 ? 0.94 : 0.99) : 0.98);
+      if (score > best) {
+        best = score;
+        found = true;
+        p.wc = wc;
+        p.splits = splits;
+        p.blocks_per_split = bps;
+        p.smem = smem;
+        p.grid = dim3((unsigned)tiles, (unsigned)splits, 1);
+        a.ring = ring;
+      }
+    }
+  }
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    if (cache->size() >= 4096) cache->clear();
+    (*cache)[key] = W4PlanEntry{p, a.ring, best, found};
+  }
+  if (!found) return false;
+  if (score_out) *score_out = best;
+  a.splits = p.splits;
+  a.units_per_split = p.blocks_per_split;
+  a.chunk_units = 0;
+  return true;
+}
+
 
 cudaError_t launch_gemv_w4_simt(GemvArgs a, cudaStream_t stream) {
   if (a.M != 1) return cudaErrorInvalidValue;
