@@ -1,4 +1,4 @@
-"""Developer sweep: cluster split-K schedule vs the persistent stream-K schedule (1 or 2 CTAs per SM).
+"""Developer sweep: cluster split-K schedule vs the persistent stream-K schedule.
     python tools/sk_compare.py [K N]..."""
 import os
 import sys
@@ -20,9 +20,8 @@ def main():
         print(f"== {K}x{N} {nbytes/1e6:.1f} MB R={R} roofline {nbytes/PEAK/1e3:.2f} us")
         for fam, name in ((capi.GEMV_MMA, "mma"),):
             row = f"   {name}:"
-            for label, sk, per_sm, ring in (("cluster", 0, 0, 0), ("sk", 1, 0, 0), ("sk-p200", 1, 200, 0), ("sk-p400", 1, 400, 0), ("sk-p800", 1, 800, 0)):
+            for label, sk, ring in (("cluster", 0, 0), ("stream-K", 1, 0), ("stream-K ring 4", 1, 4), ("stream-K ring 6", 1, 6)):
                 os.environ["XBIT_GEMV_STREAMK"] = str(sk)
-                os.environ["XBIT_GEMV_PACE"] = str(per_sm)
                 os.environ["XBIT_GEMV_RING"] = str(ring)
 
                 def fn(i):
