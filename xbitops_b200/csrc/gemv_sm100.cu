@@ -8,28 +8,34 @@
 // CTA = 64 columns x all of K, so N = 4096 gives 64 CTAs on 148 SMs; 8 bytes of weights in flight
 // per thread; one I2F per weight; M > 1 re-reads the weights M times; legacy default stream.
 //
-// Kernels in this file:
+// Kernels in this file (DESIGN.md 4.2 has the measurements behind every choice):
 //
-//   gemv_w4_kernel<MT, UPG, WC>   the W4 path (bits == 4, groupsize 32 / 64 / 128).
+//   gemv_w4_kernel<MT, UPG, WC, HYB>   the default W4 path (bits == 4, groupsize 32 / 64 / 128): cluster split-K.
 //       A producer thread streams [rows x 128 B] boxes of packed weights, plus the matching scale
 //       and zero rows, with 2-D tiled TMA loads (cp.async.bulk.tensor, 128-byte swizzle) through a
-//       4-stage shared-memory ring guarded by full/empty mbarriers; 8 consumer warps unpack
+//       3..5-stage shared-memory ring guarded by full/empty mbarriers; 8 consumer warps unpack
 //       straight out of shared memory with one conflict-free LDS.128 per 32-k unit.
-//       MT == 0  SIMT GEMV (M == 1): nibbles -> exact fp16 integers with LOP3 (mask|magic) and one
-//                HSUB2 that also removes the zero point; half2 FMA chains over (k, k+4) pairs
-//                flushed to fp32 every 64 k; per-group fp32 scale; split-K over the 4 r-lanes by
-//                warp shuffle, over warps by shared memory, over the cluster by DSMEM.
-//       MT >= 1  tensor-core skinny GEMM (M <= 8*MT): the masked nibble bits ARE fp16 values
-//                (subnormals w * 2^-24, or w * 2^-20 for the high nibble of a byte, compensated
-//                by a 2^-4 on the matching activations), so ONE LOP3 per half2 produces an
-//                m16n8k16 A fragment; products are exact and accumulate in fp32 inside the tensor
-//                core; the zero point is folded per group: s * (2^24 * acc - z * sum_k a_k).
+//       MT >= 1  tensor-core family, the default for every M (M <= 8*MT per launch), block math
+//                w4_consume_block_v2: the masked nibble / byte bits ARE fp16 subnormals (w * 2^-24), so
+//                2 PRMT + 2 LOP3 per packed word produce the m16n8k16 A fragments; products are exact,
+//                accumulation is fp32 in the tensor core; the zero point rides on one extra MMA per group.
 //                Weights are read once for all M rows (the reference re-reads them M times, :158).
-//   gemv_generic_kernel           any bits 2..8, any groupsize >= 16, any M, any N: one column per
+//       MT == 0  SIMT family (M == 1, selectable): LOP3 (mask|magic) + HSUB2 -> exact fp16 integers,
+//                half2 FMA chains flushed to fp32 every 64 k, per-group fp32 scale.
+//       Split-K: lanes -> warps (shared memory) -> thread-block cluster (DSMEM); deterministic.
+//       Epilogue variants: plain fp16 stores (also into peer GPUs' buffers), + per-rank completion
+//       flag (xbit_gemv_f16_peers_signal), or flag-in-data 8-byte {results, call number} stores
+//       (xbit_gemv_f16_peers_ll) whose consumer is the next call's activation staging.
+//   gemv_w4_streamk_kernel<MT, UPG>    persistent stream-K schedule of the same block math: one CTA per SM on
+//       half an SM, contiguous unit ranges, fp32 partial tiles + flags in the caller's workspace.
+//   gemv_w4_tc5_kernel<MPAD>           tcgen05 / TMEM family (opt-in): converter warps -> TMEM A tiles ->
+//       tcgen05.mma -> tcgen05.ld epilogue.
+//   gemv_generic_kernel                any bits 2..8, any groupsize >= 16, any M, any N: one column per
 //       thread, bit-reader over the LSB-first stream, fp32 math with the zero point folded per
 //       group.  Correctness path for the combinations the reference aborts on (:152-155).
+//   peers_wait_kernel, ll_unpack_kernel, pull_rows_kernel   one-warp / small helpers of the multi-GPU and
+//       host-buffer entry points.
 //
-// Split-K is deterministic (no atomics, no global workspace): lanes -> warps -> cluster (DSMEM).
 // Programmatic dependent launch: weights do not depend on the previous kernel in a decode step, so
 // (with XBIT_GEMV_FLAG_STATIC_WEIGHTS) the weight stream starts BEFORE griddepcontrol.wait and
 // only the activation staging waits for the previous kernel.
