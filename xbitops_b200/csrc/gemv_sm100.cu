@@ -452,25 +452,22 @@ __device__ __forceinline__ void w4_consume_block_v2(const unsigned char* __restr
   for (int q = 0; q < GPB; ++q) {
     const uint2 sraw = *reinterpret_cast<const uint2*>(st + L.s_off + q * (NT * 2));
     const uint32_t zraw = *reinterpret_cast<const unsigned short*>(st + L.z_off + q * (NT / 2));
-    // all shared-memory loads of the group first: the unpack / MMA chains below then never wait on LDS latency
-    uint4 wv[UPG], bfrag[UPG][MT];
-#pragma unroll
-    for (int uu = 0; uu < UPG; ++uu) {
-      const int u = q * UPG + uu;
-      wv[uu] = *reinterpret_cast<const uint4*>(st + ((u & 1) ? (L.w_x0 ^ kOddXor) : L.w_x0) + unit_row(u) * 128);
-#pragma unroll
-      for (int mt = 0; mt < MT; ++mt)
-        bfrag[uu][mt] = *reinterpret_cast<const uint4*>(ablk + L.brow_off[mt] + unit_row(u) * 8);
-    }
     uint32_t bz[MT];
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) bz[mt] = *reinterpret_cast<const uint32_t*>(zt_blk + q * zt_group_bytes + L.zt_off[mt]);
 
-    // (splitting the dependent HMMA chains over two accumulator sets was measured: no gain, the loop is issue bound)
+    // (hoisting all LDS.128 of the group in front of the math, or splitting the dependent HMMA chains over two
+    // accumulator sets, was measured: no gain -- the loop is issue bound -- and 24 more live registers)
     float grp[2 * MT][4];
 #pragma unroll
     for (int uu = 0; uu < UPG; ++uu) {
-      const uint32_t w4[4] = {wv[uu].x, wv[uu].y, wv[uu].z, wv[uu].w};
+      const int u = q * UPG + uu;
+      const uint4 wv = *reinterpret_cast<const uint4*>(st + ((u & 1) ? (L.w_x0 ^ kOddXor) : L.w_x0) + unit_row(u) * 128);
+      uint4 bfrag[MT];
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+        bfrag[mt] = *reinterpret_cast<const uint4*>(ablk + L.brow_off[mt] + unit_row(u) * 8);
+      const uint32_t w4[4] = {wv.x, wv.y, wv.z, wv.w};
 #pragma unroll
       for (int tt = 0; tt < 2; ++tt) {
         uint32_t ea[4], eb[4];
@@ -478,9 +475,9 @@ __device__ __forceinline__ void w4_consume_block_v2(const unsigned char* __restr
         unpack_w4_bytes(w4[2 * tt + 1], eb);
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
-          if (uu == 0) mma_m16n8k16_zero(grp[tt * MT + mt], ea[0], eb[0], ea[1], eb[1], bfrag[uu][mt].x, bfrag[uu][mt].y);
-          else         mma_m16n8k16(grp[tt * MT + mt], ea[0], eb[0], ea[1], eb[1], bfrag[uu][mt].x, bfrag[uu][mt].y);
-          mma_m16n8k16(grp[tt * MT + mt], ea[2], eb[2], ea[3], eb[3], bfrag[uu][mt].z, bfrag[uu][mt].w);
+          if (uu == 0) mma_m16n8k16_zero(grp[tt * MT + mt], ea[0], eb[0], ea[1], eb[1], bfrag[mt].x, bfrag[mt].y);
+          else         mma_m16n8k16(grp[tt * MT + mt], ea[0], eb[0], ea[1], eb[1], bfrag[mt].x, bfrag[mt].y);
+          mma_m16n8k16(grp[tt * MT + mt], ea[2], eb[2], ea[3], eb[3], bfrag[mt].z, bfrag[mt].w);
         }
       }
     }
@@ -582,7 +579,10 @@ __device__ __forceinline__ void trace_value(const GemvArgs& a, int slot, unsigne
 }
 
 template <int MT, int UPG, int WC, int HYB>
-__global__ void __launch_bounds__(kW4Threads, 2)   // (a 72-register cap for a third CTA per SM was measured: the loop grows by 20 %, slower everywhere)
+// Two CTAs per SM.  A third slot (72 registers, 3-stage ring) was measured twice: the next launch's CTAs do become
+// resident early and prefetch, but the hardware then packs three CTAs of ONE launch on some SMs and one on others,
+// and the imbalance costs more than the prefetch wins (4096x4096: 5.5 vs 4.3 us; profiles/r01_v6_trace_*).
+__global__ void __launch_bounds__(kW4Threads, 2)
 gemv_w4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap smap,
                const __grid_constant__ CUtensorMap zmap, const GemvArgs a) {
   using Cfg = W4Cfg<UPG, WC>;
