@@ -337,7 +337,7 @@ def run_gpu_arm(args):
             if rc != 0:
                 raise RuntimeError(capi.last_error())
 
-    def capture(set_list, mode=None):
+    def capture(set_list, mode=None, same_set=False):
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):          # warm outside capture (module load, NCCL channels)
@@ -348,7 +348,7 @@ def run_gpu_arm(args):
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         n = 0
-        order = [(ss, j) for ss in set_list for j in range(ss.R)]
+        order = [(ss, 0 if same_set else j) for ss in set_list for j in range(ss.R)]   # same_set: one weight set, L2-warm
         if (mode or combine) == "ll" and len(set_list) > 1:
             # every weight set once, ordered as a dependent chain: cycles (8192x8192 -> 8192x28672 -> 28672x8192),
             # whose output width is the next call's K, then the remaining square calls (which chain with themselves)
@@ -407,6 +407,12 @@ def run_gpu_arm(args):
             "rotating_sets": ss.R, "family": lib.xbit_gemv_pick_family(1, ss.K, ss.N, BITS, GROUP) if family == 0 else family}
         if solo_mode:
             per_shape[f"{ss.K}x{ss.N_total}"]["us_per_call_is"] = "kernel only (this shape cannot chain with itself)"
+        if world == 1:
+            # labelled aside: the same calls on ONE weight set (it stays in the 126 MB L2) -- not a roofline figure
+            gw, nw = capture([ss], None, same_set=True)
+            msw = timed(gw, max(3, args.steps // 4), 3) / max(3, args.steps // 4)
+            per_shape[f"{ss.K}x{ss.N_total}"]["us_per_call_l2_warm_single_buffer"] = round(msw * 1e3 / nw, 3)
+            del gw
         del g1
         if world > 1:
             for mode in ("none", "nccl", "peers", "signal"):
