@@ -73,13 +73,12 @@ def main():
         R, qw, sc, qz, a, out, nbytes = make(K, N)
         print(f"== {K}x{N} {nbytes/1e6:.1f} MB R={R} roofline {nbytes/PEAK/1e3:.2f} us")
         os.environ["XBIT_GEMV_STREAMK"] = "0"
-        fams = ((capi.GEMV_SIMT, "simt      ", 0), (capi.GEMV_MMA, "mma hyb=0 ", 0), (capi.GEMV_MMA, "mma hyb=2 ", 2))
+        fams = ((capi.GEMV_SIMT, "simt      ", 0), (capi.GEMV_MMA, "mma       ", 0))
         if os.environ.get("SWEEP_MMA_ONLY"):
             fams = fams[1:2]
         ring_env = os.environ.get("SWEEP_RING", "0")
         for fam, name, hyb in fams:
             os.environ["XBIT_GEMV_RING"] = ring_env
-            os.environ["XBIT_GEMV_HYBRID"] = str(hyb)
             for wc in (0, 2, 4, 8):
                 row = f"   {name} wc={wc if wc else 'A'}:"
                 for splits in ((0,) if wc == 0 else (1, 2, 3, 4, 5, 6, 7, 8)):
@@ -101,7 +100,6 @@ def main():
                 print(row, flush=True)
         os.environ["XBIT_GEMV_WC"] = "0"
         os.environ["XBIT_GEMV_SPLITS"] = "0"
-        os.environ["XBIT_GEMV_HYBRID"] = "0"
         os.environ["XBIT_GEMV_RING"] = "0"
         os.environ["XBIT_GEMV_WC"] = "0"
         os.environ["XBIT_GEMV_SPLITS"] = "0"

@@ -1881,10 +1881,9 @@ cudaError_t launch_gemv_w4_mma(GemvArgs a, cudaStream_t stream) {
   W4Plan p;
   if (!plan_w4(a, mt, upg, p)) return cudaErrorInvalidValue;
   apply_debug_knobs(a);
-  // M == 1: hybrid HMMA + FHFMA consumer (XBIT_GEMV_HYBRID=0 forces pure HMMA, for the sweep)
-  const int hyb = a.M == 1 ? env_int("XBIT_GEMV_HYBRID", 0) : 0;
-  W4Kernel k = mt == 1 ? (hyb == 2 ? pick_w4_kernel<1, 2>(upg, p.wc) : (hyb == 1 ? pick_w4_kernel<1, 1>(upg, p.wc) : pick_w4_kernel<1, 0>(upg, p.wc)))
-                       : pick_w4_kernel<2, 0>(upg, p.wc);
+  // (the FHFMA / HMMA hybrid of w4_consume_block -- template parameter HYB -- was measured on B200 and is no
+  // longer instantiated: it does not reduce issue slots, which is what bounds the loop)
+  W4Kernel k = mt == 1 ? pick_w4_kernel<1, 0>(upg, p.wc) : pick_w4_kernel<2, 0>(upg, p.wc);
   return k ? launch_w4(k, a, p, upg, stream) : cudaErrorInvalidValue;
 }
 
