@@ -237,7 +237,7 @@ def run_gpu_arm(args):
         try:
             import torch.distributed._symmetric_memory as symm_mem
             max_n = max(ss.N_total for ss in sets)
-            llbuf = symm_mem.empty((2, max_n), dtype=torch.int32, device=dev)     # two alternating LL buffers, 8 bytes per result pair
+            llbuf = symm_mem.empty((5, max_n), dtype=torch.int32, device=dev)     # rotating LL buffers, 8 bytes per result pair
             llbuf.zero_()
             lhdl = symm_mem.rendezvous(llbuf, dist.group.WORLD.group_name)
             lstate = torch.zeros(4, dtype=torch.int32, device=dev)
@@ -245,7 +245,7 @@ def run_gpu_arm(args):
             torch.cuda.synchronize()
             dist.barrier()
             llctx = {"buf": llbuf, "ptrs": [int(p) for p in lhdl.buffer_ptrs], "state": lstate, "plain": lplain,
-                     "stride": max_n * 4, "calls": 0, "last_n": 0}
+                     "stride": max_n * 4, "calls": 0, "last_n": 0, "mod": 2}
         except Exception as ex:  # noqa: BLE001
             if rank == 0:
                 print(f"[bench] symmetric memory unavailable ({ex}); falling back to nccl all-gather", file=sys.stderr)
@@ -288,10 +288,11 @@ def run_gpu_arm(args):
             # buffer slot by slot as the ranks deliver them; its own result goes into the other LL buffer
             c = llctx["calls"]
             chained = c > 0 and llctx["last_n"] == ss.K
-            src = (llctx["ptrs"][rank] + ((c - 1) & 1) * llctx["stride"]) if chained else ss.a.data_ptr()
-            outs = (ctypes.c_void_p * world)(*[b + (c & 1) * llctx["stride"] for b in llctx["ptrs"]])
+            mod = llctx["mod"]
+            src = (llctx["ptrs"][rank] + ((c - 1) % mod) * llctx["stride"]) if chained else ss.a.data_ptr()
+            outs = (ctypes.c_void_p * world)(*[b + (c % mod) * llctx["stride"] for b in llctx["ptrs"]])
             rc = lib.xbit_gemv_f16_peers_ll(src, ss.qw[j].data_ptr(), ss.sc[j].data_ptr(), ss.qz[j].data_ptr(), outs,
-                                            llctx["state"].data_ptr(), world, rank, 1, ss.K, ss.N, BITS, GROUP, 0, ss.N_total,
+                                            llctx["state"].data_ptr(), c, world, rank, 1, ss.K, ss.N, BITS, GROUP, 0, ss.N_total,
                                             ss.col0, family | flags | (capi.GEMV_FLAG_A_IS_LL if chained else 0), st)
             if rc != 0:
                 raise RuntimeError(capi.last_error())
@@ -325,8 +326,8 @@ def run_gpu_arm(args):
     def finish_chain(mode: str = None):
         if (mode or combine) == "ll":
             c = llctx["calls"]
-            rc = lib.xbit_ll_unpack_f16(llctx["ptrs"][rank] + ((c - 1) & 1) * llctx["stride"], llctx["plain"].data_ptr(),
-                                        llctx["last_n"], llctx["state"].data_ptr(), llctx["state"].data_ptr() + 12,
+            rc = lib.xbit_ll_unpack_f16(llctx["ptrs"][rank] + ((c - 1) % llctx["mod"]) * llctx["stride"], llctx["plain"].data_ptr(),
+                                        llctx["last_n"], llctx["state"].data_ptr(), c, llctx["state"].data_ptr() + 12,
                                         torch.cuda.current_stream().cuda_stream)
             if rc != 0:
                 raise RuntimeError(capi.last_error())
@@ -355,6 +356,10 @@ def run_gpu_arm(args):
             cyc = min(ss.R for ss in set_list)
             order = [(ss, j) for j in range(cyc) for ss in set_list]
             order += [(ss, j) for ss in set_list for j in range(cyc, ss.R)]
+        if (mode or combine) == "ll":
+            # a replayed chain starts again on buffer 0 while a slower rank may still be unpacking the last call's
+            # buffer: rotate over m buffers with (len - 1) % m != 0 so that the two never coincide
+            llctx["mod"] = next(m for m in (2, 3, 4, 5) if (len(order) - 1) % m != 0)
         with torch.cuda.graph(g):
             for ss, j in order:
                 launch(ss, j, mode)

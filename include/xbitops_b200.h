@@ -173,25 +173,31 @@ XBIT_API int xbit_peers_wait(const void* local_flags, int world, int rank, void*
                              xbit_stream_t stream);
 
 /* Flag-in-data ("LL") form of the N-split exchange, for chains of dependent GEMVs (a decode
- * step): no barrier, no fence, no wait launch.  peer_ll_out[r] is rank r's LL result buffer as
- * mapped in THIS process: M * out_row_stride / 2 slots of 8 bytes, slot = {two fp16 results,
- * call number}, in peer-mapped memory, zero-initialised once.  The epilogue stores every pair of
- * this rank's results into every rank's buffer with one 8-byte store each; local_state (two
- * zero-initialised uint32 in ordinary device memory) counts this rank's calls.  The consumer is
- * either the next xbit_gemv_f16_peers_ll call with XBIT_GEMV_FLAG_A_IS_LL (its activation staging
- * spins on exactly the slots it needs, as they arrive from the ranks) or xbit_ll_unpack_f16.
- * Use two LL buffers alternately along a chain; every rank must issue the same sequence of calls.
- * Same restrictions as xbit_gemv_f16_peers_signal; out_row_stride and col_offset must be even. */
+ * step): no barrier, no fence, no wait launch, no wait for the previous grid.  peer_ll_out[r] is
+ * rank r's LL result buffer as mapped in THIS process: M * out_row_stride / 2 slots of 8 bytes,
+ * slot = {two fp16 results, call number}, in peer-mapped memory, zero-initialised once.  The
+ * epilogue stores every pair of this rank's results into every rank's buffer with one 8-byte
+ * store each.  A chain is a sequence of calls with chain_index 0, 1, 2, ...: call 0 reads plain
+ * fp16 activations, call i > 0 (XBIT_GEMV_FLAG_A_IS_LL) reads the LL buffer call i-1 filled -- its
+ * activation staging spins on exactly the slots it needs, as they arrive from the ranks, and does
+ * not wait for call i-1's grid to complete -- and xbit_ll_unpack_f16 with chain_len = number of
+ * calls ends the chain.  Call numbers are local_state[2] (the chain base; four zero-initialised
+ * uint32 in ordinary device memory of this rank, advanced by xbit_ll_unpack_f16) + chain_index + 1,
+ * so a captured CUDA graph can be replayed.  Use two LL buffers alternately along a chain; every
+ * rank must issue the same sequence of calls.  Same restrictions as xbit_gemv_f16_peers_signal;
+ * out_row_stride and col_offset must be even. */
 XBIT_API int xbit_gemv_f16_peers_ll(const void* a_f16_or_ll, const int32_t* qweight, const void* scales_f16,
                                     const int32_t* qzeros, void* const* peer_ll_out_host_array,
-                                    void* local_state, int world, int rank, int M, int K, int N_local,
-                                    int bits, int groupsize, int add_zero_bias, int64_t out_row_stride,
-                                    int64_t col_offset, int family, xbit_stream_t stream);
+                                    void* local_state, int chain_index, int world, int rank, int M, int K,
+                                    int N_local, int bits, int groupsize, int add_zero_bias,
+                                    int64_t out_row_stride, int64_t col_offset, int family,
+                                    xbit_stream_t stream);
 
-/* LL buffer -> plain fp16 [n_elems] once every slot carries this rank's current call number
- * (local_state[1]).  n_elems must be even.  timeout_flag as in xbit_peers_wait. */
-XBIT_API int xbit_ll_unpack_f16(const void* ll_in, void* out_f16, int64_t n_elems, const void* local_state,
-                                void* timeout_flag, xbit_stream_t stream);
+/* End of a chain of chain_len calls: LL buffer (filled by the last call) -> plain fp16 [n_elems]
+ * once every slot carries the last call's number; then advances the chain base in local_state.
+ * n_elems must be even.  timeout_flag as in xbit_peers_wait. */
+XBIT_API int xbit_ll_unpack_f16(const void* ll_in, void* out_f16, int64_t n_elems, void* local_state,
+                                int chain_len, void* timeout_flag, xbit_stream_t stream);
 
 /* Host-buffer convenience used for end-to-end measurement: activations come from (pinned) host
  * memory and the result goes back to host memory; weights stay resident on the device.

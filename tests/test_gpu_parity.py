@@ -360,18 +360,18 @@ def test_flag_in_data_chain_single_gpu(dev):
     out = torch.empty((M, N), dtype=torch.float16, device=dev)
     for call, (src, flag) in enumerate(((ta.data_ptr(), 0), (ll[0].data_ptr(), capi.GEMV_FLAG_A_IS_LL))):
         outs = (ctypes.c_void_p * 1)(ll[call].data_ptr())
-        capi.check(lib.xbit_gemv_f16_peers_ll(src, tq.data_ptr(), ts.data_ptr(), tz.data_ptr(), outs, state.data_ptr(), 1, 0, M, K, N,
+        capi.check(lib.xbit_gemv_f16_peers_ll(src, tq.data_ptr(), ts.data_ptr(), tz.data_ptr(), outs, state.data_ptr(), call, 1, 0, M, K, N,
                                               4, 128, 1, N, 0, capi.GEMV_AUTO | flag, st))
-    capi.check(lib.xbit_ll_unpack_f16(ll[1].data_ptr(), out.data_ptr(), M * N, state.data_ptr(), state.data_ptr() + 12, st))
+    capi.check(lib.xbit_ll_unpack_f16(ll[1].data_ptr(), out.data_ptr(), M * N, state.data_ptr(), 2, state.data_ptr() + 12, st))
     torch.cuda.synchronize()
-    assert state.tolist() == [0, 2, 0, 0]                        # tile counter reset, two calls counted, no timeout
+    assert state.tolist() == [0, 2, 2, 0]                        # two calls, chain base advanced by two, no timeout
     slots = ll[0].view(M, N // 2, 2)
     assert bool((slots[..., 1] == 1).all()) and bool((ll[1].view(M, N // 2, 2)[..., 1] == 2).all())
     assert torch.equal(slots[..., 0].contiguous().view(torch.float16).view(M, N), y1)      # same kernel, same sums
     assert torch.equal(out, y2)
     # restrictions are reported, not executed
     rc = lib.xbit_gemv_f16_peers_ll(ta.data_ptr(), tq.data_ptr(), ts.data_ptr(), tz.data_ptr(), (ctypes.c_void_p * 1)(ll[0].data_ptr()),
-                                    state.data_ptr(), 1, 0, M, K, N, 3, 128, 1, N, 0, capi.GEMV_AUTO, st)
+                                    state.data_ptr(), 0, 1, 0, M, K, N, 3, 128, 1, N, 0, capi.GEMV_AUTO, st)
     assert rc == -1 and "bits" in capi.last_error()          # XBIT_EINVAL
     # signal form, world = 1: the flag carries the call count, the wait kernel returns at once
     flags = torch.zeros(8, dtype=torch.int32, device=dev)

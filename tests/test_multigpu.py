@@ -107,16 +107,16 @@ def _chain_ll(rank, world, dev, X):
     for call in range(3):
         k = call & 1
         outs = (ctypes.c_void_p * world)(*[int(p) + k * bufsz for p in hdl.buffer_ptrs])
-        capi.check(lib.xbit_gemv_f16_peers_ll(src, q.data_ptr(), sc.data_ptr(), z.data_ptr(), outs, state.data_ptr(), world, rank,
+        capi.check(lib.xbit_gemv_f16_peers_ll(src, q.data_ptr(), sc.data_ptr(), z.data_ptr(), outs, state.data_ptr(), call, world, rank,
                                               M, K, n_local, 4, 128, 1, N, rank * n_local, capi.GEMV_AUTO | flag, st))
         src, flag = int(hdl.buffer_ptrs[rank]) + k * bufsz, capi.GEMV_FLAG_A_IS_LL
-    capi.check(lib.xbit_ll_unpack_f16(src, out.data_ptr(), M * N, state.data_ptr(), state.data_ptr() + 12, st))
+    capi.check(lib.xbit_ll_unpack_f16(src, out.data_ptr(), M * N, state.data_ptr(), 3, state.data_ptr() + 12, st))
     torch.cuda.synchronize()
     why = []
     if int(state[3].item()) != 0:
         why.append("unpack timed out")
-    if int(state[1].item()) != 3:
-        why.append(f"call counter {int(state[1].item())}")
+    if int(state[2].item()) != 3:
+        why.append(f"chain base {int(state[2].item())}")
     e = float((out.double() - ref.double()).abs().max()) / float(ref.double().abs().max())
     if not e < 6e-3:
         why.append(f"chain error {e:.3e}")

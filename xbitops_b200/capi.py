@@ -32,9 +32,9 @@ SIGNATURES = {
     "xbit_gemv_f16_peers_signal": (_i, [_vp, _vp, _vp, _vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp), _vp, _i, _i, _i, _i, _i,
                                         _i, _i, _i, _i64, _i64, _i, _vp]),
     "xbit_peers_wait": (_i, [_vp, _i, _i, _vp, _vp]),
-    "xbit_gemv_f16_peers_ll": (_i, [_vp, _vp, _vp, _vp, ctypes.POINTER(_vp), _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i64, _i64,
+    "xbit_gemv_f16_peers_ll": (_i, [_vp, _vp, _vp, _vp, ctypes.POINTER(_vp), _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i64, _i64,
                                     _i, _vp]),
-    "xbit_ll_unpack_f16": (_i, [_vp, _vp, _i64, _vp, _vp, _vp]),
+    "xbit_ll_unpack_f16": (_i, [_vp, _vp, _i64, _vp, _i, _vp, _vp]),
     "xbit_gemv_f16_host": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
 }
 

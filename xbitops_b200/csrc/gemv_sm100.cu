@@ -671,7 +671,11 @@ gemv_w4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
     // =========================== consumers ===========================
     // stage the activations of this CTA's K range (the only data that depends on the previous
     // kernel); the mma path also needs sum_k a_k per scale group for the folded zero point
-    griddep_wait();
+    // A call fed from an LL buffer carries its dependency in the data (every slot is validated by its own call
+    // number), so it does not wait for the previous grid to complete and flush: its CTAs start staging as soon as
+    // they are resident.  (The previous launch's CTAs are all running by then -- that is when a programmatic
+    // dependent launch happens -- so whoever we spin on is making progress.)
+    if (!a.a_is_ll) griddep_wait();
     if (a.sig_wait) {                               // the previous N-split call has landed here (warp 0 polls, the others wait for it)
       if (warp == 0) peers_poll(a.sig_flags[a.sig_rank], a.world, a.sig_rank, lane);
       asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");
@@ -684,7 +688,7 @@ gemv_w4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
         const uint4* arow = reinterpret_cast<const uint4*>(a.a + (size_t)m * a.K + b0 * 128);
         // LL form: row m of the previous call's result, 2 halves per 8-byte slot; its call number = calls completed so far
         const unsigned long long* ll_row = reinterpret_cast<const unsigned long long*>(a.a) + (((size_t)m * a.K + b0 * 128) >> 1);
-        const uint32_t ll_epoch = a.a_is_ll ? a.sig_state[1] : 0u;
+        const uint32_t ll_epoch = a.a_is_ll ? a.sig_state[2] + (uint32_t)a.ll_chain_index : 0u;   // the previous call's number
         __half* srow = act_sm + (size_t)m * pitch;
         for (int v = tid; v - lane < vecs_per_row; v += kConsumerThreads) {      // warp-uniform trip count (shuffles below)
           const bool ok = v < vecs_per_row;
@@ -815,7 +819,9 @@ gemv_w4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
   };
   if (a.ll_out) {
     // flag-in-data all-gather: each pair of results goes to every rank as one {half2, call number} store
-    const uint32_t epoch = a.sig_state[1] + 1u;     // stable until the last tile of this call bumps it below
+    // call number = chain base (device memory, bumped by xbit_ll_unpack_f16 at the end of every chain, so
+    // graphs replay) + position in the chain + 1: known at launch, no counter shared with overlapping launches
+    const uint32_t epoch = a.sig_state[2] + (uint32_t)a.ll_chain_index + 1u;
     for (int o2 = tid; o2 < (nout >> 1); o2 += kW4Threads) {
       const int m = o2 / (NT / 2), col = 2 * (o2 - m * (NT / 2));
       if (col < cw) {
@@ -823,11 +829,6 @@ gemv_w4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
         const size_t slot = ((size_t)m * a.ldo + a.col_offset + n_cta + col) >> 1;
         for (int p = 0; p < a.world; ++p) ll_store(reinterpret_cast<unsigned long long*>(a.out[p]) + slot, h22u(h2), epoch);
       }
-    }
-    __syncthreads();
-    if (tid == 0 && atomicAdd(a.sig_state, 1u) == gridDim.x - 1) {   // last tile: the call is complete on this rank
-      a.sig_state[0] = 0u;
-      a.sig_state[1] = epoch;
     }
     if (tid == 0) trace_stamp(a, 7);
     return;
@@ -2103,13 +2104,14 @@ cudaError_t launch_peers_wait(const unsigned int* flags, int world, int rank, un
   return cudaLaunchKernelEx(&cfg, peers_wait_kernel, flags, world, rank, timeout_flag);
 }
 
-// ---- LL buffer -> plain fp16 (the consumer at the end of a chain): spins on each slot's call number
-__global__ void ll_unpack_kernel(const unsigned long long* __restrict__ ll, uint32_t* __restrict__ out, long long n_pairs,
-                                 const unsigned int* __restrict__ state, unsigned int* timeout_flag) {
+// ---- LL buffer -> plain fp16: the consumer at the END of a chain.  One CTA; it also advances the chain base.
+__global__ void __launch_bounds__(1024)
+ll_unpack_kernel(const unsigned long long* __restrict__ ll, uint32_t* __restrict__ out, long long n_pairs,
+                 unsigned int* __restrict__ state, int chain_len, unsigned int* timeout_flag) {
   griddep_launch_dependents();
-  griddep_wait();                                   // this rank's own call has completed: state[1] is its number
-  const uint32_t epoch = state[1];
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_pairs; i += (long long)gridDim.x * blockDim.x) {
+  griddep_wait();                                   // orders this kernel behind the previous chain end (state[2])
+  const uint32_t epoch = state[2] + (uint32_t)chain_len;   // the last call's number
+  for (long long i = threadIdx.x; i < n_pairs; i += blockDim.x) {
     uint32_t d, f;
     const long long c0 = clock64();
     for (unsigned int n = 1;; ++n) {
@@ -2122,14 +2124,18 @@ __global__ void ll_unpack_kernel(const unsigned long long* __restrict__ ll, uint
     }
     out[i] = d;
   }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    state[2] = epoch;                               // the next chain numbers its calls from here
+    state[1] = epoch;                               // calls completed (informational)
+  }
 }
 
-cudaError_t launch_ll_unpack(const void* ll_in, void* out_f16, long long n_pairs, const unsigned int* state, unsigned int* timeout_flag,
-                             cudaStream_t stream) {
+cudaError_t launch_ll_unpack(const void* ll_in, void* out_f16, long long n_pairs, unsigned int* state, int chain_len,
+                             unsigned int* timeout_flag, cudaStream_t stream) {
   cudaLaunchConfig_t cfg = {};
-  const long long blocks = (n_pairs + 255) / 256;
-  cfg.gridDim = dim3((unsigned)(blocks < 1 ? 1 : (blocks > 128 ? 128 : blocks)), 1, 1);
-  cfg.blockDim = dim3(256, 1, 1);
+  cfg.gridDim = dim3(1, 1, 1);
+  cfg.blockDim = dim3(1024, 1, 1);
   cfg.stream = stream;
   cudaLaunchAttribute attrs[1];
   attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -2137,7 +2143,7 @@ cudaError_t launch_ll_unpack(const void* ll_in, void* out_f16, long long n_pairs
   cfg.attrs = attrs;
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, ll_unpack_kernel, reinterpret_cast<const unsigned long long*>(ll_in),
-                            reinterpret_cast<uint32_t*>(out_f16), n_pairs, state, timeout_flag);
+                            reinterpret_cast<uint32_t*>(out_f16), n_pairs, state, chain_len, timeout_flag);
 }
 
 // ---- host-buffer entry: pull activation rows out of page-locked host memory with a kernel instead of a

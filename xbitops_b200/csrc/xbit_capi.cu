@@ -117,6 +117,7 @@ struct PeerSignal {
   void* state;          // local uint32 counters
   int rank;
   bool ll;              // flag-in-data form: outs are LL buffers
+  int chain_index;      // LL form: position of the call in its chain
 };
 
 static int gemv_impl(const void* a_f16, const int32_t* qweight, const void* scales_f16, const int32_t* qzeros,
@@ -168,6 +169,7 @@ static int gemv_impl(const void* a_f16, const int32_t* qweight, const void* scal
     g.sig_rank = sig->rank;
     g.sig_wait = (!sig->ll && (family_and_flags & XBIT_GEMV_FLAG_WAIT_PEERS)) ? 1 : 0;
     g.ll_out = sig->ll ? 1 : 0;
+    g.ll_chain_index = sig->chain_index;
     g.a_is_ll = (sig->ll && (family_and_flags & XBIT_GEMV_FLAG_A_IS_LL)) ? 1 : 0;
   }
 
@@ -259,26 +261,30 @@ int xbit_gemv_f16_peers_signal(const void* a_f16, const int32_t* qweight, const 
                                void* const* peer_out_host_array, void* const* peer_flags_host_array, void* local_state,
                                int world, int rank, int M, int K, int N_local, int bits, int groupsize, int add_zero_bias,
                                int64_t out_row_stride, int64_t col_offset, int family, xbit_stream_t stream) {
-  const PeerSignal sig = {peer_flags_host_array, local_state, rank, false};
+  const PeerSignal sig = {peer_flags_host_array, local_state, rank, false, 0};
   return gemv_impl(a_f16, qweight, scales_f16, qzeros, peer_out_host_array, world, M, K, N_local, bits, groupsize,
                    add_zero_bias, out_row_stride, col_offset, family, nullptr, 0, stream, &sig);
 }
 
 int xbit_gemv_f16_peers_ll(const void* a_f16_or_ll, const int32_t* qweight, const void* scales_f16, const int32_t* qzeros,
-                           void* const* peer_ll_out_host_array, void* local_state, int world, int rank, int M, int K,
-                           int N_local, int bits, int groupsize, int add_zero_bias, int64_t out_row_stride, int64_t col_offset,
-                           int family, xbit_stream_t stream) {
-  const PeerSignal sig = {nullptr, local_state, rank, true};
+                           void* const* peer_ll_out_host_array, void* local_state, int chain_index, int world, int rank, int M,
+                           int K, int N_local, int bits, int groupsize, int add_zero_bias, int64_t out_row_stride,
+                           int64_t col_offset, int family, xbit_stream_t stream) {
+  if (chain_index < 0) return fail(XBIT_EINVAL, "chain_index must be >= 0, got %d", chain_index);
+  if (((family & XBIT_GEMV_FLAG_A_IS_LL) != 0) != (chain_index > 0))
+    return fail(XBIT_EINVAL, "XBIT_GEMV_FLAG_A_IS_LL must be set exactly for chain_index > 0 (got index %d)", chain_index);
+  const PeerSignal sig = {nullptr, local_state, rank, true, chain_index};
   return gemv_impl(a_f16_or_ll, qweight, scales_f16, qzeros, peer_ll_out_host_array, world, M, K, N_local, bits, groupsize,
                    add_zero_bias, out_row_stride, col_offset, family, nullptr, 0, stream, &sig);
 }
 
-int xbit_ll_unpack_f16(const void* ll_in, void* out_f16, int64_t n_elems, const void* local_state, void* timeout_flag,
+int xbit_ll_unpack_f16(const void* ll_in, void* out_f16, int64_t n_elems, void* local_state, int chain_len, void* timeout_flag,
                        xbit_stream_t stream) {
   g_err[0] = 0;
   if (!ll_in || !out_f16 || !local_state) return fail(XBIT_EINVAL, "null pointer");
   if (n_elems < 2 || (n_elems & 1)) return fail(XBIT_EINVAL, "n_elems must be even and >= 2, got %lld", (long long)n_elems);
-  const cudaError_t e = xbit::launch_ll_unpack(ll_in, out_f16, n_elems / 2, reinterpret_cast<const unsigned int*>(local_state),
+  if (chain_len < 1) return fail(XBIT_EINVAL, "chain_len must be >= 1, got %d", chain_len);
+  const cudaError_t e = xbit::launch_ll_unpack(ll_in, out_f16, n_elems / 2, reinterpret_cast<unsigned int*>(local_state), chain_len,
                                                reinterpret_cast<unsigned int*>(timeout_flag), reinterpret_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "xbit_ll_unpack_f16 launch");
   return XBIT_OK;

@@ -37,7 +37,8 @@ struct GemvArgs {
   int sig_wait;                         // XBIT_GEMV_FLAG_WAIT_PEERS: wait for the previous call before reading activations
   // flag-in-data ("LL") form of the N-split exchange (xbit_gemv_f16_peers_ll): every pair of fp16 results
   // travels as one 8-byte {half2, call number} store, the consumer spins on the slots it needs: no fences
-  int ll_out;                           // out[p] are LL buffers ([M][ldo/2] 8-byte slots); sig_state[1] counts calls
+  int ll_out;                           // out[p] are LL buffers ([M][ldo/2] 8-byte slots); call number = sig_state[2] + ll_chain_index + 1
+  int ll_chain_index;                   // position of this call in its chain (0 = first)
   int a_is_ll;                          // a is the LL buffer the previous call filled (K/2 slots per row)
   // decomposition (filled by the planner)
   int splits;               // K splits = cluster size along grid.y
@@ -84,7 +85,7 @@ cudaError_t launch_gemv_w4_tc5(GemvArgs a, cudaStream_t stream);
 cudaError_t launch_gemv_generic(GemvArgs a, cudaStream_t stream);
 
 int device_sm_count();
-cudaError_t launch_ll_unpack(const void* ll_in, void* out_f16, long long n_pairs, const unsigned int* state, unsigned int* timeout_flag, cudaStream_t stream);
+cudaError_t launch_ll_unpack(const void* ll_in, void* out_f16, long long n_pairs, unsigned int* state, int chain_len, unsigned int* timeout_flag, cudaStream_t stream);
 cudaError_t launch_pull_rows(const void* src_host_devptr, void* dst, size_t bytes, cudaStream_t stream);
 cudaError_t launch_peers_wait(const unsigned int* flags, int world, int rank, unsigned int* timeout_flag, cudaStream_t stream);
 
