@@ -1783,12 +1783,12 @@ static bool plan_w4(GemvArgs& a, int mt, int upg, W4Plan& p, double* score_out =
   const int env_splits = env_int("XBIT_GEMV_SPLITS", 0);
   const int env_ring = env_int("XBIT_GEMV_RING", 0);
   // the decomposition is a pure function of these: computed once per shape
-  using Key = std::tuple<int, int, int, int, int, int, int, int, int>;
+  using Key = std::tuple<int, int, int, int, int, int, int, int, int, int>;
   static std::mutex mu;
   static auto* cache = new std::map<Key, W4PlanEntry>();
   int dev = 0;
   cudaGetDevice(&dev);
-  const Key key(dev, a.M, a.K, a.N, upg, mt, env_wc, env_splits, env_ring);
+  const Key key(dev, a.M, a.K, a.N, upg, mt, env_wc, env_splits, env_ring, a.ll_out);
   {
     std::lock_guard<std::mutex> lock(mu);
     auto it = cache->find(key);
@@ -1837,6 +1837,9 @@ static bool plan_w4(GemvArgs& a, int mt, int upg, W4Plan& p, double* score_out =
       double score = (double)ctas / (double)(waves * slots) * ((double)slots / (double)cap);   // fill of the whole machine
       if (!two_per_sm) score *= 1.2;                                                            // (cap/2 slots already halve it)
       if (waves > 1) score *= 0.75;                                      // every extra wave serialises a prologue and an epilogue
+      // chains of LL-fed calls overlap: the next call's clusters must find 8 free slots in one GPC while this call still
+      // runs, so 8-CTA clusters that fill the machine start late (4 GPUs, 8192x8192: 8.0 vs 6.0 us per call with 4-CTA clusters)
+      if (a.ll_out && splits == 8 && tiles * 4 >= sms - 20) score *= 0.5;
       if (bps * 128 < 1024) score *= 0.8;
       score *= 1.0 - 0.02 * log2((double)splits);                        // at equal fill fewer splits win (smaller DSMEM reduction)
       score *= wc == 4 ? 1.0 : (wc == 2 ? (bps * 128 >= 4096 ? 0.94 : 0.99) : 0.98);
