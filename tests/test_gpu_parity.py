@@ -367,8 +367,10 @@ def test_flag_in_data_chain_single_gpu(dev):
     assert state.tolist() == [0, 2, 2, 0]                        # two calls, chain base advanced by two, no timeout
     slots = ll[0].view(M, N // 2, 2)
     assert bool((slots[..., 1] == 1).all()) and bool((ll[1].view(M, N // 2, 2)[..., 1] == 2).all())
-    assert torch.equal(slots[..., 0].contiguous().view(torch.float16).view(M, N), y1)      # same kernel, same sums
-    assert torch.equal(out, y2)
+    # (the chain planner may pick another K split than the plain call: same block math, other fp32 summation order)
+    got1 = slots[..., 0].contiguous().view(torch.float16).view(M, N)
+    assert float((got1.double() - y1.double()).abs().max()) <= 2e-3 * float(y1.double().abs().max())
+    assert float((out.double() - y2.double()).abs().max()) <= 4e-3 * float(y2.double().abs().max())
     # restrictions are reported, not executed
     rc = lib.xbit_gemv_f16_peers_ll(ta.data_ptr(), tq.data_ptr(), ts.data_ptr(), tz.data_ptr(), (ctypes.c_void_p * 1)(ll[0].data_ptr()),
                                     state.data_ptr(), 0, 1, 0, M, K, N, 3, 128, 1, N, 0, capi.GEMV_AUTO, st)
