@@ -168,7 +168,7 @@ XBIT_API int xbit_gemv_f16_peers_signal(const void* a_f16, const int32_t* qweigh
 
 /* Enqueues a one-warp kernel that returns once every rank has published as many calls as this
  * rank (local_flags = this rank's own flag array).  timeout_flag (device uint32, may be NULL) is
- * set to 1 if a peer did not arrive within about 2 s -- the kernel never hangs. */
+ * set to 1 if a peer did not arrive within about 30 s of SM clocks -- the kernel never hangs. */
 XBIT_API int xbit_peers_wait(const void* local_flags, int world, int rank, void* timeout_flag,
                              xbit_stream_t stream);
 
@@ -182,7 +182,8 @@ XBIT_API int xbit_peers_wait(const void* local_flags, int world, int rank, void*
  * activation staging spins on exactly the slots it needs, as they arrive from the ranks, and does
  * not wait for call i-1's grid to complete -- and xbit_ll_unpack_f16 with chain_len = number of
  * calls ends the chain.  Call numbers are local_state[2] (the chain base; four zero-initialised
- * uint32 in ordinary device memory of this rank, advanced by xbit_ll_unpack_f16) + chain_index + 1,
+ * uint32 in ordinary device memory of this rank, advanced by xbit_ll_unpack_f16; local_state[3] is
+ * set to 1 if a slot did not arrive within about 30 s) + chain_index + 1,
  * so a captured CUDA graph can be replayed.  Use two LL buffers alternately along a chain; every
  * rank must issue the same sequence of calls.  Same restrictions as xbit_gemv_f16_peers_signal;
  * out_row_stride and col_offset must be even. */

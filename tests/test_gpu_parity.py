@@ -389,6 +389,31 @@ def test_flag_in_data_chain_single_gpu(dev):
     assert int(flags[0]) == 2 and state2.tolist() == [0, 2, 0, 0] and torch.equal(y, y1)
 
 
+def test_sharded_chain_wrapper_single_gpu(dev):
+    """ShardedQChain (world = 1): 2048 -> 4096 -> 2048 -> 2048, repeated calls (chain base advances), M = 2."""
+    from xbitops_b200.sharded import ShardedQChain
+    dims = (2048, 4096, 2048, 2048)
+    layers, ref_layers = [], []
+    for i in range(3):
+        K, N = dims[i], dims[i + 1]
+        qw, s, qz, _ = synth.make_inputs(K, N, 4, 128, M=1, seed=40 + i)
+        tq, ts, tz = ti(qw, dev), t16(s, dev) * 0.05, ti(qz, dev)
+        layers.append((tq, ts, tz, K, N))
+    a = synth.make_inputs(dims[0], 32, 4, 128, M=2, seed=9)[3]
+    ta = t16(a, dev)
+    ref = ta
+    for (tq, ts, tz, K, N) in layers:
+        ref = X.gemv(ref, tq, ts, tz, 128, 4, K, 1)
+    chain = ShardedQChain(layers, 128, 4, 1, max_rows=2)
+    for _ in range(8):                                                                     # back-to-back chains
+        y = chain(ta)
+    torch.cuda.synchronize()
+    assert tuple(y.shape) == (2, dims[-1]) and chain._bufs[2].tolist()[2:] == [24, 0]     # 8 chains of 3 calls, no timeout
+    assert float((y.double() - ref.double()).abs().max()) <= 6e-3 * float(ref.double().abs().max())
+    with pytest.raises(ValueError):
+        ShardedQChain([layers[0], layers[2]], 128, 4, 1)                                   # 4096 != 2048: not a chain
+
+
 def test_peer_entry_point_single_process(dev, c_oracle):
     """xbit_gemv_f16_peers with world=2 emulated inside one process: two 'rank' buffers on the same
     device, each shard's epilogue stores its slice into both (multi-process NVLink is in test_multigpu)."""

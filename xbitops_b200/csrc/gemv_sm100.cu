@@ -506,10 +506,15 @@ __device__ __forceinline__ void w4_consume_block_v2(const unsigned char* __restr
   }
 }
 
+// Every cross-GPU spin in this file gives up after about 30 s of SM clocks and reports it (timeout flag /
+// local_state[3]) instead of hanging the GPU.  Long on purpose: the peer may simply be late (another process,
+// lazy module loading, a descheduled host thread); 2 s was observed to fire spuriously once in a few runs.
+constexpr long long kSpinGuardClocks = 60000000000ll;
+
 // Fused gather wait: ONE lane per CTA polls this rank's flag array until every rank's slot has reached
 // this rank's own published call count (relaxed system-scope polls with a back-off, one fence at the
 // end).  Thousands of threads polling one L2 sector delay the very NVLink write they wait for: with
-// all 8 warps of every CTA polling, the wait cost 14 us per call (profiles/r01_v6_bench_n2_*).  ~2 s guard.
+// all 8 warps of every CTA polling, the wait cost 14 us per call (profiles/r01_v6_bench_n2_*).
 __device__ __forceinline__ bool peers_poll(const unsigned int* flags, int world, int rank, int lane) {
   bool ok = true;
   if (lane == 0) {
@@ -520,7 +525,7 @@ __device__ __forceinline__ bool peers_poll(const unsigned int* flags, int world,
       for (unsigned int n = 1;; ++n) {
         asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(f) : "l"(flags + p) : "memory");
         if ((int)(f - expected) >= 0) break;
-        if ((n & 255u) == 0 && clock64() - c0 > 4000000000ll) { ok = false; break; }
+        if ((n & 255u) == 0 && clock64() - c0 > kSpinGuardClocks) { ok = false; break; }
         __nanosleep(200);
       }
     }
@@ -535,15 +540,18 @@ __device__ __forceinline__ bool peers_poll(const unsigned int* flags, int world,
 __device__ __forceinline__ void ll_store(unsigned long long* slot, uint32_t data, uint32_t epoch) {
   asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(slot), "r"(data), "r"(epoch) : "memory");
 }
-// 8 consecutive halves = 4 slots = 32 bytes; spins until all four carry `epoch` (~2 s guard, then garbage)
-__device__ __forceinline__ uint4 ll_load8(const unsigned long long* slots, uint32_t epoch) {
+// 8 consecutive halves = 4 slots = 32 bytes; spins until all four carry `epoch` (guard: reports in local_state[3])
+__device__ __forceinline__ uint4 ll_load8(const unsigned long long* slots, uint32_t epoch, unsigned int* timeout_flag) {
   uint4 q0, q1;
   const long long c0 = clock64();
   for (unsigned int n = 1;; ++n) {
     asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q0.x), "=r"(q0.y), "=r"(q0.z), "=r"(q0.w) : "l"(slots) : "memory");
     asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q1.x), "=r"(q1.y), "=r"(q1.z), "=r"(q1.w) : "l"(slots + 2) : "memory");
     if (q0.y == epoch && q0.w == epoch && q1.y == epoch && q1.w == epoch) break;
-    if ((n & 1023u) == 0 && clock64() - c0 > 4000000000ll) break;
+    if ((n & 1023u) == 0 && clock64() - c0 > kSpinGuardClocks) {
+      *timeout_flag = 1u;
+      break;
+    }
   }
   return make_uint4(q0.x, q0.z, q1.x, q1.z);
 }
@@ -629,7 +637,12 @@ gemv_w4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
   // Let the next kernel in the stream become resident now: its producer starts streaming ITS weights
   // while this kernel is still running (its consumers block in griddepcontrol.wait until this grid
   // has completed and flushed).  One kernel uses at most about half of an SM's shared memory.
-  griddep_launch_dependents();
+  // Exception: the FIRST call of an LL chain.  The calls behind it do not wait for the grid before them, and they
+  // read the chain base that the previous chain's xbit_ll_unpack_f16 advances; so this call releases its dependents
+  // only after its own griddepcontrol.wait has returned, i.e. after that kernel has completed (otherwise the next
+  // calls can start on the stale base, match the previous chain's slots and publish call numbers nobody waits for).
+  const bool defer_dependents = a.ll_out && !a.a_is_ll;
+  if (!defer_dependents) griddep_launch_dependents();
 
   float tot[kMma ? 2 * MT : 1][4];
   float tot_s[4] = {0.f, 0.f, 0.f, 0.f};            // FHFMA partial sums (HYB only)
@@ -676,6 +689,7 @@ gemv_w4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
     // they are resident.  (The previous launch's CTAs are all running by then -- that is when a programmatic
     // dependent launch happens -- so whoever we spin on is making progress.)
     if (!a.a_is_ll) griddep_wait();
+    if (defer_dependents) griddep_launch_dependents();
     if (a.sig_wait) {                               // the previous N-split call has landed here (warp 0 polls, the others wait for it)
       if (warp == 0) peers_poll(a.sig_flags[a.sig_rank], a.world, a.sig_rank, lane);
       asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");
@@ -694,7 +708,7 @@ gemv_w4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
           const bool ok = v < vecs_per_row;
           uint4 val = make_uint4(0, 0, 0, 0);
           if (ok) {
-            if (a.a_is_ll) val = ll_load8(ll_row + 4 * (size_t)v, ll_epoch);   // arrives slot by slot from every rank
+            if (a.a_is_ll) val = ll_load8(ll_row + 4 * (size_t)v, ll_epoch, a.sig_state + 3);   // arrives slot by slot from every rank
             else           val = __ldcg(arow + v);                            // L2 only: may just have been written by peer GPUs
             *reinterpret_cast<uint4*>(srow + v * 8) = kV2 ? permute_act8_v2(val) : permute_act8<kMma>(val);
           }
@@ -2120,7 +2134,7 @@ ll_unpack_kernel(const unsigned long long* __restrict__ ll, uint32_t* __restrict
     for (unsigned int n = 1;; ++n) {
       asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(d), "=r"(f) : "l"(ll + i) : "memory");
       if (f == epoch) break;
-      if ((n & 1023u) == 0 && clock64() - c0 > 4000000000ll) {
+      if ((n & 1023u) == 0 && clock64() - c0 > kSpinGuardClocks) {
         if (timeout_flag) *timeout_flag = 1u;
         break;
       }

@@ -167,3 +167,82 @@ class ShardedQLinear:
         return out
 
     __call__ = forward
+
+
+class ShardedQChain:
+    """A chain of dependent N-split GEMVs (a decode step: y = L_n(...L_2(L_1(x)))) in the flag-in-data form
+    (xbit_gemv_f16_peers_ll): every layer's epilogue stores {two results, call number} slots into every rank's LL
+    buffer over NVLink, the next layer's kernel spins on the slots it needs while staging its activations -- no
+    barrier, no fence, no wait launch between the layers -- and xbit_ll_unpack_f16 hands back plain fp16.
+
+    layers: sequence of (qweight_shard, scales_shard, qzeros_shard, in_features, out_features) with
+    out_features[i] == in_features[i + 1]; W4 fast path only (bits 4, groupsize 32/64/128, in_features % 128 == 0,
+    shard width % 32 == 0), M <= 16."""
+
+    def __init__(self, layers, groupsize: int, bits: int = 4, add_zero_bias: int = 0, group=None, max_rows: int = 1):
+        self.layers = list(layers)
+        if not self.layers:
+            raise ValueError("empty chain")
+        self.groupsize, self.bits, self.add_zero_bias, self.group = groupsize, bits, add_zero_bias, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        for i, (q, _, _, k, n) in enumerate(self.layers):
+            if n % self.world or q.shape[1] != n // self.world:
+                raise ValueError(f"layer {i}: qweight shard has {q.shape[1]} columns, expected {n // self.world}")
+            if i + 1 < len(self.layers) and self.layers[i + 1][3] != n:
+                raise ValueError(f"layer {i}: out_features {n} != in_features {self.layers[i + 1][3]} of the next layer")
+            if bits != 4 or groupsize not in (32, 64, 128) or k % 128 or (n // self.world) % 32:
+                raise ValueError("the flag-in-data chain needs the W4 fast path (bits 4, groupsize 32/64/128, K%128=0, shard%32=0)")
+        if max_rows > 16:
+            raise ValueError("the flag-in-data chain takes at most 16 activation rows")
+        self.max_rows = max_rows
+        # a replayed / repeated chain starts again on buffer 0 while a slower rank may still be unpacking the last
+        # layer's buffer: rotate over m buffers with (len - 1) % m != 0 so that the two never coincide
+        self.nbuf = next(m for m in (2, 3, 4, 5) if (len(self.layers) - 1) % m != 0)
+        self._bufs = None
+
+    def _buffers(self, device):
+        if self._bufs is not None:
+            return self._bufs
+        max_n = max(l[4] for l in self.layers)
+        shape = (self.nbuf, self.max_rows, max_n)            # one int32 per result: 8 bytes per pair
+        if self.world > 1:
+            import torch.distributed._symmetric_memory as symm_mem
+            ll = symm_mem.empty(shape, dtype=torch.int32, device=device)
+            ll.zero_()
+            hdl = symm_mem.rendezvous(ll, self.group.group_name if self.group is not None else dist.group.WORLD.group_name)
+            torch.cuda.synchronize(device)
+            hdl.barrier()                                    # every rank's slots are zero before anyone stores
+            ptrs = [int(p) for p in hdl.buffer_ptrs]
+        else:
+            ll = torch.zeros(shape, dtype=torch.int32, device=device)
+            ptrs = [ll.data_ptr()]
+        state = torch.zeros(4, dtype=torch.int32, device=device)     # [2] = chain base, [3] = timeout flag
+        self._bufs = (ll, ptrs, state, self.max_rows * max_n * 4)
+        return self._bufs
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """x [M, in_features of the first layer] fp16, replicated on every rank -> [M, out_features of the last]."""
+        lib = capi.load()
+        m = x.shape[0]
+        if m > self.max_rows or x.dtype != torch.float16 or not x.is_contiguous():
+            raise ValueError("x must be a contiguous fp16 [M <= max_rows, K] tensor")
+        ll, ptrs, state, stride = self._buffers(x.device)
+        st = torch.cuda.current_stream().cuda_stream
+        src = x.data_ptr()
+        for i, (q, sc, z, k, n) in enumerate(self.layers):
+            b = i % self.nbuf
+            outs = (ctypes.c_void_p * self.world)(*[p + b * stride for p in ptrs])
+            n_local = n // self.world
+            capi.check(lib.xbit_gemv_f16_peers_ll(src, q.data_ptr(), sc.data_ptr(), z.data_ptr(), outs, state.data_ptr(), i,
+                                                  self.world, self.rank, m, k, n_local, self.bits, self.groupsize,
+                                                  int(self.add_zero_bias), n, self.rank * n_local,
+                                                  capi.GEMV_AUTO | (capi.GEMV_FLAG_A_IS_LL if i else 0), st))
+            src = ptrs[self.rank] + b * stride
+        n_last = self.layers[-1][4]
+        out = torch.empty((m, n_last), dtype=torch.float16, device=x.device)
+        capi.check(lib.xbit_ll_unpack_f16(src, out.data_ptr(), m * n_last, state.data_ptr(), len(self.layers),
+                                          state.data_ptr() + 12, st))
+        return out
+
+    __call__ = forward
