@@ -71,3 +71,31 @@ def test_sharded_qlinear_gloo_world2(M):
         port = _free_port()
         mp.spawn(_worker, args=(world, port, M, ret), nprocs=world, join=True)
         assert ret.get(0) is True and ret.get(1) is True
+
+
+def test_sharded_chain_argument_checks():
+    """ShardedQChain validates the chain on the host, before anything touches the GPU: consecutive layers must
+    fit, shards must have the right width, only the W4 fast path and M <= 16 are accepted; the LL buffers rotate
+    over m slots with (len - 1) % m != 0."""
+    from xbitops_b200.sharded import ShardedQChain
+
+    def layer(K, N, bits=4, g=128):
+        qw, s, qz, _ = synth.make_inputs(K, N, bits, g, M=1, seed=K + N)
+        return (torch.from_numpy(qw), torch.from_numpy(s.view(np.int16)).view(torch.float16), torch.from_numpy(qz), K, N)
+
+    a, b, c = layer(256, 512), layer(512, 256), layer(256, 256)
+    assert ShardedQChain([a, b, c], 128).nbuf == 3            # 3 layers: (3 - 1) % 2 == 0 -> three buffers
+    assert ShardedQChain([a, b], 128).nbuf == 2
+    assert ShardedQChain([a, b, c, c, c, c, c], 128).nbuf == 4          # (7 - 1) % 2 == (7 - 1) % 3 == 0
+    with pytest.raises(ValueError):
+        ShardedQChain([], 128)
+    with pytest.raises(ValueError):
+        ShardedQChain([a, c], 128)                              # 512 outputs do not feed 256 inputs
+    with pytest.raises(ValueError):
+        ShardedQChain([(a[0][:, :64], a[1], a[2], 256, 512)], 128)   # shard width does not match out_features / world
+    with pytest.raises(ValueError):
+        ShardedQChain([layer(256, 512, bits=3)], 128, bits=3)  # fast path only
+    with pytest.raises(ValueError):
+        ShardedQChain([layer(192, 512, g=64)], 64)              # K % 128 != 0
+    with pytest.raises(ValueError):
+        ShardedQChain([a], 128, max_rows=17)
