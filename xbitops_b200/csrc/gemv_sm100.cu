@@ -1813,7 +1813,6 @@ static bool plan_w4(GemvArgs& a, int mt, int upg, W4Plan& p, double* score_out =
       a.ring = e.ring;
       a.splits = p.splits;
       a.units_per_split = p.blocks_per_split;
-      a.chunk_units = 0;
       if (score_out) *score_out = e.score;
       return true;
     }
@@ -1878,7 +1877,6 @@ static bool plan_w4(GemvArgs& a, int mt, int upg, W4Plan& p, double* score_out =
   if (score_out) *score_out = best;
   a.splits = p.splits;
   a.units_per_split = p.blocks_per_split;
-  a.chunk_units = 0;
   return true;
 }
 

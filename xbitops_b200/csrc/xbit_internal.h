@@ -42,8 +42,7 @@ struct GemvArgs {
   int a_is_ll;                          // a is the LL buffer the previous call filled (K/2 slots per row)
   // decomposition (filled by the planner)
   int splits;               // K splits = cluster size along grid.y
-  int units_per_split;      // 32-k units per split
-  int chunk_units;          // activation staging chunk, in 32-k units
+  int units_per_split;      // 128-k blocks per split
   // persistent stream-K schedule (gemv_w4_streamk_kernel)
   float* sk_partials;       // [grid][M * 128] fp32 partial tiles (workspace)
   unsigned int* sk_flags;   // [grid] "partial ready" flags, zero outside a launch (workspace)
@@ -53,18 +52,8 @@ struct GemvArgs {
   int sk_act_units;         // 256-k activation chunks staged per CTA
   int sk_act_abs;           // 1: chunk index = stage inside the tile (whole K staged); 0: the CTA's own unit index
   int ring;                 // pipeline depth of gemv_w4_kernel (stages, <= 8)
-  unsigned long long* trace;   // tools/trace.py only: per-CTA globaltimer stamps [cta][8], null in production
+  unsigned long long* trace;   // tools/trace.py only: per-CTA globaltimer stamps [cta][16], null in production
   int debug_skip;           // tools/sweep.py only: 1 = consumers skip the math (feed ceiling), results are garbage
-};
-
-struct GemvPlan {
-  int family;     // XBIT_GEMV_*
-  int ct;         // 32-column chunks per CTA (W4 kernels)
-  int splits;
-  int units_per_split;
-  int chunk_units;
-  size_t smem_bytes;
-  dim3 grid;
 };
 
 cudaError_t launch_dequant(const DqArgs& a, cudaStream_t stream, int* path_taken);
