@@ -11,8 +11,17 @@ step     one pass over the workload's rotating set: for every shape, R distinct 
          n+1 prefetch weights while call n drains).
 N = 1    workload llama2-7b  = BASELINE.json configs[1]: 4096x4096, 4096x11008, 11008x4096, batch 1.
 N > 1    workload llama2-70b = configs[3]: 8192x8192, 8192x28672, 28672x8192 N-split over the ranks,
-         output slices combined by an all-gather (NCCL), strong scaling; rank 0 also times the
+         strong scaling.  --combine says how the output slices are exchanged: `ll` (default) = the
+         step ordered as ONE dependent chain (8192x8192 -> 8192x28672 -> 28672x8192 -> ...), every
+         call's epilogue stores {results, call number} slots into every rank's buffer over NVLink and
+         the next call spins on the slots it needs while staging its activations; `peers` = fused
+         peer stores + a symmetric-memory barrier per call; `signal` = peer stores + completion
+         flags awaited inside the next call; `nccl` = all_gather_into_tensor per call; `none` =
+         kernel only.  per_shape carries the other modes for comparison; rank 0 also times the
          unsharded workload alone and reports it as `single_gpu_same_workload` for context.
+e2e      (N = 1) the same calls through xbit_gemv_f16_host with pinned host buffers: activations
+         pulled over PCIe and results stored into host memory inside every call, replayed from a
+         CUDA graph, host wall clock including one sync per step.
 --impl reference   the reference's CPU implementation of the path (oracle/_ref: the unmodified
          src/cpp_simulate.cc dequant, N-sliced over all host threads, then the oracle's dot) on a
          bounded sample (one call per shape).  This is the only place besides cpu_baseline where
