@@ -246,7 +246,7 @@ def run_gpu_arm(args):
         try:
             import torch.distributed._symmetric_memory as symm_mem
             max_n = max(ss.N_total for ss in sets)
-            llbuf = symm_mem.empty((5, max_n), dtype=torch.int32, device=dev)     # rotating LL buffers, 8 bytes per result pair
+            llbuf = symm_mem.empty((8, max_n), dtype=torch.int32, device=dev)     # rotating LL buffers, 8 bytes per result pair
             llbuf.zero_()
             lhdl = symm_mem.rendezvous(llbuf, dist.group.WORLD.group_name)
             lstate = torch.zeros(4, dtype=torch.int32, device=dev)
@@ -368,7 +368,7 @@ def run_gpu_arm(args):
         if (mode or combine) == "ll":
             # a replayed chain starts again on buffer 0 while a slower rank may still be unpacking the last call's
             # buffer: rotate over m buffers with (len - 1) % m != 0 so that the two never coincide
-            llctx["mod"] = next(m for m in (2, 3, 4, 5) if (len(order) - 1) % m != 0)
+            llctx["mod"] = next(m for m in range(2, 9) if (len(order) - 1) % m != 0)
         with torch.cuda.graph(g):
             for ss, j in order:
                 launch(ss, j, mode)

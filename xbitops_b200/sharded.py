@@ -198,7 +198,7 @@ class ShardedQChain:
         self.max_rows = max_rows
         # a replayed / repeated chain starts again on buffer 0 while a slower rank may still be unpacking the last
         # layer's buffer: rotate over m buffers with (len - 1) % m != 0 so that the two never coincide
-        self.nbuf = next(m for m in (2, 3, 4, 5) if (len(self.layers) - 1) % m != 0)
+        self.nbuf = next(m for m in range(2, 9) if (len(self.layers) - 1) % m != 0)
         self._bufs = None
 
     def _buffers(self, device):
