@@ -68,7 +68,10 @@ enum {
   XBIT_GEMV_MMA = 2,      /* W4 tensor-core kernel: register-level unpack straight into mma.sync
                              m16n8k16 fragments, fp32 accumulation, M <= 16                          */
   XBIT_GEMV_GENERIC = 3,  /* any bits 2..8, any groupsize >= 16, any M: SIMT, fp32 accumulation      */
-  XBIT_GEMV_TCGEN05 = 4   /* W4 g128, M <= 16: tcgen05.mma with the unpacked weights in TMEM          */
+  XBIT_GEMV_TCGEN05 = 4,  /* W4 g128, M <= 16: tcgen05.mma with the unpacked weights in TMEM          */
+  XBIT_GEMV_PERSIST = 5   /* W4, M <= 8: one persistent CTA per SM, per-warp TMA rings, block-granular
+                             stream-K (same tensor-core block math as XBIT_GEMV_MMA); AUTO's choice
+                             wherever it applies                                                       */
 };
 
 /* Flags OR-ed into the `family` argument of xbit_gemv_f16_ex / xbit_gemv_f16_peers_ex. */
@@ -184,8 +187,11 @@ XBIT_API int xbit_peers_wait(const void* local_flags, int world, int rank, void*
  * calls ends the chain.  Call numbers are local_state[2] (the chain base; four zero-initialised
  * uint32 in ordinary device memory of this rank, advanced by xbit_ll_unpack_f16; local_state[3] is
  * set to 1 if a slot did not arrive within about 30 s) + chain_index + 1,
- * so a captured CUDA graph can be replayed.  Use two LL buffers alternately along a chain; every
- * rank must issue the same sequence of calls.  Same restrictions as xbit_gemv_f16_peers_signal;
+ * so a captured CUDA graph can be replayed.  Rotate over nbuf >= 2 LL buffers along a chain (call i
+ * writes buffer i % nbuf and reads buffer (i - 1) % nbuf) with (chain_len - 1) % nbuf != 0: a
+ * repeated or replayed chain starts again on buffer 0 while a slower rank may still be unpacking
+ * the last call's buffer, so the two must never coincide (a single-call chain alternates two
+ * buffers between repetitions instead).  Every rank must issue the same sequence of calls.  Same restrictions as xbit_gemv_f16_peers_signal;
  * out_row_stride and col_offset must be even. */
 XBIT_API int xbit_gemv_f16_peers_ll(const void* a_f16_or_ll, const int32_t* qweight, const void* scales_f16,
                                     const int32_t* qzeros, void* const* peer_ll_out_host_array,

@@ -142,7 +142,7 @@ def test_dequant_bf16_scales_and_full_size_properties(dev):
 # ------------------------------------------------------------------ gemv
 
 FAMILIES = [(capi.GEMV_SIMT, (1, 3)), (capi.GEMV_MMA, (1, 2, 7, 8, 9, 16)), (capi.GEMV_GENERIC, (1, 5)),
-            (capi.GEMV_TCGEN05, (1, 2, 5, 8, 11, 16))]
+            (capi.GEMV_TCGEN05, (1, 2, 5, 8, 11, 16)), (capi.GEMV_PERSIST, (1, 2, 3, 5, 8))]
 
 
 @pytest.mark.parametrize("family,Ms", FAMILIES)
@@ -155,6 +155,8 @@ def test_gemv_w4_families_vs_truth(family, Ms, dev, c_oracle):
             for M in Ms:
                 if family == capi.GEMV_TCGEN05 and g != 128:
                     continue                     # the tcgen05 family covers groupsize 128 (others: mma.sync family)
+                if family == capi.GEMV_PERSIST and capi.load().xbit_gemv_pick_family(M, K, N, 4, g) != capi.GEMV_PERSIST:
+                    continue                     # M * K too large to stage in one SM's shared memory: AUTO uses the cluster kernel
                 y64 = a[:M].astype(np.float64) @ w.astype(np.float64)
                 got = X.gemv(t16(a[:M], dev), tq, ts, tz, g, 4, K, bias, family=family).cpu().numpy()
                 assert got.shape == (M, N)
@@ -200,6 +202,36 @@ def test_gemv_streamk_schedule(dev, c_oracle, monkeypatch):
     torch.cuda.synchronize()
     ws = ops.gemv_workspace(dev)
     assert int(ws[: 148 * 4].view(torch.int32).abs().sum()) == 0      # ready flags cleared
+
+
+def test_gemv_persistent_schedule(dev, c_oracle, monkeypatch):
+    """The default W4 schedule (one persistent CTA per SM, per-warp rings): block-granular CTA boundaries with the
+    cross-CTA fix-up through the workspace (XBIT_W4P_FINE=1) and tile-aligned boundaries (=0) give results within
+    fp32 summation-order noise of each other, are deterministic, and leave the workspace zeroed."""
+    from xbitops_b200 import ops
+    # whole tiles per CTA, tiles shared by 2..3 CTAs (long K), fewer blocks than warps (128 x 32), more tiles than
+    # SMs, every groupsize of the fast path, odd block counts (K = 4224: 33 blocks)
+    cases = ((4096, 4096, 1, 128, 1), (11008, 4096, 1, 128, 1), (4096, 11008, 2, 128, 0), (28672, 1024, 1, 128, 1),
+             (4224, 4128, 1, 128, 1), (1024, 96, 3, 64, 0), (2048, 2048, 8, 32, 1), (128, 32, 1, 32, 0),
+             (256, 64, 2, 128, 1), (8192, 8192, 4, 64, 0), (384, 4736, 1, 128, 1))
+    for (K, N, M, g, bias) in cases:
+        qw, s, qz, a = synth.make_inputs(K, N, 4, g, M=M, seed=K + N + M)
+        w = c_oracle.dequant(qw, s, qz, g, 4, K, bias)
+        y64 = a.astype(np.float64) @ w.astype(np.float64)
+        tq, ts, tz, ta = ti(qw, dev), t16(s, dev), ti(qz, dev), t16(a, dev)
+        ys = {}
+        for fine in ("1", "0"):
+            monkeypatch.setenv("XBIT_W4P_FINE", fine)
+            y1 = X.gemv(ta, tq, ts, tz, g, 4, K, bias, family=capi.GEMV_PERSIST)
+            y2 = X.gemv(ta, tq, ts, tz, g, 4, K, bias, family=capi.GEMV_PERSIST)
+            assert torch.equal(y1, y2), f"persist fine={fine} {K}x{N} M={M}: not deterministic"
+            assert_gemv_close(y1.cpu().numpy(), y64, f"persist fine={fine} {K}x{N} M={M} g={g}")
+            ys[fine] = y1
+        assert float((ys["1"].double() - ys["0"].double()).abs().max()) <= 2e-3 * float(np.abs(y64).max())
+    monkeypatch.delenv("XBIT_W4P_FINE")
+    torch.cuda.synchronize()
+    ws = ops.gemv_workspace(dev)
+    assert int(ws.view(torch.int32).abs().sum()) == 0      # partial slots and flags cleared
 
 
 def test_gemv_shapes_dtypes_and_large_m(dev, c_oracle):
@@ -254,7 +286,7 @@ def test_gemv_full_size_properties(K, N, dev):
     a = torch.randn((4, K), device=dev, generator=gen).to(torch.float16)
     w = X.dequant(qw, s, qz, g, bits, K, 1)
     truth = (a.double() @ w.double()).cpu().numpy()
-    for fam in (capi.GEMV_SIMT, capi.GEMV_MMA, capi.GEMV_TCGEN05):
+    for fam in (capi.GEMV_SIMT, capi.GEMV_MMA, capi.GEMV_TCGEN05, capi.GEMV_PERSIST):
         y = X.gemv(a, qw, s, qz, g, bits, K, 1, family=fam)
         assert_gemv_close(y.cpu().numpy(), truth, f"{K}x{N} family {fam}", floor_of(fam))
         y1 = X.gemv(a[2:3], qw, s, qz, g, bits, K, 1, family=fam)

@@ -93,7 +93,8 @@ def _chain_ll(rank, world, dev, X):
         ref = X.gemv(ref, tq, ts, tz, 128, 4, K, 1)
     q, sc, z = shard_columns(tq, ts, tz, 4, world, rank)
     name = dist.group.WORLD.group_name
-    ll = symm_mem.empty((2, M, N), dtype=torch.int32, device=dev)       # 8-byte slot per pair of results
+    NBUF, REPS = 3, 4                                                   # (chain_len - 1) % NBUF != 0: see include/xbitops_b200.h
+    ll = symm_mem.empty((NBUF, M, N), dtype=torch.int32, device=dev)    # 8-byte slot per pair of results
     ll.zero_()
     hdl = symm_mem.rendezvous(ll, name)
     state = torch.zeros(4, dtype=torch.int32, device=dev)
@@ -103,19 +104,20 @@ def _chain_ll(rank, world, dev, X):
     st = torch.cuda.current_stream().cuda_stream
     n_local = N // world
     bufsz = M * N * 4
-    src, flag = ta.data_ptr(), 0
-    for call in range(3):
-        k = call & 1
-        outs = (ctypes.c_void_p * world)(*[int(p) + k * bufsz for p in hdl.buffer_ptrs])
-        capi.check(lib.xbit_gemv_f16_peers_ll(src, q.data_ptr(), sc.data_ptr(), z.data_ptr(), outs, state.data_ptr(), call, world, rank,
-                                              M, K, n_local, 4, 128, 1, N, rank * n_local, capi.GEMV_AUTO | flag, st))
-        src, flag = int(hdl.buffer_ptrs[rank]) + k * bufsz, capi.GEMV_FLAG_A_IS_LL
-    capi.check(lib.xbit_ll_unpack_f16(src, out.data_ptr(), M * N, state.data_ptr(), 3, state.data_ptr() + 12, st))
+    for _ in range(REPS):                   # the same chain back to back, as a replayed CUDA graph would issue it
+        src, flag = ta.data_ptr(), 0
+        for call in range(3):
+            k = call % NBUF
+            outs = (ctypes.c_void_p * world)(*[int(p) + k * bufsz for p in hdl.buffer_ptrs])
+            capi.check(lib.xbit_gemv_f16_peers_ll(src, q.data_ptr(), sc.data_ptr(), z.data_ptr(), outs, state.data_ptr(), call, world, rank,
+                                                  M, K, n_local, 4, 128, 1, N, rank * n_local, capi.GEMV_AUTO | flag, st))
+            src, flag = int(hdl.buffer_ptrs[rank]) + k * bufsz, capi.GEMV_FLAG_A_IS_LL
+        capi.check(lib.xbit_ll_unpack_f16(src, out.data_ptr(), M * N, state.data_ptr(), 3, state.data_ptr() + 12, st))
     torch.cuda.synchronize()
     why = []
     if int(state[3].item()) != 0:
         why.append("unpack timed out")
-    if int(state[2].item()) != 3:
+    if int(state[2].item()) != 3 * REPS:
         why.append(f"chain base {int(state[2].item())}")
     e = float((out.double() - ref.double()).abs().max()) / float(ref.double().abs().max())
     if not e < 6e-3:
@@ -127,6 +129,16 @@ def _chain_ll(rank, world, dev, X):
     for _ in range(8):                      # back-to-back chains: the chain base must be seen fresh by every call
         yc = chain(ta)
     torch.cuda.synchronize()
+    chain.check_timeout()
+    one = ShardedQChain([(q, sc, z, K, N)], 128, 4, 1, max_rows=M)      # a single-layer chain alternates its two buffers
+    y1 = X.gemv(ta, tq, ts, tz, 128, 4, K, 1)
+    for _ in range(4):
+        yo = one(ta)
+    torch.cuda.synchronize()
+    one.check_timeout()
+    eo = float((yo.double() - y1.double()).abs().max()) / float(y1.double().abs().max())
+    if not eo < 6e-3:
+        why.append(f"single-layer chain error {eo:.3e}")
     ec = float((yc.double() - ref.double()).abs().max()) / float(ref.double().abs().max())
     if not ec < 6e-3 or chain._bufs[2].tolist()[2:] != [24, 0]:
         why.append(f"ShardedQChain error {ec:.3e} state {chain._bufs[2].tolist()}")

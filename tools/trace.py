@@ -74,6 +74,30 @@ def run(K, N, fam, pdl=True, calls=48):
     print(f"   clk/stage percentiles 5/25/50/75/95: " + " ".join(f"{np.percentile(per, q):.0f}" for q in (5, 25, 50, 75, 95)))
     print(f"   consumer warp 0: loop {np.median(loop):.0f} clk for {np.median(nt):.0f} stages ({np.median(loop / np.maximum(nt, 1)):.0f} clk/stage), "
           f"waiting for data {100 * cwait.sum() / loop.sum():.0f}% of it; producer waiting for free slots {np.median(pwait):.0f} clk")
+    # CTAs per SM within one launch (slot 12 = smid + 1, persistent kernel only)
+    if t[slots[10]][:, 12].max() > 0:
+        import collections
+        hist = collections.Counter()
+        for sl in slots[4:-2]:
+            sm = t[sl][:, 12]
+            sm = sm[sm > 0] - 1
+            per = collections.Counter(sm.tolist())
+            hist.update(collections.Counter(per.values()))
+        print(f"   CTAs of one launch per SM (histogram over launches): {dict(sorted(hist.items()))}")
+        # do slow CTAs share an SM with another CTA of the same launch?
+        slow, fast = [], []
+        for sl in slots[4:-2]:
+            tt = t[sl]
+            live = tt[:, 12] > 0
+            sm = tt[live, 12]
+            cnt = collections.Counter(sm.tolist())
+            dur = (tt[live, 5] - tt[live, 3]).astype(float)
+            for s_, d_ in zip(sm.tolist(), dur.tolist()):
+                (slow if cnt[s_] > 1 else fast).append(d_)
+        if slow:
+            print(f"   staged -> consumed: alone on the SM median {np.median(fast)/1e3:.2f} us (n={len(fast)}), sharing it {np.median(slow)/1e3:.2f} us (n={len(slow)})")
+        else:
+            print(f"   staged -> consumed: alone on the SM median {np.median(fast)/1e3:.2f} us p95 {np.percentile(fast, 95)/1e3:.2f} (n={len(fast)}); no SM ever holds two CTAs of a launch")
     for k, name in enumerate(NAMES):
         med, mx, mn = [], [], []
         for rel in rows:
@@ -87,12 +111,13 @@ def run(K, N, fam, pdl=True, calls=48):
 
 
 def main():
+    fam = int(os.environ.get("TRACE_FAMILY", capi.GEMV_MMA))
     shapes = [(int(sys.argv[i]), int(sys.argv[i + 1])) for i in range(1, len(sys.argv) - 1, 2)] or \
         [(4096, 4096), (4096, 11008), (11008, 4096), (8192, 8192)]
     for K, N in shapes:
-        run(K, N, capi.GEMV_MMA, pdl=True)
+        run(K, N, fam, pdl=True)
         if os.environ.get("TRACE_NO_PDL"):
-            run(K, N, capi.GEMV_MMA, pdl=False)
+            run(K, N, fam, pdl=False)
 
 
 if __name__ == "__main__":

@@ -16,10 +16,12 @@ PKG = Path(__file__).resolve().parent
 ROOT = PKG.parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libxbitops_b200.so"
-CUDA_SOURCES = ["xbit_capi.cu", "dq_sm100.cu", "gemv_sm100.cu"]
-CUDA_DEPS = CUDA_SOURCES + ["unpack.cuh", "xbit_internal.h"]
+LIB_DEV = PKG / "libxbitops_b200_dev.so"      # -DXBIT_DEVTOOLS: phase stamps / skip-math knobs for tools/*.py only
+OBJ = PKG / "_obj"
+CUDA_SOURCES = ["xbit_capi.cu", "dq_sm100.cu", "gemv_sm100.cu", "gemv_w4p_sm100.cu"]
+CUDA_DEPS = CUDA_SOURCES + ["unpack.cuh", "gemv_prims.cuh", "xbit_internal.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC,-fvisibility=hidden", "-shared"]
+              "-Xcompiler", "-fPIC,-fvisibility=hidden"]
 
 
 def _newer(target: Path, deps) -> bool:
@@ -36,17 +38,34 @@ def nvcc_path() -> str:
     return "nvcc"
 
 
-def build_lib(force: bool = False, verbose: bool = False) -> Path:
-    deps = [CSRC / d for d in CUDA_DEPS] + [ROOT / "include" / "xbitops_b200.h"]
-    if force or _newer(LIB, deps):
-        cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-              ["-o", str(LIB)] + [str(CSRC / s) for s in CUDA_SOURCES]
+def build_lib(force: bool = False, verbose: bool = False, dev: bool = False) -> Path:
+    """One object per .cu (compiled in parallel), then one shared library."""
+    from concurrent.futures import ThreadPoolExecutor
+    lib = LIB_DEV if dev else LIB
+    hdrs = [CSRC / d for d in CUDA_DEPS if not d.endswith(".cu")] + [ROOT / "include" / "xbitops_b200.h"]
+    OBJ.mkdir(exist_ok=True)
+    extra = ["-DXBIT_DEVTOOLS"] if dev else []
+    jobs, objs = [], []
+    for s in CUDA_SOURCES:
+        o = OBJ / (s[:-3] + ("_dev.o" if dev else ".o"))
+        objs.append(o)
+        if force or _newer(o, [CSRC / s] + hdrs):
+            jobs.append([nvcc_path()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", str(o), str(CSRC / s)])
+
+    def run(cmd):
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
-            raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+            raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+        return r.stderr
+
+    if jobs:
+        with ThreadPoolExecutor(len(jobs)) as ex:
+            logs = list(ex.map(run, jobs))
         if verbose:
-            print(r.stderr)
-    return LIB
+            print("\n".join(logs))
+    if jobs or force or _newer(lib, objs):
+        run([nvcc_path(), "-shared", "-o", str(lib)] + [str(o) for o in objs])
+    return lib
 
 
 def torch_ext_path() -> Path | None:
@@ -81,5 +100,7 @@ def build_torch_ext(force: bool = False) -> Path:
 
 if __name__ == "__main__":
     print(build_lib(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--dev" in sys.argv:
+        print(build_lib(force="--force" in sys.argv, dev=True))
     if "--torch" in sys.argv:
         print(build_torch_ext(force="--force" in sys.argv))

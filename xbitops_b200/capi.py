@@ -9,7 +9,7 @@ from pathlib import Path
 from . import _build
 
 XBIT_OK = 0
-GEMV_AUTO, GEMV_SIMT, GEMV_MMA, GEMV_GENERIC, GEMV_TCGEN05 = 0, 1, 2, 3, 4
+GEMV_AUTO, GEMV_SIMT, GEMV_MMA, GEMV_GENERIC, GEMV_TCGEN05, GEMV_PERSIST = 0, 1, 2, 3, 4, 5
 GEMV_FLAG_STATIC_WEIGHTS = 0x100
 GEMV_FLAG_WAIT_PEERS = 0x200
 GEMV_FLAG_A_IS_LL = 0x400
@@ -42,7 +42,9 @@ _lib = None
 
 
 def lib_path() -> Path:
-    return _build.LIB
+    # XBIT_DEVTOOLS_LIB=1 (tools/*.py only): the -DXBIT_DEVTOOLS build with phase stamps and skip-math knobs
+    import os
+    return _build.LIB_DEV if os.environ.get("XBIT_DEVTOOLS_LIB") else _build.LIB
 
 
 def load(build_if_missing: bool = True) -> ctypes.CDLL:
@@ -53,7 +55,7 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
     path = lib_path()
     if build_if_missing:
         try:
-            _build.build_lib()
+            _build.build_lib(dev=(path == _build.LIB_DEV))
         except Exception:
             if not path.exists():
                 raise

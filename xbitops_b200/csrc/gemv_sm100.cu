@@ -48,6 +48,7 @@
 #include <math.h>
 #include <string.h>
 
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <set>
@@ -55,6 +56,7 @@
 #include <utility>
 
 #include "unpack.cuh"
+#include "gemv_prims.cuh"
 #include "xbit_internal.h"
 #include "../../include/xbitops_b200.h"
 
@@ -65,25 +67,6 @@ namespace xbit {
 constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
 
-__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-
-// D += A(16x16, row) * B(16x8, col), fp16 inputs, fp32 accumulate
-__device__ __forceinline__ void mma_m16n8k16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
-                                             uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-}
-// D = A * B with a zero C operand (first MMA of a scale group)
-__device__ __forceinline__ void mma_m16n8k16_zero(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
-                                                  uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
-      : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
-      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "f"(0.f));
-}
 
 // One packed W4 word (8 consecutive k of one column) -> four half2 of EXACT (w - z):
 //   e[0] = (k0, k4)  e[1] = (k1, k5)  e[2] = (k2, k6)  e[3] = (k3, k7)
@@ -137,33 +120,6 @@ __device__ __forceinline__ uint4 permute_act8(uint4 v) {
   return o;
 }
 
-// ---- mbarrier / TMA primitives
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) {}
-}
-// 2-D tiled TMA load (cp.async.bulk.tensor; SASS: UTMALDG): one instruction moves a whole box and
-// zero-fills anything outside the tensor.  L2 evict-first: every weight byte is used exactly once.
-__device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* tmap, int c0, int c1, uint64_t* bar, uint64_t policy) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
-      ::"r"(smem_u32(dst_smem)), "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(policy) : "memory");
-}
 
 // CTA = 8 consumer warps (WC column chunks of 32 columns x WK = 8/WC K-slices) + 1 producer warp.
 constexpr int kMaxStages = 8;
@@ -418,25 +374,6 @@ __device__ __forceinline__ W4Lane2<MT> make_w4_lane2(int lane, int wc, int wk, i
   return L;
 }
 
-// activations [8 consecutive k] -> (a0 - a1/16, a4 - a5/16) (a1/16, a5/16) (a2 - a3/16, a6 - a7/16) (a3/16, a7/16)
-__device__ __forceinline__ uint4 permute_act8_v2(uint4 v) {
-  const __half2 sixteenth = u2h2(0x2C002C00u);   // 0.0625
-  uint4 o;
-  const __half2 p15 = __hmul2(u2h2(prmt(v.x, v.z, 0x7632)), sixteenth);
-  const __half2 p37 = __hmul2(u2h2(prmt(v.y, v.w, 0x7632)), sixteenth);
-  o.x = h22u(__hsub2(u2h2(prmt(v.x, v.z, 0x5410)), p15));
-  o.y = h22u(p15);
-  o.z = h22u(__hsub2(u2h2(prmt(v.y, v.w, 0x5410)), p37));
-  o.w = h22u(p37);
-  return o;
-}
-
-__device__ __forceinline__ void unpack_w4_bytes(uint32_t w, uint32_t (&e)[4]) {
-  e[1] = prmt(w, 0u, 0x4240);      // bytes 0, 2 zero-extended into the two halves
-  e[3] = prmt(w, 0u, 0x4341);      // bytes 1, 3
-  e[0] = e[1] & 0x000F000Fu;
-  e[2] = e[3] & 0x000F000Fu;
-}
 
 // One 128-k block: `st` = stage base, `ablk` = this lane's activations of the block, `zt_blk` = the
 // block's group-sum table ([GPB][M][4] words).  tot accumulates 2^-24 * y.
@@ -1592,12 +1529,11 @@ bool gemv_w4_supported(const GemvArgs& a) {
   return a.bits == 4 && group_ok && a.K % 128 == 0 && a.N % 32 == 0 && (al & 15u) == 0 && a.M >= 1;
 }
 
-static int env_int(const char* name, int dflt) {
+int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return (v && *v) ? atoi(v) : dflt;
 }
 
-constexpr size_t kMaxDynSmem = 220 * 1024;
 
 struct W4Plan {
   int wc, splits, blocks_per_split;
@@ -1615,14 +1551,18 @@ static size_t w4_smem_bytes(int upg, int wc, int mt, int m, int blocks_per_split
          + (size_t)(splits > 1 ? splits : 0) * m * nt * sizeof(float);                // clus_sm
 }
 
-// developer knobs of one launch: tools/sweep.py (skip the math) and tools/trace.py (phase stamps)
-static void apply_debug_knobs(GemvArgs& a) {
-  a.debug_skip = env_int("XBIT_GEMV_DEBUG_SKIP", 0);
+// developer knobs of one launch: tools/sweep.py (skip the math) and tools/trace.py (phase stamps).  Only in the
+// -DXBIT_DEVTOOLS build (libxbitops_b200_dev.so, used by tools/); the shipped library has neither.
+void apply_debug_knobs(GemvArgs& a) {
+  a.debug_skip = 0;
   a.trace = nullptr;
+#ifdef XBIT_DEVTOOLS
+  a.debug_skip = env_int("XBIT_GEMV_DEBUG_SKIP", 0);
   if (const char* tp = getenv("XBIT_GEMV_TRACE")) {   // device buffer of [launch % 64][1024 CTAs][16] stamps
-    static int launches = 0;
-    a.trace = reinterpret_cast<unsigned long long*>(strtoull(tp, nullptr, 0)) + (size_t)(launches++ % 64) * 16384;
+    static std::atomic<int> launches{0};
+    a.trace = reinterpret_cast<unsigned long long*>(strtoull(tp, nullptr, 0)) + (size_t)(launches.fetch_add(1) % 64) * 16384;
   }
+#endif
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -1643,12 +1583,12 @@ static EncodeTiledFn encode_tiled_fn() {
 
 // Host-side cost matters for the per-call (e2e) figure: cuTensorMapEncodeTiled is a pure function of
 // its arguments, so the encoded maps are kept in a small cache keyed by all of them.
-static cudaError_t encode_2d(CUtensorMap* map, CUtensorMapDataType dt, const void* base, uint64_t inner, uint64_t outer,
-                             uint64_t row_bytes, uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle sw) {
-  using Key = std::tuple<int, const void*, uint64_t, uint64_t, uint64_t, uint32_t, uint32_t, int>;
+cudaError_t encode_2d(CUtensorMap* map, CUtensorMapDataType dt, const void* base, uint64_t inner, uint64_t outer,
+                      uint64_t row_bytes, uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle sw, CUtensorMapL2promotion promo) {
+  using Key = std::tuple<int, const void*, uint64_t, uint64_t, uint64_t, uint32_t, uint32_t, int, int>;
   static std::mutex mu;
   static auto* cache = new std::map<Key, CUtensorMap>();
-  const Key key((int)dt, base, inner, outer, row_bytes, box_inner, box_outer, (int)sw);
+  const Key key((int)dt, base, inner, outer, row_bytes, box_inner, box_outer, (int)sw, (int)promo);
   {
     std::lock_guard<std::mutex> lock(mu);
     auto it = cache->find(key);
@@ -1664,7 +1604,7 @@ static cudaError_t encode_2d(CUtensorMap* map, CUtensorMapDataType dt, const voi
   const cuuint32_t box[2] = {box_inner, box_outer};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = enc(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
-                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                         promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
   std::lock_guard<std::mutex> lock(mu);
   if (cache->size() >= 8192) cache->clear();
@@ -1673,7 +1613,7 @@ static cudaError_t encode_2d(CUtensorMap* map, CUtensorMapDataType dt, const voi
 }
 
 // opt in to large dynamic shared memory once per (device, kernel); not a stream operation
-static cudaError_t ensure_max_dyn_smem(const void* kern) {
+cudaError_t ensure_max_dyn_smem(const void* kern) {
   static std::mutex mu;
   static auto* done = new std::set<std::pair<int, const void*>>();
   int dev = 0;
@@ -1889,6 +1829,14 @@ cudaError_t launch_gemv_w4_simt(GemvArgs a, cudaStream_t stream) {
   apply_debug_knobs(a);
   W4Kernel k = pick_w4_kernel<0, 0>(upg, p.wc);
   return k ? launch_w4(k, a, p, upg, stream) : cudaErrorInvalidValue;
+}
+
+// true when the cluster split-K kernel has a decomposition for this problem (the staged activations of a large
+// M * K may not fit in shared memory for any K split)
+bool gemv_w4_mma_has_plan(GemvArgs a) {
+  if (!gemv_w4_supported(a) || a.M > 16) return false;
+  W4Plan p;
+  return plan_w4(a, a.M <= 8 ? 1 : 2, upg_of(a.groupsize), p);
 }
 
 cudaError_t launch_gemv_w4_mma(GemvArgs a, cudaStream_t stream) {

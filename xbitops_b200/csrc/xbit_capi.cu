@@ -80,7 +80,9 @@ size_t xbit_gemv_workspace_bytes(int M, int, int, int bits, int) {
   // balanced stream-K schedule (partial tiles + ready flags; left zeroed after every call).
   // Without it (NULL / too small) split-K is reduced through cluster shared memory instead.
   if (bits != 4) return 0;
-  return xbit::gemv_w4_streamk_workspace_bytes(M > 16 ? 16 : (M < 1 ? 1 : M));
+  const int m = M > 16 ? 16 : (M < 1 ? 1 : M);
+  const size_t sk = xbit::gemv_w4_streamk_workspace_bytes(m), pp = xbit::gemv_w4p_workspace_bytes(m);
+  return sk > pp ? sk : pp;
 }
 
 static int pick_family(const xbit::GemvArgs& a) {
@@ -98,6 +100,7 @@ static int pick_family(const xbit::GemvArgs& a) {
   if (forced == XBIT_GEMV_MMA) return XBIT_GEMV_MMA;
   if (forced == XBIT_GEMV_GENERIC) return XBIT_GEMV_GENERIC;
   if (forced == XBIT_GEMV_TCGEN05 && xbit::gemv_w4_tc5_supported(a)) return XBIT_GEMV_TCGEN05;
+  if (a.M <= 8 && xbit::gemv_w4p_applicable(a)) return XBIT_GEMV_PERSIST;
   return XBIT_GEMV_MMA;
 }
 
@@ -180,9 +183,21 @@ static int gemv_impl(const void* a_f16, const int32_t* qweight, const void* scal
     g.M = M - m0;
     xbit::GemvArgs probe = g;
     int family = family_req;
+    int auto_slab = 0;
     if (family == XBIT_GEMV_AUTO) {
-      probe.M = g.M > 16 ? 16 : g.M;
-      family = pick_family(probe);
+      // the largest slab of rows (16, 8, 4, 2, 1) one of the W4 kernels can stage; the generic kernel otherwise
+      // (e.g. M = 16 with K = 32768 has no K split that fits the activations in shared memory)
+      family = XBIT_GEMV_GENERIC;
+      for (int slab_try = g.M > 16 ? 16 : g.M; slab_try >= 1; slab_try = slab_try > 1 ? (slab_try + 1) / 2 : 0) {
+        probe.M = slab_try;
+        const int f = pick_family(probe);
+        if (f == XBIT_GEMV_GENERIC) break;
+        if (f != XBIT_GEMV_MMA || xbit::gemv_w4_mma_has_plan(probe) || use_streamk(probe, XBIT_GEMV_MMA, workspace, workspace_bytes)) {
+          family = f;
+          auto_slab = slab_try;
+          break;
+        }
+      }
     }
     int slab;
     cudaError_t e;
@@ -195,9 +210,14 @@ static int gemv_impl(const void* a_f16, const int32_t* qweight, const void* scal
         break;
       case XBIT_GEMV_MMA:
         if (!xbit::gemv_w4_supported(g)) return fail(XBIT_EINVAL, "MMA family needs bits=4, groupsize in {32, 64, 128}, K%%128=0, N%%32=0, 16-byte aligned pointers");
-        slab = g.M > 16 ? 16 : g.M; g.M = slab;
+        slab = auto_slab ? auto_slab : (g.M > 16 ? 16 : g.M); g.M = slab;
         if (use_streamk(g, XBIT_GEMV_MMA, workspace, workspace_bytes)) e = xbit::launch_gemv_w4_streamk(g, XBIT_GEMV_MMA, workspace, workspace_bytes, st);
         else e = xbit::launch_gemv_w4_mma(g, st);
+        break;
+      case XBIT_GEMV_PERSIST:
+        slab = auto_slab ? auto_slab : (g.M > 8 ? 8 : g.M); g.M = slab;
+        if (!xbit::gemv_w4p_applicable(g)) return fail(XBIT_EINVAL, "PERSIST family needs bits=4, groupsize in {32, 64, 128}, K%%128=0, N%%32=0, 16-byte aligned pointers and M*K small enough to stage");
+        e = xbit::launch_gemv_w4p(g, workspace, workspace_bytes, st);
         break;
       case XBIT_GEMV_TCGEN05:
         slab = g.M > 16 ? 16 : g.M; g.M = slab;

@@ -1,5 +1,6 @@
 // xbit_internal.h -- argument blocks and launcher prototypes shared by the C ABI and the kernels.
 #pragma once
+#include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -62,11 +63,16 @@ cudaError_t launch_dequant(const DqArgs& a, cudaStream_t stream, int* path_taken
 bool gemv_w4_supported(const GemvArgs& a);
 cudaError_t launch_gemv_w4_simt(GemvArgs a, cudaStream_t stream);   // M <= 4
 cudaError_t launch_gemv_w4_mma(GemvArgs a, cudaStream_t stream);    // M <= 16
+bool gemv_w4_mma_has_plan(GemvArgs a);                              // false: no K split stages M * K in shared memory
 // persistent, balanced stream-K variant of the two (needs workspace); false = not applicable here
 bool gemv_w4_streamk_applicable(const GemvArgs& a, int family);
 bool gemv_w4_prefers_streamk(const GemvArgs& a, int family);      // AUTO policy: cluster grid fills the machine badly
 size_t gemv_w4_streamk_workspace_bytes(int M);
 cudaError_t launch_gemv_w4_streamk(GemvArgs a, int family, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+// persistent per-SM schedule with per-warp TMA rings (gemv_w4p_sm100.cu): the default for M <= 8
+bool gemv_w4p_applicable(const GemvArgs& a);
+size_t gemv_w4p_workspace_bytes(int M);
+cudaError_t launch_gemv_w4p(const GemvArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 // tcgen05 + TMEM path (bits 4, groupsize 128, M <= 8)
 bool gemv_w4_tc5_supported(const GemvArgs& a);
 cudaError_t launch_gemv_w4_tc5(GemvArgs a, cudaStream_t stream);
@@ -74,6 +80,14 @@ cudaError_t launch_gemv_w4_tc5(GemvArgs a, cudaStream_t stream);
 cudaError_t launch_gemv_generic(GemvArgs a, cudaStream_t stream);
 
 int device_sm_count();
+int env_int(const char* name, int dflt);
+void apply_debug_knobs(GemvArgs& a);   // no-op unless built with -DXBIT_DEVTOOLS
+constexpr size_t kMaxDynSmem = 220 * 1024;
+// cached cuTensorMapEncodeTiled (a pure function of its arguments) and the one-time dynamic shared memory opt-in
+cudaError_t encode_2d(CUtensorMap* map, CUtensorMapDataType dt, const void* base, uint64_t inner, uint64_t outer,
+                      uint64_t row_bytes, uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle sw,
+                      CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+cudaError_t ensure_max_dyn_smem(const void* kern);
 cudaError_t launch_ll_unpack(const void* ll_in, void* out_f16, long long n_pairs, unsigned int* state, int chain_len, unsigned int* timeout_flag, cudaStream_t stream);
 cudaError_t launch_pull_rows(const void* src_host_devptr, void* dst, size_t bytes, cudaStream_t stream);
 cudaError_t launch_peers_wait(const unsigned int* flags, int world, int rank, unsigned int* timeout_flag, cudaStream_t stream);

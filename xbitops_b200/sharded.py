@@ -198,7 +198,10 @@ class ShardedQChain:
         self.max_rows = max_rows
         # a replayed / repeated chain starts again on buffer 0 while a slower rank may still be unpacking the last
         # layer's buffer: rotate over m buffers with (len - 1) % m != 0 so that the two never coincide
-        self.nbuf = next(m for m in range(2, 9) if (len(self.layers) - 1) % m != 0)
+        # (a single-layer chain has no such m: it alternates two buffers from one forward() to the next instead, which
+        # covers eager calls; a CAPTURED single-layer chain must not be replayed back to back without a rank barrier)
+        self.nbuf = next((m for m in range(2, 9) if (len(self.layers) - 1) % m != 0), 2)
+        self._first_buf = 0
         self._bufs = None
 
     def _buffers(self, device):
@@ -231,7 +234,7 @@ class ShardedQChain:
         st = torch.cuda.current_stream().cuda_stream
         src = x.data_ptr()
         for i, (q, sc, z, k, n) in enumerate(self.layers):
-            b = i % self.nbuf
+            b = (self._first_buf + i) % self.nbuf
             outs = (ctypes.c_void_p * self.world)(*[p + b * stride for p in ptrs])
             n_local = n // self.world
             capi.check(lib.xbit_gemv_f16_peers_ll(src, q.data_ptr(), sc.data_ptr(), z.data_ptr(), outs, state.data_ptr(), i,
@@ -243,6 +246,18 @@ class ShardedQChain:
         out = torch.empty((m, n_last), dtype=torch.float16, device=x.device)
         capi.check(lib.xbit_ll_unpack_f16(src, out.data_ptr(), m * n_last, state.data_ptr(), len(self.layers),
                                           state.data_ptr() + 12, st))
+        if len(self.layers) == 1:
+            self._first_buf ^= 1                             # never the buffer a slower rank may still be unpacking
         return out
+
+    def check_timeout(self) -> None:
+        """Synchronises and raises if a slot of any call so far did not arrive within the spin guard (a peer died or
+        never issued its call); clears the flag.  The kernels never hang, but their results are then garbage."""
+        if self._bufs is None:
+            return
+        state = self._bufs[2]
+        if int(state[3].item()) != 0:
+            state[3] = 0
+            raise RuntimeError("xbitops_b200: a flag-in-data slot never arrived (peer rank missing or out of step)")
 
     __call__ = forward
