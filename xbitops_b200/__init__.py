@@ -10,14 +10,14 @@ The compiled pybind11 twin (module name `XbitOps`, same as the reference) is bui
 There is no CPU fallback: the ops raise if the CUDA library is missing.
 """
 from . import capi, synth  # noqa: F401
-from .capi import GEMV_AUTO, GEMV_GENERIC, GEMV_MMA, GEMV_SIMT  # noqa: F401
+from .capi import GEMV_AUTO, GEMV_GENERIC, GEMV_MMA, GEMV_PERSIST, GEMV_SIMT  # noqa: F401
 
 __version__ = "0.1.0"
 
 
 def __getattr__(name):
     # torch is imported lazily so that `import xbitops_b200.synth` stays light
-    if name in ("dequant", "gemv"):
+    if name in ("dequant", "gemv", "set_static_weights", "get_static_weights"):
         from . import ops
         return getattr(ops, name)
     if name in ("ShardedQLinear", "shard_columns"):

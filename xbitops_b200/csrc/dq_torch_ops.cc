@@ -14,12 +14,17 @@
 //   * dtypes and the scales/qzeros shapes are validated explicitly; failures are RuntimeError
 //     (never exit()/abort());
 //   * gemv accepts every bits in [2, 8] and any groupsize >= 16 (the reference aborts unless
-//     bits == 4 && groupsize == 128, gemv_w4a16_pt.cu:152-155).
+//     bits == 4 && groupsize == 128, gemv_w4a16_pt.cu:152-155);
+//   * one extra module function, set_static_weights(bool) (default False, or env XBIT_STATIC_WEIGHTS=1 at import):
+//     the caller's promise that qweight / scales / qzeros are resident model weights, never written by the kernel
+//     that precedes a gemv call in its stream.  gemv then prefetches them under programmatic dependent launch while
+//     that kernel drains (XBIT_GEMV_FLAG_STATIC_WEIGHTS); activations are still read only after it has finished.
 // No kernel lives here: this file only validates, allocates and calls include/xbitops_b200.h.
 #include <ATen/cuda/CUDAContext.h>
 #include <c10/cuda/CUDAGuard.h>
 #include <torch/extension.h>
 
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <utility>
@@ -60,6 +65,11 @@ void check_quant_args(const torch::Tensor& qweight, const torch::Tensor& scales,
   TORCH_CHECK(scales.device() == qweight.device() && qzeros.device() == qweight.device(),
               "qweight, scales and qzeros must be on the same device");
 }
+
+std::atomic<bool> g_static_weights{[] {
+  const char* v = std::getenv("XBIT_STATIC_WEIGHTS");
+  return v && *v && *v != '0';
+}()};
 
 void raise_if(int rc) { TORCH_CHECK(rc == XBIT_OK, "xbitops_b200: ", xbit_last_error()); }
 
@@ -126,10 +136,11 @@ torch::Tensor op_gemv(const torch::Tensor& input_a, const torch::Tensor& qweight
       ws = gemv_workspace(qweight.device(), stream, ws_bytes);
       ws_ptr = ws.data_ptr();
     }
-    raise_if(xbit_gemv_f16(input_a.data_ptr(), qweight.data_ptr<int32_t>(), f16_scale.data_ptr(),
-                           qzeros.data_ptr<int32_t>(), output.data_ptr(), (int)mat_m, in_features, (int)qweight.size(1),
-                           bits, groupsize, add_zero_bias, qweight.size(1), ws_ptr, ws_bytes,
-                           reinterpret_cast<xbit_stream_t>(stream)));
+    raise_if(xbit_gemv_f16_ex(input_a.data_ptr(), qweight.data_ptr<int32_t>(), f16_scale.data_ptr(),
+                              qzeros.data_ptr<int32_t>(), output.data_ptr(), (int)mat_m, in_features, (int)qweight.size(1),
+                              bits, groupsize, add_zero_bias, qweight.size(1), ws_ptr, ws_bytes,
+                              XBIT_GEMV_AUTO | (g_static_weights.load() ? XBIT_GEMV_FLAG_STATIC_WEIGHTS : 0),
+                              reinterpret_cast<xbit_stream_t>(stream)));
   }
   if (ori_dtype == torch::kBFloat16) output = output.to(torch::kBFloat16);
   return output;
@@ -146,4 +157,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         "gemv, \nfunction type: const torch::Tensor& input_a, const torch::Tensor& qweight, "
         "const torch::Tensor& scales, const torch::Tensor& qzeros, int groupsize, int bits, int in_features, "
         "int add_zero_bias");
+  m.def("set_static_weights", [](bool on) { g_static_weights.store(on); },
+        "promise that the weight tensors passed to gemv are never written by the kernel preceding the call in its "
+        "stream (resident model weights): gemv then prefetches them while that kernel drains");
+  m.def("get_static_weights", []() { return g_static_weights.load(); });
 }

@@ -38,7 +38,7 @@
 
 namespace xbit {
 
-constexpr int kPMaxWarps = 16;                      // consumer warps per CTA: 8 (two blocks per step), 12 or 16 (one)
+
 constexpr int kPMaxRing = 8;
 constexpr long long kPSpinGuardClocks = 60000000000ll;   // ~30 s: see kSpinGuardClocks in gemv_sm100.cu
 
@@ -51,9 +51,11 @@ struct W4PArgs {
   int nb;                   // 128-k blocks per tile = K / 128
   int total;                // tiles * nb
   int unit;                 // CTA boundaries are multiples of `unit` blocks: 1 (stream-K, needs ws) or nb (tile aligned)
+  int uq, ur;               // (total / unit) = uq * grid + ur
   int ring;                 // two-block slots per consumer warp
   int static_weights;
   int all_wait;             // every consumer warp executes griddepcontrol.wait (comparison knob)
+  int stage_redux;          // group reductions of the activation staging with REDUX instead of shuffle trees (A/B knob)
   int prefetch_delay;       // SM clocks the producer waits before its first request (only when it starts ahead of the wait)
   const __half* scales;     // [G, N]: copied into the rings with cp.async (64 bytes per block and group: too small for TMA requests)
   const uint32_t* qzeros;   // [G, zwords]
@@ -63,13 +65,13 @@ struct W4PArgs {
   int debug_skip;
 };
 
-template <int UPG>
+template <int UPG, int BPS>
 struct W4PCfg {
   static constexpr int GPB = 4 / UPG;                                   // scale groups per 128-k block
   static constexpr int kBlockBytes = 2048;                              // 16 word-rows x 32 columns
-  static constexpr int kWSlot = 2 * kBlockBytes;                        // a ring slot holds the two blocks of a step
-  static constexpr int kSSlot = 2 * GPB * 64;                           // their scale rows (32 columns x fp16)
-  static constexpr int kZSlot = 2 * GPB * 16;                           // their zero rows (4 words)
+  static constexpr int kWSlot = BPS * kBlockBytes;                      // a ring slot holds BPS (1 or 2) consecutive blocks
+  static constexpr int kSSlot = BPS * GPB * 64;                         // their scale rows (32 columns x fp16)
+  static constexpr int kZSlot = BPS * GPB * 16;                         // their zero rows (4 words)
 };
 
 __device__ __forceinline__ void cp_async_16(void* dst_smem, const void* src) {
@@ -183,6 +185,107 @@ __device__ __forceinline__ void w4p_consume(const unsigned char* const (&wp)[NB]
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Integer block math (groupsize 128, M <= 2): 2 LOP3 per packed word instead of 2 PRMT + 2 LOP3, 8 IMMA per block
+// instead of 18 HMMA, dependent MMA chains of 4 instead of 9.
+//   * A operand = the packed word itself, masked: (w & 0x0F0F0F0F) are the even nibbles of a word as four u8, and
+//     (w & 0xF0F0F0F0) the odd nibbles times 16 -- still u8, so no shift is needed;
+//   * B operand = the activations as 24-bit fixed point relative to the largest |a| of their scale group, split into
+//     three unsigned byte planes: u = a * 2^(22-E) + 2^22 is read straight out of the mantissa of
+//     fmaf(a, 2^(22-E), 1.5 * 2^23) (odd k: a * 2^(18-E), to undo the 16 of the A operand), its three low bytes are the
+//     planes, and a fourth plane of ones gives S = sum_k A_k for the 2^22 offset:
+//         sum_k A_k q_k = D0 + 256 D1 + 65536 D2 - 2^22 S,   all four sums exact in int32;
+//     rounding the activations to 2^(E-23) (odd k: 2^(E-19)) of their group maximum is 2 to 5 orders of magnitude below
+//     the fp16 rounding of the result;
+//   * mma.sync.m16n8k32.u8.u8.s32: weight columns on M, (row 0: d0 d1 d2 ones, row 1: d0 d1 d2 ones) on N, so lane
+//     (t, g) holds, for its four weight columns, the pair (D0, D1) or (D2, S) of activation row t / 2 and folds it with
+//     ONE integer multiply-add (D0 + 256 D1, resp. D2 - 64 S, to be scaled by 65536) before the single I2F;
+//   * the zero point is applied per lane and column: -(s z) * sum_k a_k, with the group sums staged next to the group's
+//     2^(E-22).
+struct W4PLaneI {
+  uint32_t w_x0;            // byte offset of this lane's 16-byte chunk in a weight block for even units (odd: ^ 16)
+  uint32_t s_off, z_off;    // byte offsets of this lane's 4 scales / 4 zero nibbles in a block's scale / zero row
+  const unsigned char* bptr;   // digit plane of this lane's B column (lane / 4), or the ones / zero constant
+  int bstride;              // bytes per word-row in that plane: 8, or 0 for the constants
+  int lane_row;             // 2 * (lane % 4): this lane's word-row inside a unit pair
+  int crow4;                // 4 * (activation row of this lane's accumulators) = 4 * ((lane % 4) / 2)
+  int cmul;                 // 256 for (D0, D1) lanes, -64 for (D2, S) lanes
+  uint32_t ssel;            // PRMT selector: scale of column (lane % 4) of the lane's four into the low half
+  int zsh;                  // 4 * (lane % 4)
+  float zbias;
+};
+
+__device__ __forceinline__ void pimma(int (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void pimma_zero(int (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+      : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(0));
+}
+
+// NB (1 or 2) blocks of 128 k = one scale group each.  wrow[b] = first word-row of the block inside the activation
+// row (16 * k-block), gt[b] = the group's table entry {2^(E-22) row 0, row 1, sum_k a_k row 0, row 1}.
+// tot[tt][h] accumulates sf * 2^(E-22) * (D0 + 256 D1 | D2 - 64 S) for weight column 4g + 2tt + h; zc[m] the zero-point
+// term of column 4g + t for activation row m.
+template <int NB>
+__device__ __forceinline__ void w4p_consume_i8(const unsigned char* const (&wp)[NB], const unsigned char* const (&sp)[NB],
+                                               const unsigned char* const (&zp)[NB], const int (&wrow)[NB],
+                                               const float* const (&gt)[NB], const W4PLaneI& L, float (&tot)[2][2], float (&zc)[2]) {
+  uint2 sraw[NB];
+  uint32_t zraw[NB];
+  float gsv[NB];
+  float2 aq[NB];
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    sraw[b] = *reinterpret_cast<const uint2*>(sp[b] + L.s_off);
+    zraw[b] = *reinterpret_cast<const unsigned short*>(zp[b] + L.z_off);
+    gsv[b] = *reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(gt[b]) + L.crow4);
+    aq[b] = *reinterpret_cast<const float2*>(gt[b] + 2);
+  }
+  int acc[NB][2][4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int urow = 8 * (u >> 1) + (u & 1);
+    uint4 wv[NB];
+    uint2 bf[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      wv[b] = *reinterpret_cast<const uint4*>(wp[b] + ((u & 1) ? (L.w_x0 ^ 16u) : L.w_x0) + urow * 128);
+      bf[b] = *reinterpret_cast<const uint2*>(L.bptr + (wrow[b] + urow + L.lane_row) * L.bstride);
+    }
+#pragma unroll
+    for (int tt = 0; tt < 2; ++tt)
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        const uint32_t w0 = tt == 0 ? wv[b].x : wv[b].z, w1 = tt == 0 ? wv[b].y : wv[b].w;
+        const uint32_t a0 = w0 & 0x0F0F0F0Fu, a1 = w1 & 0x0F0F0F0Fu, a2 = w0 & 0xF0F0F0F0u, a3 = w1 & 0xF0F0F0F0u;
+        if (u == 0) pimma_zero(acc[b][tt], a0, a1, a2, a3, bf[b].x, bf[b].y);
+        else        pimma(acc[b][tt], a0, a1, a2, a3, bf[b].x, bf[b].y);
+      }
+  }
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    const float2 s01 = __half22float2(u2h2(sraw[b].x));
+    const float2 s23 = __half22float2(u2h2(sraw[b].y));
+    const float sfg[4] = {s01.x * gsv[b], s01.y * gsv[b], s23.x * gsv[b], s23.y * gsv[b]};
+#pragma unroll
+    for (int tt = 0; tt < 2; ++tt)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int v = acc[b][tt][2 * h] + L.cmul * acc[b][tt][2 * h + 1];
+        tot[tt][h] = fmaf(sfg[2 * tt + h], (float)v, tot[tt][h]);
+      }
+    // zero point of column 4g + t: -(s * (z + bias)) * sum_k a_k per activation row
+    const float sz = __half2float(__ushort_as_half((unsigned short)prmt(sraw[b].x, sraw[b].y, L.ssel))) *
+                     ((float)((zraw[b] >> L.zsh) & 0xFu) + L.zbias);
+    zc[0] = fmaf(sz, aq[b].x, zc[0]);
+    zc[1] = fmaf(sz, aq[b].y, zc[1]);
+  }
+}
+
 // slice (eighth of the CTA's range) of consumer warp w: warps w and w + 4 share an SM sub-partition and adjacent
 // slices differ by at most one block, so every sub-partition gets two ADJACENT slices
 template <int NW>
@@ -192,12 +295,20 @@ __device__ __forceinline__ int p_slice_of(int w) { return (w & 3) * (NW / 4) + (
 // MODE 1 (DUAL): a ring per warp, the two blocks together (two accumulator sets); MODE 2 (PAIR): a ring per PAIR of
 // warps, warp 2p takes the first block of every step and warp 2p+1 the second -- 16 consumer warps at 56 registers
 // share the 8 rings (and the shared memory) of the 8-warp forms.  Two CTAs (of consecutive launches) per SM.
-template <int UPG, int NW, int MODE>
-__global__ void __launch_bounds__((NW + 1) * 32, 2)
+// BPS: blocks per ring slot.  2 = one TMA request per step of two blocks; 1 = one request per block, which keeps more
+// requests in flight per byte of shared memory (a consumer holds ONE 2 KiB slot while it computes, not two blocks'
+// worth): the form for matrices that do not fit the rings whole and keep streaming while the CTA computes.
+// MINB: CTAs per SM the register budget is cut for: 2 = two launches co-resident (the whole share of a CTA fits its
+// rings and is prefetched while the previous launch computes), 1 = one CTA per SM with 16 consumer warps and deeper rings
+// (larger matrices, which keep streaming while they compute: what counts there is the compute rate and bytes in flight).
+template <int UPG, int NW, int MODE, bool I8, int BPS, int MINB>
+__global__ void __launch_bounds__((NW + 1) * 32, MINB)
 gemv_w4p_kernel(const __grid_constant__ CUtensorMap wmap2, const __grid_constant__ CUtensorMap wmap1, const W4PArgs a) {
-  using Cfg = W4PCfg<UPG>;
+  using Cfg = W4PCfg<UPG, BPS>;
   constexpr int GPB = Cfg::GPB;
   constexpr bool DUAL = MODE == 1, PAIR = MODE == 2;
+  static_assert(!PAIR || BPS == 2, "a pair of warps shares the two blocks of a slot");
+  static_assert(!I8 || UPG == 4, "the integer block math covers groupsize 128");
   constexpr int kPWarps = PAIR ? NW / 2 : NW;       // rings = slices of the CTA's range
   constexpr int kPConsumerThreads = NW * 32;
   constexpr int LPR = kPWarps <= 8 ? 4 : 2;         // producer lanes per ring
@@ -219,30 +330,38 @@ gemv_w4p_kernel(const __grid_constant__ CUtensorMap wmap2, const __grid_constant
   uint64_t* empty_bar = full_bar + kPWarps * kPMaxRing;
   int* cnt_sm = reinterpret_cast<int*>(empty_bar + kPWarps * kPMaxRing);              // [32] arrival counters of shared tiles
   int* bnd_sm = cnt_sm + 32;                                                          // [slices + 1] first block of every slice
-  float* part_sm = reinterpret_cast<float*>(bnd_sm + 32);                             // [slices][2 warps][2][2][M][32] partial tiles
-  uint32_t* zt_sm = reinterpret_cast<uint32_t*>(part_sm + kPWarps * 8 * a.M * 32);    // [groups][M][4]: (hi, lo) of sum_k a_k / 64, 3 zero words
+  float* part_sm = reinterpret_cast<float*>(bnd_sm + 32);                             // [slices]([2 warps])[2]([2])[M][32] partial tiles
+  uint32_t* zt_sm = reinterpret_cast<uint32_t*>(part_sm + kPWarps * (PAIR ? 8 : 2) * a.M * 32);    // [groups][M][4]: (hi, lo) of sum_k a_k / 64, 3 zero words
   __half* act_sm = reinterpret_cast<__half*>(zt_sm + (size_t)nb * GPB * a.M * 4);     // [M][pitch]
+  // integer block math instead: group table {2^(E-22) row 0, row 1, sum_k a_k row 0, row 1}, the ones / zero constants,
+  // and three digit planes per activation row ([K/8 word-rows][even k x4, odd k x4] bytes each; plane p starts
+  // p * (K + 128) + 8 * {0, 1, 8, 9}[p % 4] bytes in, which keeps the 8 lanes (t, g < 3) of a half-warp on distinct banks)
+  float* gt_sm = reinterpret_cast<float*>(zt_sm);                                     // [groups][4]
+  unsigned char* const_sm = reinterpret_cast<unsigned char*>(gt_sm + (size_t)nb * 4);    // 8 x 0x01, 8 x 0x00
+  unsigned char* dig_sm = const_sm + 16;                                              // [3 * M planes]
+  auto plane_off = [&](int p) { return (size_t)p * (a.K + 128) + 8 * ((p & 1) + 8 * ((p >> 1) & 1)); };
 
-  // this CTA's range of the tile-major block list
-  const long long U = a.total / a.unit;
-  const int lo = (int)(U * c / G) * a.unit, hi = (int)(U * (c + 1) / G) * a.unit;
+  // this CTA's range of the tile-major block list: units [U*c/G, U*(c+1)/G) with U = uq*G + ur (no 64-bit division here:
+  // the time from CTA start to the first TMA request is on the critical path whenever the CTA could not start early)
+  auto unit_begin = [&](int cc) { return a.uq * cc + (a.ur * cc) / G; };
+  const int lo = unit_begin(c) * a.unit, hi = unit_begin(c + 1) * a.unit;
   const int len = hi - lo;
+  const long long U = (long long)a.uq * G + a.ur;
 
-  if (tid == 0) {
-    P_TRACE(0);
+  if (tid < kPWarps * kPMaxRing) {
+    if (tid == 0) {
+      P_TRACE(0);
 #ifdef XBIT_DEVTOOLS
-    {
       unsigned int smid;
       asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
       P_TRACE_VALUE(12, (unsigned long long)smid + 1);
-    }
 #endif
-    for (int w = 0; w < kPWarps; ++w)
-      for (int s = 0; s < R; ++s) {
-        mbar_init(&full_bar[w * kPMaxRing + s], 1 + LPR);   // the TMA issuer's expect_tx arrival + LPR cp.async arrivals
-        mbar_init(&empty_bar[w * kPMaxRing + s], PAIR ? 2 : 1);
-      }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if ((tid & (kPMaxRing - 1)) < R) {
+      mbar_init(&full_bar[tid], 1 + LPR);           // the TMA issuer's expect_tx arrival + LPR cp.async arrivals
+      mbar_init(&empty_bar[tid], PAIR ? 2 : 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
   }
   if (tid < 32) {
     cnt_sm[tid] = 0;
@@ -278,7 +397,7 @@ gemv_w4p_kernel(const __grid_constant__ CUtensorMap wmap2, const __grid_constant
       const unsigned char* zbase = reinterpret_cast<const unsigned char*>(a.qzeros);
       int s = 0, ph = 0;
       for (int n = 0; j < jend; ++n) {
-        const int nblk = min(2, min(jend - j, nb - kb));
+        const int nblk = min(BPS, min(jend - j, nb - kb));
         uint64_t* fb = &full_bar[w * kPMaxRing + s];
         if (n >= R) mbar_wait(&empty_bar[w * kPMaxRing + s], ph ^ 1);
         if (sub == 0) {
@@ -289,14 +408,14 @@ gemv_w4p_kernel(const __grid_constant__ CUtensorMap wmap2, const __grid_constant
         unsigned char* zdst = zring + (w * R + s) * Cfg::kZSlot;
         const int rows = nblk * GPB, row0 = kb * GPB;
 #pragma unroll
-        for (int rr = 0; rr < 2 * GPB; ++rr)
+        for (int rr = 0; rr < BPS * GPB; ++rr)
           if (rr < rows) {
 #pragma unroll
             for (int ch = 0; ch < 4; ch += LPR)
               cp_async_16(sdst + rr * 64 + ch * 16, sbase + ((size_t)(row0 + rr) * a.N + tile * 32) * 2 + ch * 16);
           }
 #pragma unroll
-        for (int rr = 0; rr < 2 * GPB; ++rr)
+        for (int rr = 0; rr < BPS * GPB; ++rr)
           if (rr < rows && (rr % LPR) == sub) cp_async_16(zdst + rr * 16, zbase + ((size_t)(row0 + rr) * a.zwords + tile * 4) * 4);
         cp_async_mbar_arrive_noinc(fb);
         j += nblk;
@@ -324,6 +443,23 @@ gemv_w4p_kernel(const __grid_constant__ CUtensorMap wmap2, const __grid_constant
     L.brow_off = m * pitch + lane_row * 8;
     L.zt_off = (m * 4 + r) * 4;
   }
+  W4PLaneI LI;
+  if constexpr (I8) {
+    LI.w_x0 = L.w_x0;
+    LI.s_off = L.s_off;
+    LI.z_off = L.z_off;
+    // B column c8: planes (row 0: d0 d1 d2, ones; row 1: d0 d1 d2, ones); rows >= M read the zero constant
+    const int brow = c8 >> 2, bdig = c8 & 3;
+    if (bdig == 3) { LI.bptr = const_sm; LI.bstride = 0; }
+    else if (brow >= a.M) { LI.bptr = const_sm + 8; LI.bstride = 0; }
+    else { LI.bptr = dig_sm + plane_off(brow * 3 + bdig); LI.bstride = 8; }
+    LI.lane_row = 2 * r;
+    LI.crow4 = 4 * (r >> 1);
+    LI.cmul = (r & 1) ? -64 : 256;
+    LI.ssel = (r & 1) ? (0x4400u | ((r & 2) ? 0x76u : 0x32u)) : (0x4400u | ((r & 2) ? 0x54u : 0x10u));
+    LI.zsh = 4 * r;
+    LI.zbias = (float)a.zero_bias;
+  }
 
   const int rg = PAIR ? warp >> 1 : warp, hh = PAIR ? warp & 1 : 0;   // ring, and which block of a step this warp takes
   const int rho = slice_of_ring(rg);
@@ -343,6 +479,92 @@ gemv_w4p_kernel(const __grid_constant__ CUtensorMap wmap2, const __grid_constant
   if (a.all_wait || warp == 0) griddep_wait();
   if (!a.all_wait) asm volatile("bar.sync 1, %0;" ::"n"(kPConsumerThreads) : "memory");
   if (tid == 0) P_TRACE(2);
+  if constexpr (I8) {
+    // stage the activations once per CTA as three unsigned byte planes of 24-bit fixed point relative to the largest |a|
+    // of their scale group (see w4p_consume_i8), plus per group 2^(E-22) and sum_k a_k.  A group = 16 consecutive
+    // vectors = half a warp.
+    if (tid < 4) reinterpret_cast<uint32_t*>(const_sm)[tid] = tid < 2 ? 0x01010101u : 0u;
+    const int vecs = a.K >> 3;
+    constexpr int kBatch = 2;
+    for (int m = 0; m < a.M; ++m) {
+      const uint4* arow = reinterpret_cast<const uint4*>(a.a + (size_t)m * a.K);
+      unsigned char* const pl0 = dig_sm + plane_off(m * 3 + 0);
+      unsigned char* const pl1 = dig_sm + plane_off(m * 3 + 1);
+      unsigned char* const pl2 = dig_sm + plane_off(m * 3 + 2);
+      for (int v0 = warp * 32; v0 < vecs; v0 += kBatch * kPConsumerThreads) {
+        uint4 val[kBatch];
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b) {
+          const int v = v0 + b * kPConsumerThreads + lane;
+          val[b] = make_uint4(0, 0, 0, 0);
+          if (v < vecs) val[b] = __ldcg(arow + v);
+        }
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b) {
+          const int vw = v0 + b * kPConsumerThreads;                // warp-uniform
+          if (vw >= vecs) break;
+          const int v = vw + lane;
+          const bool ok = v < vecs;
+          const float2 f0 = __half22float2(u2h2(val[b].x)), f1 = __half22float2(u2h2(val[b].y));
+          const float2 f2 = __half22float2(u2h2(val[b].z)), f3 = __half22float2(u2h2(val[b].w));
+          // largest |a| of the group as fp16 bits (the bit patterns of non-negative halves order like integers): one
+          // REDUX over the half-warp instead of a shuffle tree -- this phase sits on the critical path of every call
+          const __half2 ax = __hmax2(__habs2(u2h2(val[b].x)), __habs2(u2h2(val[b].y)));
+          const __half2 az = __hmax2(__habs2(u2h2(val[b].z)), __habs2(u2h2(val[b].w)));
+          const uint32_t am2 = h22u(__hmax2(ax, az));
+          // (full-warp REDUX twice, one per half: a half-warp mask makes the compiler serialise the halves)
+          const bool upper = (lane & 16) != 0;
+          const uint32_t amax1 = max(am2 & 0xFFFFu, am2 >> 16);
+          uint32_t amax;
+          if (a.stage_redux) {
+            const uint32_t mlo = __reduce_max_sync(0xffffffffu, upper ? 0u : amax1);
+            const uint32_t mhi = __reduce_max_sync(0xffffffffu, upper ? amax1 : 0u);
+            amax = upper ? mhi : mlo;
+          } else {
+            amax = amax1;
+#pragma unroll
+            for (int o = 1; o < 16; o <<= 1) amax = max(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+          }
+          // |a| < 2^E with E = exponent field - 14; q = a * 2^(22-E) (odd k: 2^(18-E)); inf / nan activations poison the group
+          const uint32_t eb = amax >> 10;
+          const float se = __uint_as_float((163u - eb) << 23), so = __uint_as_float((159u - eb) << 23);
+          const float gs = eb >= 31u ? __uint_as_float(0x7fc00000u) : __uint_as_float((91u + eb) << 23);
+          const float kMagic = 12582912.f;         // 1.5 * 2^23: the bits of (q + kMagic) are 0x4B400000 + q
+          const uint32_t u0 = __float_as_uint(fmaf(f0.x, se, kMagic)), u1 = __float_as_uint(fmaf(f0.y, so, kMagic));
+          const uint32_t u2 = __float_as_uint(fmaf(f1.x, se, kMagic)), u3 = __float_as_uint(fmaf(f1.y, so, kMagic));
+          const uint32_t u4 = __float_as_uint(fmaf(f2.x, se, kMagic)), u5 = __float_as_uint(fmaf(f2.y, so, kMagic));
+          const uint32_t u6 = __float_as_uint(fmaf(f3.x, se, kMagic)), u7 = __float_as_uint(fmaf(f3.y, so, kMagic));
+          // sum_k q_k in units of 2^(E-22), exactly, in integers (|.| <= 2^29): even k + 16 * odd k - 68 * 0x4B400000
+          const int q1 = (int)(((u0 + u2) + (u4 + u6)) + 16u * ((u1 + u3) + (u5 + u7)) - 68u * 0x4B400000u);
+          int qsum;
+          if (a.stage_redux) {
+            const int slo = __reduce_add_sync(0xffffffffu, upper ? 0 : q1);
+            const int shi = __reduce_add_sync(0xffffffffu, upper ? q1 : 0);
+            qsum = upper ? shi : slo;
+          } else {
+            qsum = q1;
+#pragma unroll
+            for (int o = 1; o < 16; o <<= 1) qsum += __shfl_xor_sync(0xffffffffu, qsum, o);
+          }
+          const float sum = (float)qsum * gs;
+          // byte j of (u0, u2, u4, u6) -> even word of plane j, of (u1, u3, u5, u7) -> odd word
+          const uint32_t e02 = prmt(u0, u2, 0x5140), e46 = prmt(u4, u6, 0x5140);
+          const uint32_t o13 = prmt(u1, u3, 0x5140), o57 = prmt(u5, u7, 0x5140);
+          const uint32_t e02h = prmt(u0, u2, 0x0062), e46h = prmt(u4, u6, 0x0062);
+          const uint32_t o13h = prmt(u1, u3, 0x0062), o57h = prmt(u5, u7, 0x0062);
+          if (ok) {
+            *reinterpret_cast<uint2*>(pl0 + (size_t)v * 8) = make_uint2(prmt(e02, e46, 0x5410), prmt(o13, o57, 0x5410));
+            *reinterpret_cast<uint2*>(pl1 + (size_t)v * 8) = make_uint2(prmt(e02, e46, 0x7632), prmt(o13, o57, 0x7632));
+            *reinterpret_cast<uint2*>(pl2 + (size_t)v * 8) = make_uint2(prmt(e02h, e46h, 0x5410), prmt(o13h, o57h, 0x5410));
+            if ((lane & 15) == 0) {
+              gt_sm[(v >> 4) * 4 + m] = gs;
+              gt_sm[(v >> 4) * 4 + 2 + m] = sum;
+            }
+          }
+        }
+      }
+    }
+  } else
   {
     // stage the activations once per CTA as (a0 - a1/16, a1/16) pairs in fragment order, and per scale group and
     // batch row sum_k a_k / 64 as an fp16 (hi, lo) pair for the zero-point MMA.  All loads of a thread are issued
@@ -389,6 +611,7 @@ gemv_w4p_kernel(const __grid_constant__ CUtensorMap wmap2, const __grid_constant
 
 #ifdef XBIT_DEVTOOLS
   const long long loop0 = a.trace ? clock64() : 0;
+  long long wait_clk = 0;
   bool first_wait = true;
 #endif
 
@@ -399,12 +622,21 @@ gemv_w4p_kernel(const __grid_constant__ CUtensorMap wmap2, const __grid_constant
     for (int tt = 0; tt < 2; ++tt)
 #pragma unroll
       for (int i = 0; i < 4; ++i) tot[tt][i] = 0.f;
+    float toti[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, zci[2] = {0.f, 0.f};   // integer block math (I8)
 
     for (int i = 0; i < cnt; i += 2) {
       const int s0 = s, ph0 = ph;
       if (++s == R) { s = 0; ph ^= 1; }
-      mbar_wait(&my_full[s0], ph0);
+      const bool two_slots = BPS == 1 && i + 2 <= cnt;              // the step's second block sits in the next slot
+      const int s1 = s, ph1 = ph;
+      if (two_slots) { if (++s == R) { s = 0; ph ^= 1; } }
 #ifdef XBIT_DEVTOOLS
+      const long long w0c = a.trace ? clock64() : 0;
+#endif
+      mbar_wait(&my_full[s0], ph0);
+      if (two_slots) mbar_wait(&my_full[s1], ph1);
+#ifdef XBIT_DEVTOOLS
+      if (a.trace) wait_clk += clock64() - w0c;
       if (first_wait && tid == 0) P_TRACE(4);
       first_wait = false;
       if (a.debug_skip != 1)
@@ -413,9 +645,46 @@ gemv_w4p_kernel(const __grid_constant__ CUtensorMap wmap2, const __grid_constant
         const unsigned char* const w0 = my_w + s0 * Cfg::kWSlot;
         const unsigned char* const sc0 = my_s + s0 * Cfg::kSSlot;
         const unsigned char* const z0 = my_z + s0 * Cfg::kZSlot;
+        const unsigned char* const w1 = BPS == 2 ? w0 + Cfg::kBlockBytes : my_w + s1 * Cfg::kWSlot;      // the step's second block
+        const unsigned char* const sc1 = BPS == 2 ? sc0 + GPB * 64 : my_s + s1 * Cfg::kSSlot;
+        const unsigned char* const z1 = BPS == 2 ? z0 + GPB * 16 : my_z + s1 * Cfg::kZSlot;
         const __half* const a0 = act_sm + (kb + i) * 128;
         const unsigned char* const zt0 = zt_bytes + (size_t)(kb + i) * GPB * zt_group_bytes;
-        if (PAIR) {
+        if constexpr (I8) {
+          const float* const g0 = gt_sm + (size_t)(kb + i) * 4;
+          if (PAIR) {
+            if (i + hh < cnt) {
+              const unsigned char* const wp[1] = {w0 + hh * Cfg::kBlockBytes};
+              const unsigned char* const sp[1] = {sc0 + hh * 64};
+              const unsigned char* const zp[1] = {z0 + hh * 16};
+              const int wr[1] = {(kb + i + hh) * 16};
+              const float* const gp[1] = {g0 + hh * 4};
+              w4p_consume_i8<1>(wp, sp, zp, wr, gp, LI, toti, zci);
+            }
+          } else if (DUAL && i + 2 <= cnt) {
+            const unsigned char* const wp[2] = {w0, w1};
+            const unsigned char* const sp[2] = {sc0, sc1};
+            const unsigned char* const zp[2] = {z0, z1};
+            const int wr[2] = {(kb + i) * 16, (kb + i + 1) * 16};
+            const float* const gp[2] = {g0, g0 + 4};
+            w4p_consume_i8<2>(wp, sp, zp, wr, gp, LI, toti, zci);
+          } else {
+            const unsigned char* const wp[1] = {w0};
+            const unsigned char* const sp[1] = {sc0};
+            const unsigned char* const zp[1] = {z0};
+            const int wr[1] = {(kb + i) * 16};
+            const float* const gp[1] = {g0};
+            w4p_consume_i8<1>(wp, sp, zp, wr, gp, LI, toti, zci);
+            if (!DUAL && i + 2 <= cnt) {
+              const unsigned char* const wp1[1] = {w1};
+              const unsigned char* const sp1[1] = {sc1};
+              const unsigned char* const zp1[1] = {z1};
+              const int wr1[1] = {(kb + i + 1) * 16};
+              const float* const gp1[1] = {g0 + 4};
+              w4p_consume_i8<1>(wp1, sp1, zp1, wr1, gp1, LI, toti, zci);
+            }
+          }
+        } else if (PAIR) {
           if (i + hh < cnt) {
             const unsigned char* const wp[1] = {w0 + hh * Cfg::kBlockBytes};
             const unsigned char* const sp[1] = {sc0 + hh * GPB * 64};
@@ -425,9 +694,9 @@ gemv_w4p_kernel(const __grid_constant__ CUtensorMap wmap2, const __grid_constant
             w4p_consume<UPG, 1>(wp, sp, zp, ap, ztp, zt_group_bytes, L, tot);
           }
         } else if (DUAL && i + 2 <= cnt) {
-          const unsigned char* const wp[2] = {w0, w0 + Cfg::kBlockBytes};
-          const unsigned char* const sp[2] = {sc0, sc0 + GPB * 64};
-          const unsigned char* const zp[2] = {z0, z0 + GPB * 16};
+          const unsigned char* const wp[2] = {w0, w1};
+          const unsigned char* const sp[2] = {sc0, sc1};
+          const unsigned char* const zp[2] = {z0, z1};
           const __half* const ap[2] = {a0, a0 + 128};
           const unsigned char* const ztp[2] = {zt0, zt0 + GPB * zt_group_bytes};
           w4p_consume<UPG, 2>(wp, sp, zp, ap, ztp, zt_group_bytes, L, tot);
@@ -439,9 +708,9 @@ gemv_w4p_kernel(const __grid_constant__ CUtensorMap wmap2, const __grid_constant
           const unsigned char* const ztp[1] = {zt0};
           w4p_consume<UPG, 1>(wp, sp, zp, ap, ztp, zt_group_bytes, L, tot);
           if (!DUAL && i + 2 <= cnt) {
-            const unsigned char* const wp1[1] = {w0 + Cfg::kBlockBytes};
-            const unsigned char* const sp1[1] = {sc0 + GPB * 64};
-            const unsigned char* const zp1[1] = {z0 + GPB * 16};
+            const unsigned char* const wp1[1] = {w1};
+            const unsigned char* const sp1[1] = {sc1};
+            const unsigned char* const zp1[1] = {z1};
             const __half* const ap1[1] = {a0 + 128};
             const unsigned char* const ztp1[1] = {zt0 + GPB * zt_group_bytes};
             w4p_consume<UPG, 1>(wp1, sp1, zp1, ap1, ztp1, zt_group_bytes, L, tot);
@@ -449,7 +718,10 @@ gemv_w4p_kernel(const __grid_constant__ CUtensorMap wmap2, const __grid_constant
         }
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&my_empty[s0]);
+      if (lane == 0) {
+        mbar_arrive(&my_empty[s0]);
+        if (two_slots) mbar_arrive(&my_empty[s1]);
+      }
     }
 
     if (tid == 0) P_TRACE(5);
@@ -460,17 +732,37 @@ gemv_w4p_kernel(const __grid_constant__ CUtensorMap wmap2, const __grid_constant
     const bool is_first = (j == p0);                                // this piece starts the portion
     const bool contributes = !PAIR || hh < cnt;                     // the second warp of a pair has nothing in a one-block piece
     const int par = PAIR ? (tile & 1) : 0;                          // pair partners are at most one piece apart
-    auto part_of = [&](int sl, int h, int first) { return part_sm + (size_t)((((sl * 2 + h) * 2 + first) * 2 + par) * a.M) * 32; };
+    auto part_of = [&](int sl, int h, int first) {
+      return part_sm + (size_t)((PAIR ? ((sl * 2 + h) * 2 + first) * 2 + par : sl * 2 + first) * a.M) * 32;
+    };
     if (contributes) {
       float* mine = part_of(rho, hh, is_first ? 1 : 0);
+      if constexpr (I8) {
+        // lanes (t, t ^ 1) hold (D0 + 256 D1) and 65536 (D2 - 64 S) of activation row t / 2: the even one stores the sum;
+        // then every lane takes the zero-point term of ITS column 4g + t off both rows
+        const int row = r >> 1;
 #pragma unroll
-      for (int tt = 0; tt < 2; ++tt)
+        for (int tt = 0; tt < 2; ++tt)
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int m = 2 * r + (q & 1);
-          const int col = 4 * c8 + 2 * tt + (q >> 1);
-          if (m < a.M) mine[m * 32 + col] = tot[tt][q] * 16777216.f;
-        }
+          for (int h = 0; h < 2; ++h) {
+            const float v = (r & 1) ? toti[tt][h] * 65536.f : toti[tt][h];
+            const float y = v + __shfl_xor_sync(0xffffffffu, v, 1);
+            if ((r & 1) == 0 && row < a.M) mine[row * 32 + 4 * c8 + 2 * tt + h] = y;
+          }
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+          if (m < a.M) mine[m * 32 + 4 * c8 + r] -= zci[m];
+      } else {
+#pragma unroll
+        for (int tt = 0; tt < 2; ++tt)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int m = 2 * r + (q & 1);
+            const int col = 4 * c8 + 2 * tt + (q >> 1);
+            if (m < a.M) mine[m * 32 + col] = tot[tt][q] * 16777216.f;
+          }
+      }
     }
     if (PAIR) asm volatile("bar.sync %0, 64;" ::"r"(2 + rg) : "memory");   // both warps of the pair have written their parts
     else __syncwarp();
@@ -544,6 +836,7 @@ gemv_w4p_kernel(const __grid_constant__ CUtensorMap wmap2, const __grid_constant
 #ifdef XBIT_DEVTOOLS
   if (tid == 0 && a.trace) {
     P_TRACE_VALUE(8, (unsigned long long)(clock64() - loop0));
+    P_TRACE_VALUE(9, (unsigned long long)wait_clk);
     P_TRACE_VALUE(11, (unsigned long long)(jend - (lo + (int)((long long)len * rho / kPWarps))));
     P_TRACE(7);
   }
@@ -555,18 +848,20 @@ gemv_w4p_kernel(const __grid_constant__ CUtensorMap wmap2, const __grid_constant
 static int p_upg_of(int groupsize) { return groupsize == 32 ? 1 : (groupsize == 64 ? 2 : 4); }
 
 struct W4PPlan {
-  int grid, unit, ring, nw, mode;
+  int grid, unit, ring, nw, mode, i8, bps, minb;
+  bool preferred;
   size_t smem;
 };
 
-static size_t w4p_smem_bytes(int upg, int nr, int m, int k, int ring) {
+static size_t w4p_smem_bytes(int upg, int nr, int m, int k, int ring, bool i8, int bps, bool pair) {
   const int gpb = 4 / upg;
+  const size_t acts = i8 ? (size_t)(k / 128) * 16 + 16 + (size_t)3 * m * (k + 128) + 128      // group table, constants, digit planes
+                         : (size_t)(k / 128) * gpb * m * 16 + (size_t)m * (k + 8) * sizeof(__half);   // zt_sm, act_sm
   return 1024                                                        // alignment slack
-         + (size_t)nr * ring * (4096 + 160 * gpb)                    // rings of two-block slots
+         + (size_t)nr * ring * bps * (2048 + 80 * gpb)                // rings of bps-block slots
          + (size_t)2 * nr * kPMaxRing * 8 + 256                      // mbarriers, counters, slice boundaries
-         + (size_t)nr * 8 * m * 32 * sizeof(float)                   // part_sm
-         + (size_t)(k / 128) * gpb * m * 16                          // zt_sm
-         + (size_t)m * (k + 8) * sizeof(__half);                     // act_sm
+         + (size_t)nr * (pair ? 8 : 2) * m * 32 * sizeof(float)       // part_sm
+         + acts;
 }
 
 size_t gemv_w4p_workspace_bytes(int M) {
@@ -579,48 +874,81 @@ static bool plan_w4p(const GemvArgs& a, bool have_ws, W4PPlan& p) {
   const int upg = p_upg_of(a.groupsize);
   const long long tiles = a.N / 32, nb = a.K / 128;
   if (tiles * nb > 0x3fffffffLL) return false;
-  // ring: as deep as half an SM allows (so that the next call's CTA is co-resident), 2..3 two-block slots per warp; when
-  // the staged activations of a large M * K leave no room for that, one CTA per SM with whatever fits
-  const size_t half = 112 * 1024;
-  // 16 consumer warps in pairs (MODE 2) unless overridden: XBIT_W4P_WARPS = 8 (two blocks per warp and step), 12 (a ring per warp)
-  const int env_nw = env_int("XBIT_W4P_WARPS", 16);
-  p.nw = env_nw == 8 ? 8 : (env_nw == 12 ? 12 : 16);
+  // Two shapes of CTA, both 8 consumer warps that take two blocks per step (measured on the Llama shapes,
+  // profiles/r02_ptime_*; 12 warps with a ring each and 16 warps in pairs were slower everywhere):
+  //   half SM:  rings of 2..3 two-block slots, two launches co-resident: a matrix whose per-CTA share fits the rings is
+  //             prefetched whole while the previous call computes (4096 x 4096: 3.4 us against 4.3 us for the cluster
+  //             kernel);
+  //   full SM:  rings of 4 slots, one CTA per SM and the register budget of one: larger matrices keep streaming while
+  //             they compute, and what counts is the compute rate and the bytes in flight (8192 x 28672: 23.4 against
+  //             26.0 us).
+  // XBIT_W4P_WARPS = 8 / 12 / 16 and XBIT_W4P_RING override (tools/ptime.py).
+  const long long total_blocks = tiles * nb;
+  const long long share = (total_blocks + sms - 1) / sms;           // blocks per CTA
+  const bool small = share <= 8 * 2 * 3;                            // fits 8 rings of 3 two-block slots
+  const int env_nw = env_int("XBIT_W4P_WARPS", 0);
+  p.nw = env_nw == 16 ? 16 : (env_nw == 12 ? 12 : 8);
   p.mode = p.nw == 8 ? 1 : (p.nw == 12 ? 0 : 2);
-  const int nw = p.mode == 2 ? p.nw / 2 : p.nw;     // rings
-  int ring = 0;
-  for (int r = 3; r >= 2 && !ring; --r)
-    if (w4p_smem_bytes(upg, nw, a.M, a.K, r) <= half) ring = r;
-  for (int r = 4; r >= 2 && !ring; --r)
-    if (w4p_smem_bytes(upg, nw, a.M, a.K, r) <= kMaxDynSmem) ring = r;
-  if (!ring) return false;
-  const int env_ring = env_int("XBIT_W4P_RING", 0);
-  if (env_ring >= 2 && env_ring <= kPMaxRing && w4p_smem_bytes(upg, nw, a.M, a.K, env_ring) <= kMaxDynSmem) ring = env_ring;
-  p.ring = ring;
-  p.smem = w4p_smem_bytes(upg, nw, a.M, a.K, ring);
+  const int nr = p.mode == 2 ? p.nw / 2 : p.nw;     // rings
+  // integer block math: groupsize 128, M <= 2 (XBIT_W4P_I8=0: the fp16 exact-product math everywhere)
+  const bool i8 = a.groupsize == 128 && a.M <= 2 && env_int("XBIT_W4P_I8", 1) != 0;
+  p.i8 = i8 ? 1 : 0;
   // CTA boundaries: block granular (perfect balance, tiles shared between CTAs meet in the workspace) or tile aligned
   // (nothing crosses CTAs).  Cost model in blocks per CTA; the cross-CTA fix-up is worth about 4 blocks of time.
+  // Tile-aligned: always one CTA per SM, also when there are fewer tiles (CTAs without work hold their slot until the
+  // previous launch has finished, so that the hardware never stacks two working CTAs of one launch on an SM: measured
+  // 2.7 us against 1.7 us for the stacked ones, profiles/r02_*trace*)
   const long long total = tiles * nb;
   const long long g_fine = total < sms ? total : sms;
-  // tile-aligned: always one CTA per SM, also when there are fewer tiles (CTAs without work hold their slot until the
-  // previous launch has finished, so that the hardware never stacks two working CTAs of one launch on an SM: measured
-  // 2.7 us against 1.7 us for the stacked ones, profiles/r02_trace_*)
-  const long long g_tile = sms;
-  const long long cost_fine = (total + g_fine - 1) / g_fine + (total % g_fine == 0 && (total / g_fine) % nb == 0 ? 0 : 4);
+  // (the finisher of a shared tile waits for CTAs that finish when it does: worth about 4 blocks + a quarter of a tile)
+  const long long cost_fine = (total + g_fine - 1) / g_fine + (total % g_fine == 0 && (total / g_fine) % nb == 0 ? 0 : 4 + nb / 4);
   const long long cost_tile = (tiles + sms - 1) / sms * nb;
   bool fine = have_ws && cost_fine < cost_tile;
   const int env_unit = env_int("XBIT_W4P_FINE", -1);
   if (env_unit == 0) fine = false;
   if (env_unit == 1 && have_ws) fine = true;
   p.unit = fine ? 1 : (int)nb;
-  p.grid = (int)(fine ? g_fine : g_tile);
+  p.grid = (int)(fine ? g_fine : sms);
   const int env_grid = env_int("XBIT_W4P_GRID", 0);
   if (env_grid > 0 && (env_grid <= total || !fine)) p.grid = env_grid;
+  // Rings: at most half an SM, so that the next call's CTA is co-resident.  If a warp's whole share fits its ring, slots
+  // of two blocks (one TMA request per step); otherwise slots of one block, as many as fit: the warp then holds one
+  // 2 KiB slot while it computes and everything else can be in flight.  A large M * K that leaves no room for that takes
+  // one CTA per SM with whatever fits.
+  const long long per_cta = fine ? (total + p.grid - 1) / p.grid : (tiles + p.grid - 1) / p.grid * nb;
+  const long long per_ring = (per_cta + nr - 1) / nr + 1;
+  const size_t half = 113 * 1024;
+  const bool pair = p.mode == 2;
+  int bps = 2, ring = 0;
+  (void)per_ring;
+  if (small)
+    for (int r = 3; r >= 2 && !ring; --r)
+      if (w4p_smem_bytes(upg, nr, a.M, a.K, r, i8, 2, pair) <= half) ring = r;
+  for (int r = 4; r >= 2 && !ring; --r)
+    if (w4p_smem_bytes(upg, nr, a.M, a.K, r, i8, 2, pair) <= kMaxDynSmem) ring = r;
+  if (!ring) return false;
+  const int env_bps = env_int("XBIT_W4P_BPS", 0), env_ring = env_int("XBIT_W4P_RING", 0);
+  if ((env_bps == 1 && !pair) || env_bps == 2) bps = env_bps;
+  if (env_ring >= 2 && env_ring <= kPMaxRing) ring = env_ring;
+  if (w4p_smem_bytes(upg, nr, a.M, a.K, ring, i8, bps, pair) > kMaxDynSmem) return false;
+  p.ring = ring;
+  p.bps = bps;
+  p.smem = w4p_smem_bytes(upg, nr, a.M, a.K, ring, i8, bps, pair);
+  p.minb = (p.smem <= half && p.nw != 16) ? 2 : 1;
+  // AUTO prefers this kernel where it was measured ahead of the cluster split-K kernel: shares that fit the rings (any
+  // block math), and with the integer block math every matrix that gets the 4-slot rings
+  p.preferred = (small && p.minb == 2) || (i8 && ring >= 4);
   return true;
 }
 
 bool gemv_w4p_applicable(const GemvArgs& a) {
   W4PPlan p;
   return plan_w4p(a, false, p);
+}
+
+bool gemv_w4p_preferred(const GemvArgs& a) {
+  W4PPlan p;
+  return plan_w4p(a, true, p) && p.preferred;
 }
 
 using W4PKernel = void (*)(const CUtensorMap, const CUtensorMap, const W4PArgs);
@@ -643,10 +971,13 @@ cudaError_t launch_gemv_w4p(const GemvArgs& g_in, void* workspace, size_t worksp
   a.nb = g.K / 128;
   a.total = (g.N / 32) * a.nb;
   a.unit = p.unit;
+  a.uq = (a.total / p.unit) / p.grid;
+  a.ur = (a.total / p.unit) % p.grid;
   a.ring = p.ring;
   a.static_weights = g.static_weights;
   a.all_wait = env_int("XBIT_W4P_ALLWAIT", 0);
   a.prefetch_delay = env_int("XBIT_W4P_DELAY", 0);
+  a.stage_redux = env_int("XBIT_W4P_REDUX", 1);
   a.scales = g.scales;
   a.qzeros = g.qzeros;
   a.zwords = g.zwords;
@@ -654,9 +985,13 @@ cudaError_t launch_gemv_w4p(const GemvArgs& g_in, void* workspace, size_t worksp
   a.trace = g.trace;
   a.debug_skip = g.debug_skip;
   W4PKernel kern = nullptr;
-#define XBIT_W4P_CASE(UPG_) \
-  if (upg == UPG_) kern = p.nw == 8 ? gemv_w4p_kernel<UPG_, 8, 1> : (p.nw == 16 ? gemv_w4p_kernel<UPG_, 16, 2> : gemv_w4p_kernel<UPG_, 12, 0>);
-  XBIT_W4P_CASE(1) XBIT_W4P_CASE(2) XBIT_W4P_CASE(4)
+#define XBIT_W4P_CASE(UPG_, I8_)                                                                        \
+  if (upg == UPG_ && (p.i8 != 0) == I8_) {                                                              \
+    if (p.nw == 16) kern = gemv_w4p_kernel<UPG_, 16, 2, I8_, 2, 1>;                                     \
+    else if (p.nw == 12) kern = gemv_w4p_kernel<UPG_, 12, 0, I8_, 2, 2>;                                \
+    else kern = p.minb == 2 ? gemv_w4p_kernel<UPG_, 8, 1, I8_, 2, 2> : gemv_w4p_kernel<UPG_, 8, 1, I8_, 2, 1>; \
+  }
+  XBIT_W4P_CASE(1, false) XBIT_W4P_CASE(2, false) XBIT_W4P_CASE(4, false) XBIT_W4P_CASE(4, true)
 #undef XBIT_W4P_CASE
 
   alignas(64) CUtensorMap wmap2, wmap1;

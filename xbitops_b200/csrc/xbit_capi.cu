@@ -100,7 +100,7 @@ static int pick_family(const xbit::GemvArgs& a) {
   if (forced == XBIT_GEMV_MMA) return XBIT_GEMV_MMA;
   if (forced == XBIT_GEMV_GENERIC) return XBIT_GEMV_GENERIC;
   if (forced == XBIT_GEMV_TCGEN05 && xbit::gemv_w4_tc5_supported(a)) return XBIT_GEMV_TCGEN05;
-  if (a.M <= 8 && xbit::gemv_w4p_applicable(a)) return XBIT_GEMV_PERSIST;
+  if (a.M <= 8 && xbit::gemv_w4p_preferred(a)) return XBIT_GEMV_PERSIST;
   return XBIT_GEMV_MMA;
 }
 

@@ -71,6 +71,7 @@ size_t gemv_w4_streamk_workspace_bytes(int M);
 cudaError_t launch_gemv_w4_streamk(GemvArgs a, int family, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 // persistent per-SM schedule with per-warp TMA rings (gemv_w4p_sm100.cu): the default for M <= 8
 bool gemv_w4p_applicable(const GemvArgs& a);
+bool gemv_w4p_preferred(const GemvArgs& a);    // AUTO policy: measured ahead of the cluster split-K kernel here
 size_t gemv_w4p_workspace_bytes(int M);
 cudaError_t launch_gemv_w4p(const GemvArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 // tcgen05 + TMEM path (bits 4, groupsize 128, M <= 8)

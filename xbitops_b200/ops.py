@@ -7,6 +7,8 @@ libxbitops_b200.so.  The compiled twin of this file is csrc/dq_torch_ops.cc (mod
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import capi
@@ -53,6 +55,20 @@ def _stream_handle() -> int:
 
 
 _WORKSPACES: dict = {}
+_STATIC_WEIGHTS = os.environ.get("XBIT_STATIC_WEIGHTS", "0") not in ("", "0")
+
+
+def set_static_weights(on: bool) -> None:
+    """The caller's promise that qweight / scales / qzeros passed to gemv are resident model weights, never written by
+    the kernel that precedes the call in its stream (default False; env XBIT_STATIC_WEIGHTS=1 at import).  gemv then
+    prefetches them under programmatic dependent launch while that kernel drains (XBIT_GEMV_FLAG_STATIC_WEIGHTS);
+    activations are still read only after it has finished.  Same switch as XbitOps.set_static_weights of the twin."""
+    global _STATIC_WEIGHTS
+    _STATIC_WEIGHTS = bool(on)
+
+
+def get_static_weights() -> bool:
+    return _STATIC_WEIGHTS
 
 
 def gemv_workspace(device: torch.device) -> torch.Tensor:
@@ -115,7 +131,8 @@ def gemv(input_a, qweight, scales, qzeros, groupsize, bits, in_features, add_zer
             ws = gemv_workspace(qweight.device)
             capi.check(lib.xbit_gemv_f16_ex(input_a.data_ptr(), qweight.data_ptr(), f16_scale.data_ptr(),
                                             qzeros.data_ptr(), out16.data_ptr(), m, in_features, n, bits, groupsize,
-                                            int(add_zero_bias), n, ws.data_ptr(), ws.numel(), int(family),
+                                            int(add_zero_bias), n, ws.data_ptr(), ws.numel(),
+                                            int(family) | (capi.GEMV_FLAG_STATIC_WEIGHTS if _STATIC_WEIGHTS else 0),
                                             _stream_handle()))
         if scales.dtype == torch.bfloat16:
             return out16.to(torch.bfloat16)
