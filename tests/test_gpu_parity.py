@@ -231,7 +231,9 @@ def test_gemv_persistent_schedule(dev, c_oracle, monkeypatch):
     monkeypatch.delenv("XBIT_W4P_FINE")
     torch.cuda.synchronize()
     ws = ops.gemv_workspace(dev)
-    assert int(ws.view(torch.int32).abs().sum()) == 0      # partial slots and flags cleared
+    lib = capi.load()
+    lo = lib.xbit_gemv_workspace_bytes(16, 0, 0, 4, 128) - 148 * 8 * 32 * 8       # the persistent kernel's region is the tail
+    assert int(ws[lo:].view(torch.int32).abs().sum()) == 0      # partial slots and flags cleared
 
 
 def test_gemv_shapes_dtypes_and_large_m(dev, c_oracle):
@@ -293,7 +295,10 @@ def test_gemv_full_size_properties(K, N, dev):
             # M <= 2 runs the integer block math, M >= 3 the fp16 exact-product math: rows agree bit for bit within each
             y1 = X.gemv(a[1:2], qw, s, qz, g, bits, K, 1, family=fam)
             assert torch.equal(y1[0], X.gemv(a[:2], qw, s, qz, g, bits, K, 1, family=fam)[1])
-            assert torch.equal(X.gemv(a[1:4], qw, s, qz, g, bits, K, 1, family=fam)[1], y[2])
+            # (3 and 4 rows may get different warp counts / rings, i.e. another fp32 summation order: fp16 rounding of the
+            # same sums, not bit identity)
+            y3 = X.gemv(a[1:4], qw, s, qz, g, bits, K, 1, family=fam)[1].double()
+            assert float((y3 - y[2].double()).abs().max()) <= 2.0 ** -9 * float(y[2].double().abs().max())
         else:
             y1 = X.gemv(a[2:3], qw, s, qz, g, bits, K, 1, family=fam)
             assert torch.equal(y1[0], y[2])
@@ -424,7 +429,9 @@ def test_flag_in_data_chain_single_gpu(dev):
                                                   capi.GEMV_AUTO | capi.GEMV_FLAG_WAIT_PEERS, st))
     capi.check(lib.xbit_peers_wait(flags.data_ptr(), 1, 0, state2.data_ptr() + 12, st))
     torch.cuda.synchronize()
-    assert int(flags[0]) == 2 and state2.tolist() == [0, 2, 0, 0] and torch.equal(y, y1)
+    assert int(flags[0]) == 2 and state2.tolist() == [0, 2, 0, 0]
+    # (the plain call may run the persistent schedule, the signal form is raised by the cluster kernel: other summation order)
+    assert float((y.double() - y1.double()).abs().max()) <= 2e-3 * float(y1.double().abs().max())
 
 
 def test_sharded_chain_wrapper_single_gpu(dev):

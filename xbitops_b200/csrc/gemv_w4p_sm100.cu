@@ -868,7 +868,7 @@ size_t gemv_w4p_workspace_bytes(int M) {
   return (size_t)device_sm_count() * (size_t)(M < 1 ? 1 : (M > 8 ? 8 : M)) * 32 * sizeof(unsigned long long);
 }
 
-static bool plan_w4p(const GemvArgs& a, bool have_ws, W4PPlan& p) {
+static bool plan_w4p_nw(const GemvArgs& a, bool have_ws, W4PPlan& p, bool allow16) {
   if (!gemv_w4_supported(a) || a.M > 8) return false;
   const int sms = device_sm_count();
   const int upg = p_upg_of(a.groupsize);
@@ -886,9 +886,12 @@ static bool plan_w4p(const GemvArgs& a, bool have_ws, W4PPlan& p) {
   const long long total_blocks = tiles * nb;
   const long long share = (total_blocks + sms - 1) / sms;           // blocks per CTA
   const bool small = share <= 8 * 2 * 3;                            // fits 8 rings of 3 two-block slots
+  // (XBIT_W4P_WARPS: 8 / 32 = 8 / 16 warps with a ring each and two blocks per step; 12 = a ring each, one block at a
+  // time; 16 = pairs of warps sharing a ring -- the last two only for tools/ptime.py comparisons)
+  const bool large = share >= 100 && a.K <= 8192;                   // 16 warps pay off from about 35 MB (8192 x 8192: 8.6 vs 8.7 us, 8192 x 28672: 22.3 vs 23.0)
   const int env_nw = env_int("XBIT_W4P_WARPS", 0);
-  p.nw = env_nw == 16 ? 16 : (env_nw == 12 ? 12 : 8);
-  p.mode = p.nw == 8 ? 1 : (p.nw == 12 ? 0 : 2);
+  p.nw = (env_nw == 16 || env_nw == 32) ? 16 : (env_nw == 12 ? 12 : (env_nw == 8 ? 8 : (large && allow16 ? 16 : 8)));
+  p.mode = (p.nw == 8 || env_nw == 32 || env_nw == 0) ? 1 : (p.nw == 12 ? 0 : 2);
   const int nr = p.mode == 2 ? p.nw / 2 : p.nw;     // rings
   // integer block math: groupsize 128, M <= 2 (XBIT_W4P_I8=0: the fp16 exact-product math everywhere)
   const bool i8 = a.groupsize == 128 && a.M <= 2 && env_int("XBIT_W4P_I8", 1) != 0;
@@ -924,7 +927,7 @@ static bool plan_w4p(const GemvArgs& a, bool have_ws, W4PPlan& p) {
   if (small)
     for (int r = 3; r >= 2 && !ring; --r)
       if (w4p_smem_bytes(upg, nr, a.M, a.K, r, i8, 2, pair) <= half) ring = r;
-  for (int r = 4; r >= 2 && !ring; --r)
+  for (int r = (nr == 16 ? 2 : 4); r >= 2 && !ring; --r)      // (16 rings: 3 slots measured no better than 2)
     if (w4p_smem_bytes(upg, nr, a.M, a.K, r, i8, 2, pair) <= kMaxDynSmem) ring = r;
   if (!ring) return false;
   const int env_bps = env_int("XBIT_W4P_BPS", 0), env_ring = env_int("XBIT_W4P_RING", 0);
@@ -937,8 +940,13 @@ static bool plan_w4p(const GemvArgs& a, bool have_ws, W4PPlan& p) {
   p.minb = (p.smem <= half && p.nw != 16) ? 2 : 1;
   // AUTO prefers this kernel where it was measured ahead of the cluster split-K kernel: shares that fit the rings (any
   // block math), and with the integer block math every matrix that gets the 4-slot rings
-  p.preferred = (small && p.minb == 2) || (i8 && ring >= 4);
+  p.preferred = (small && p.minb == 2) || (i8 && (ring >= 4 || (nr == 16 && ring >= 2)));
   return true;
+}
+
+static bool plan_w4p(const GemvArgs& a, bool have_ws, W4PPlan& p) {
+  // sixteen consumer warps where they pay off and their rings fit next to the staged activations, eight otherwise
+  return plan_w4p_nw(a, have_ws, p, true) || plan_w4p_nw(a, have_ws, p, false);
 }
 
 bool gemv_w4p_applicable(const GemvArgs& a) {
@@ -987,7 +995,8 @@ cudaError_t launch_gemv_w4p(const GemvArgs& g_in, void* workspace, size_t worksp
   W4PKernel kern = nullptr;
 #define XBIT_W4P_CASE(UPG_, I8_)                                                                        \
   if (upg == UPG_ && (p.i8 != 0) == I8_) {                                                              \
-    if (p.nw == 16) kern = gemv_w4p_kernel<UPG_, 16, 2, I8_, 2, 1>;                                     \
+    if (p.nw == 16 && p.mode == 1) kern = gemv_w4p_kernel<UPG_, 16, 1, I8_, 2, 1>;                      \
+    else if (p.nw == 16) kern = gemv_w4p_kernel<UPG_, 16, 2, I8_, 2, 1>;                                \
     else if (p.nw == 12) kern = gemv_w4p_kernel<UPG_, 12, 0, I8_, 2, 2>;                                \
     else kern = p.minb == 2 ? gemv_w4p_kernel<UPG_, 8, 1, I8_, 2, 2> : gemv_w4p_kernel<UPG_, 8, 1, I8_, 2, 1>; \
   }

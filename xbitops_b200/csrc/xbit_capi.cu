@@ -75,15 +75,20 @@ int xbit_dequant_f16(const int32_t* qweight, const void* scales_f16, const int32
   return XBIT_OK;
 }
 
+static size_t persist_ws_offset(int m);
+
 size_t xbit_gemv_workspace_bytes(int M, int, int, int bits, int) {
   // Optional: with this much zero-initialised scratch the W4 path runs the persistent, perfectly
   // balanced stream-K schedule (partial tiles + ready flags; left zeroed after every call).
   // Without it (NULL / too small) split-K is reduced through cluster shared memory instead.
   if (bits != 4) return 0;
   const int m = M > 16 ? 16 : (M < 1 ? 1 : M);
-  const size_t sk = xbit::gemv_w4_streamk_workspace_bytes(m), pp = xbit::gemv_w4p_workspace_bytes(m);
-  return sk > pp ? sk : pp;
+  // two disjoint regions: [0, sk) the stream-K kernel's flags + partial tiles, [sk, sk + pp) the persistent kernel's
+  // {partial, flag} slots (the former leaves its partial tiles behind, which must never be read as slots)
+  return persist_ws_offset(m) + xbit::gemv_w4p_workspace_bytes(m);
 }
+
+static size_t persist_ws_offset(int m) { return (xbit::gemv_w4_streamk_workspace_bytes(m) + 255) / 256 * 256; }
 
 static int pick_family(const xbit::GemvArgs& a) {
   if (!xbit::gemv_w4_supported(a)) return XBIT_GEMV_GENERIC;
@@ -217,7 +222,12 @@ static int gemv_impl(const void* a_f16, const int32_t* qweight, const void* scal
       case XBIT_GEMV_PERSIST:
         slab = auto_slab ? auto_slab : (g.M > 8 ? 8 : g.M); g.M = slab;
         if (!xbit::gemv_w4p_applicable(g)) return fail(XBIT_EINVAL, "PERSIST family needs bits=4, groupsize in {32, 64, 128}, K%%128=0, N%%32=0, 16-byte aligned pointers and M*K small enough to stage");
-        e = xbit::launch_gemv_w4p(g, workspace, workspace_bytes, st);
+        {
+          // the persistent kernel's region of the workspace lies behind the stream-K kernel's (xbit_gemv_workspace_bytes)
+          const size_t off = persist_ws_offset(g.M);
+          const bool has = workspace && workspace_bytes > off;
+          e = xbit::launch_gemv_w4p(g, has ? static_cast<unsigned char*>(workspace) + off : nullptr, has ? workspace_bytes - off : 0, st);
+        }
         break;
       case XBIT_GEMV_TCGEN05:
         slab = g.M > 16 ? 16 : g.M; g.M = slab;
