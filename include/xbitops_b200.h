@@ -108,6 +108,8 @@ XBIT_API int xbit_dequant_f16(const int32_t* qweight, const void* scales_f16, co
  * (every call leaves it zeroed again), and must not be shared by calls that can run concurrently
  * (calls ordered on one stream may share it). */
 XBIT_API size_t xbit_gemv_workspace_bytes(int M, int K, int N, int bits, int groupsize);
+/* (two disjoint regions: the stream-K schedule's flags and partial tiles, then the persistent schedule's
+ * {partial, flag} slots for up to 4 matrices per launch) */
 
 /* y[m, n] = RN16( sum_k a[m, k] * DQ[k, n] ), fp32 accumulation.
  * a_f16 is [M, K] row-major contiguous.  out_row_stride is in elements (>= N).
@@ -125,6 +127,28 @@ XBIT_API int xbit_gemv_f16_ex(const void* a_f16, const int32_t* qweight, const v
                               int groupsize, int add_zero_bias, int64_t out_row_stride,
                               void* workspace, size_t workspace_bytes, int family,
                               xbit_stream_t stream);
+
+/* One weight matrix of a multi-projection call: the arguments of xbit_gemv_f16 that differ per matrix. */
+typedef struct xbit_gemv_problem {
+  const int32_t* qweight;    /* [ceil(K*bits/32), N] */
+  const void* scales_f16;    /* [G, N]               */
+  const int32_t* qzeros;     /* [G, ceil(N*bits/32)] */
+  void* out_f16;             /* [M, N], row stride out_row_stride */
+  int N;
+  int64_t out_row_stride;
+} xbit_gemv_problem;
+
+/* Multi-projection GEMV: `count` (1..4) weight matrices applied to ONE activation matrix, e.g. the Q, K and V
+ * projections or gate + up of a decoder layer:  out_p[m, n] = RN16( sum_k a[m, k] * DQ_p[k, n] )  for every p.
+ * Semantically -- and, where the fused path applies, BIT FOR BIT -- the same as `count` xbit_gemv_f16_ex calls
+ * with the same family | flags word, one per matrix (/root/reference/src/dq_torch_ops.cc:46-78 is one op call per
+ * projection).  Where all matrices take the persistent W4 schedule (bits 4, group size 32/64/128, K % 128 == 0,
+ * N % 32 == 0, M <= 8) they run as ONE launch: one kernel boundary, one activation staging, the weight rings
+ * running ahead from one matrix into the next.  Otherwise the matrices are launched one after the other.
+ * workspace: as for xbit_gemv_f16 (xbit_gemv_workspace_bytes covers 4 matrices). */
+XBIT_API int xbit_gemv_f16_multi(const void* a_f16, const xbit_gemv_problem* problems, int count, int M, int K,
+                                 int bits, int groupsize, int add_zero_bias, void* workspace,
+                                 size_t workspace_bytes, int family, xbit_stream_t stream);
 
 /* The family xbit_gemv_f16 would pick (XBIT_GEMV_*), for introspection and the bench log. */
 XBIT_API int xbit_gemv_pick_family(int M, int K, int N, int bits, int groupsize);

@@ -236,6 +236,34 @@ def test_gemv_persistent_schedule(dev, c_oracle, monkeypatch):
     assert int(ws[lo:].view(torch.int32).abs().sum()) == 0      # partial slots and flags cleared
 
 
+def test_gemv_multi_projection_is_bit_identical(dev):
+    """xbit_gemv_f16_multi: Q/K/V and gate + up in one launch give, bit for bit, what separate gemv
+    calls give (the reference issues one op per projection, dq_torch_ops.cc:46-78); unequal widths, M = 2, a group size
+    of the fp16 block math, and a combination that cannot be fused (bits 3) fall back to separate launches."""
+    gen = torch.Generator(device=dev).manual_seed(99)
+
+    def rand_proj(K, N, bits, g):
+        qw = torch.randint(-2**31, 2**31 - 1, ((K * bits + 31) // 32, N), dtype=torch.int32, device=dev, generator=gen)
+        qz = torch.randint(-2**31, 2**31 - 1, (K // g, (N * bits + 31) // 32), dtype=torch.int32, device=dev, generator=gen)
+        s = (torch.rand((K // g, N), device=dev, generator=gen) * 0.018 + 0.002).to(torch.float16)
+        return qw, s, qz
+
+    cases = ((4096, (4096, 4096, 4096), 1, 4, 128),        # Q, K, V of Llama-2-7B
+             (4096, (11008, 11008), 1, 4, 128),            # gate, up
+             (8192, (8192, 1024, 1024), 2, 4, 128),        # grouped-query attention: unequal widths
+             (2048, (2048, 512, 2048, 64), 3, 4, 64),      # four matrices, fp16 block math
+             (1024, (256, 512), 1, 3, 128))                # not fusable: the generic kernel, one launch per matrix
+    for (K, Ns, M, bits, g) in cases:
+        a = torch.randn((M, K), device=dev, generator=gen).to(torch.float16)
+        projs = [rand_proj(K, N, bits, g) for N in Ns]
+        fused = X.gemv_multi(a, projs, g, bits, K, 1)
+        for (q, s, z), y in zip(projs, fused):
+            sep = X.gemv(a, q, s, z, g, bits, K, 1)
+            assert torch.equal(y, sep), f"multi K={K} Ns={Ns} M={M} g={g}: differs from the separate call"
+            truth = a.double() @ X.dequant(q, s, z, g, bits, K, 1).double()
+            assert_gemv_close(y.cpu().numpy(), truth.cpu().numpy(), f"multi K={K} N={q.shape[1]}")
+
+
 def test_gemv_shapes_dtypes_and_large_m(dev, c_oracle):
     K, N, g = 1024, 512, 128
     qw, s, qz, a = synth.make_inputs(K, N, 4, g, M=40, seed=3)

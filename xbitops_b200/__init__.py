@@ -17,7 +17,7 @@ __version__ = "0.1.0"
 
 def __getattr__(name):
     # torch is imported lazily so that `import xbitops_b200.synth` stays light
-    if name in ("dequant", "gemv", "set_static_weights", "get_static_weights"):
+    if name in ("dequant", "gemv", "gemv_multi", "set_static_weights", "get_static_weights"):
         from . import ops
         return getattr(ops, name)
     if name in ("ShardedQLinear", "shard_columns"):

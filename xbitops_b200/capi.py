@@ -24,6 +24,7 @@ SIGNATURES = {
     "xbit_gemv_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "xbit_gemv_f16": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i64, _vp, _sz, _vp]),
     "xbit_gemv_f16_ex": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i64, _vp, _sz, _i, _vp]),
+    "xbit_gemv_f16_multi": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _sz, _i, _vp]),
     "xbit_gemv_pick_family": (_i, [_i, _i, _i, _i, _i]),
     "xbit_gemv_f16_peers": (_i, [_vp, _vp, _vp, _vp, ctypes.POINTER(_vp), _i, _i, _i, _i, _i, _i, _i, _i64, _i64,
                                  _vp, _sz, _vp]),
@@ -37,6 +38,13 @@ SIGNATURES = {
     "xbit_ll_unpack_f16": (_i, [_vp, _vp, _i64, _vp, _i, _vp, _vp]),
     "xbit_gemv_f16_host": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
 }
+
+
+
+class GemvProblem(ctypes.Structure):
+    """struct xbit_gemv_problem (include/xbitops_b200.h)"""
+    _fields_ = [("qweight", _vp), ("scales_f16", _vp), ("qzeros", _vp), ("out_f16", _vp), ("N", _i), ("out_row_stride", _i64)]
+
 
 _lib = None
 

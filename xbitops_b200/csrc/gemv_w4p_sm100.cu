@@ -31,6 +31,8 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <algorithm>
+
 #include "gemv_prims.cuh"
 #include "unpack.cuh"
 #include "xbit_internal.h"
@@ -42,27 +44,40 @@ namespace xbit {
 constexpr int kPMaxRing = 8;
 constexpr long long kPSpinGuardClocks = 60000000000ll;   // ~30 s: see kSpinGuardClocks in gemv_sm100.cu
 
-struct W4PArgs {
-  const __half* a;          // [M, K]
+constexpr int kPMaxProblems = 4;                    // weight matrices per launch (xbit_gemv_f16_multi)
+
+// one weight matrix of a launch: all of them share the activations, M, K, bits and group size
+struct W4PProblem {
+  const __half* scales;     // [G, N]: copied into the rings with cp.async (64 bytes per block and group: too small for TMA requests)
+  const uint32_t* qzeros;   // [G, zwords]
   __half* out[kMaxPeers];   // world output buffers ([M, ldo] each)
-  int world;
   long long ldo, col_offset;
-  int M, K, N, zero_bias;
-  int nb;                   // 128-k blocks per tile = K / 128
+  int N, zwords;
   int total;                // tiles * nb
   int unit;                 // CTA boundaries are multiples of `unit` blocks: 1 (stream-K, needs ws) or nb (tile aligned)
   int uq, ur;               // (total / unit) = uq * grid + ur
-  int ring;                 // two-block slots per consumer warp
+  unsigned long long* ws;   // [grid][M][32] {fp32 partial, flag} slots, zero outside a launch
+};
+
+struct W4PArgs {
+  const __half* a;          // [M, K]
+  int world;
+  int M, K, zero_bias;
+  int nb;                   // 128-k blocks per tile = K / 128
+  int ring;                 // slots per ring
   int static_weights;
   int all_wait;             // every consumer warp executes griddepcontrol.wait (comparison knob)
   int stage_redux;          // group reductions of the activation staging with REDUX instead of shuffle trees (A/B knob)
   int prefetch_delay;       // SM clocks the producer waits before its first request (only when it starts ahead of the wait)
-  const __half* scales;     // [G, N]: copied into the rings with cp.async (64 bytes per block and group: too small for TMA requests)
-  const uint32_t* qzeros;   // [G, zwords]
-  int zwords;
-  unsigned long long* ws;   // [grid][M][32] {fp32 partial, flag} slots, zero outside a launch
+  int count;                // weight matrices: the CTA works through its range of each, one after the other
+  W4PProblem prob[kPMaxProblems];
   unsigned long long* trace;
   int debug_skip;
+};
+
+// tensor maps of the launch: [problem][0] = box of two blocks, [problem][1] = box of one block
+struct W4PMaps {
+  CUtensorMap m[2 * kPMaxProblems];
 };
 
 template <int UPG, int BPS>
@@ -303,7 +318,7 @@ __device__ __forceinline__ int p_slice_of(int w) { return (w & 3) * (NW / 4) + (
 // (larger matrices, which keep streaming while they compute: what counts there is the compute rate and bytes in flight).
 template <int UPG, int NW, int MODE, bool I8, int BPS, int MINB>
 __global__ void __launch_bounds__((NW + 1) * 32, MINB)
-gemv_w4p_kernel(const __grid_constant__ CUtensorMap wmap2, const __grid_constant__ CUtensorMap wmap1, const W4PArgs a) {
+gemv_w4p_kernel(const __grid_constant__ W4PMaps maps, const __grid_constant__ W4PArgs a) {
   using Cfg = W4PCfg<UPG, BPS>;
   constexpr int GPB = Cfg::GPB;
   constexpr bool DUAL = MODE == 1, PAIR = MODE == 2;
@@ -328,10 +343,11 @@ gemv_w4p_kernel(const __grid_constant__ CUtensorMap wmap2, const __grid_constant
   unsigned char* zring = sring + kPWarps * R * Cfg::kSSlot;                           // [8][R] zero slots
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(zring + kPWarps * R * Cfg::kZSlot);     // [8][kPMaxRing]
   uint64_t* empty_bar = full_bar + kPWarps * kPMaxRing;
-  int* cnt_sm = reinterpret_cast<int*>(empty_bar + kPWarps * kPMaxRing);              // [32] arrival counters of shared tiles
-  int* bnd_sm = cnt_sm + 32;                                                          // [slices + 1] first block of every slice
-  float* part_sm = reinterpret_cast<float*>(bnd_sm + 32);                             // [slices]([2 warps])[2]([2])[M][32] partial tiles
-  uint32_t* zt_sm = reinterpret_cast<uint32_t*>(part_sm + kPWarps * (PAIR ? 8 : 2) * a.M * 32);    // [groups][M][4]: (hi, lo) of sum_k a_k / 64, 3 zero words
+  int* cnt_sm = reinterpret_cast<int*>(empty_bar + kPWarps * kPMaxRing);              // [problems][16] arrival counters of shared tiles
+  int* bnd_sm = cnt_sm + kPMaxProblems * 16;                                          // [problems][32] first block of every slice
+  float* part_sm = reinterpret_cast<float*>(bnd_sm + kPMaxProblems * 32);             // [problems][slices]([2 warps])[2]([2])[M][32] partial tiles
+  const int part_stride = kPWarps * (PAIR ? 8 : 2) * a.M * 32;                        // floats per problem
+  uint32_t* zt_sm = reinterpret_cast<uint32_t*>(part_sm + a.count * part_stride);    // [groups][M][4]: (hi, lo) of sum_k a_k / 64, 3 zero words
   __half* act_sm = reinterpret_cast<__half*>(zt_sm + (size_t)nb * GPB * a.M * 4);     // [M][pitch]
   // integer block math instead: group table {2^(E-22) row 0, row 1, sum_k a_k row 0, row 1}, the ones / zero constants,
   // and three digit planes per activation row ([K/8 word-rows][even k x4, odd k x4] bytes each; plane p starts
@@ -341,12 +357,9 @@ gemv_w4p_kernel(const __grid_constant__ CUtensorMap wmap2, const __grid_constant
   unsigned char* dig_sm = const_sm + 16;                                              // [3 * M planes]
   auto plane_off = [&](int p) { return (size_t)p * (a.K + 128) + 8 * ((p & 1) + 8 * ((p >> 1) & 1)); };
 
-  // this CTA's range of the tile-major block list: units [U*c/G, U*(c+1)/G) with U = uq*G + ur (no 64-bit division here:
-  // the time from CTA start to the first TMA request is on the critical path whenever the CTA could not start early)
-  auto unit_begin = [&](int cc) { return a.uq * cc + (a.ur * cc) / G; };
-  const int lo = unit_begin(c) * a.unit, hi = unit_begin(c + 1) * a.unit;
-  const int len = hi - lo;
-  const long long U = (long long)a.uq * G + a.ur;
+  // this CTA's range of a matrix' tile-major block list: units [U*c/G, U*(c+1)/G) with U = uq*G + ur (no 64-bit division
+  // here: the time from CTA start to the first TMA request is on the critical path whenever the CTA could not start early)
+  auto range_lo = [&](const W4PProblem& P, int cc) { return (P.uq * cc + (P.ur * cc) / G) * P.unit; };
 
   if (tid < kPWarps * kPMaxRing) {
     if (tid == 0) {
@@ -363,9 +376,13 @@ gemv_w4p_kernel(const __grid_constant__ CUtensorMap wmap2, const __grid_constant
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
   }
-  if (tid < 32) {
-    cnt_sm[tid] = 0;
-    if (tid <= kPWarps) bnd_sm[tid] = lo + (int)(((long long)len * tid) / kPWarps);
+  if (tid < kPMaxProblems * 32) {
+    const int pi = tid >> 5, i = tid & 31;
+    if (i < 16) cnt_sm[pi * 16 + i] = 0;
+    if (pi < a.count && i <= kPWarps) {
+      const int plo = range_lo(a.prob[pi], c), plen = range_lo(a.prob[pi], c + 1) - plo;
+      bnd_sm[pi * 32 + i] = plo + (int)(((long long)plen * i) / kPWarps);
+    }
   }
   __syncthreads();
   // the next kernel in the stream may become resident now: its producer streams ITS weights while this one runs
@@ -383,45 +400,46 @@ gemv_w4p_kernel(const __grid_constant__ CUtensorMap wmap2, const __grid_constant
     }
     if (lane < kPWarps * LPR) {
       const int w = lane / LPR, sub = lane % LPR, rho = slice_of_ring(w);
-      int j = lo + (int)((long long)len * rho / kPWarps);
-      const int jend = lo + (int)((long long)len * (rho + 1) / kPWarps);
-      int tile = j / nb, kb = j - tile * nb;
       uint64_t policy = 0;
       if (sub == 0) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-      if (lane == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&wmap2) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&wmap1) : "memory");
-        P_TRACE(1);
-      }
-      const unsigned char* sbase = reinterpret_cast<const unsigned char*>(a.scales) + sub * 16;
-      const unsigned char* zbase = reinterpret_cast<const unsigned char*>(a.qzeros);
-      int s = 0, ph = 0;
-      for (int n = 0; j < jend; ++n) {
-        const int nblk = min(BPS, min(jend - j, nb - kb));
-        uint64_t* fb = &full_bar[w * kPMaxRing + s];
-        if (n >= R) mbar_wait(&empty_bar[w * kPMaxRing + s], ph ^ 1);
-        if (sub == 0) {
-          mbar_arrive_expect_tx(fb, (uint32_t)(nblk * Cfg::kBlockBytes));
-          tma_load_2d(wring + (w * R + s) * Cfg::kWSlot, nblk == 2 ? &wmap2 : &wmap1, tile * 32, kb * 16, fb, policy);
-        }
-        unsigned char* sdst = sring + (w * R + s) * Cfg::kSSlot + sub * 16;
-        unsigned char* zdst = zring + (w * R + s) * Cfg::kZSlot;
-        const int rows = nblk * GPB, row0 = kb * GPB;
-#pragma unroll
-        for (int rr = 0; rr < BPS * GPB; ++rr)
-          if (rr < rows) {
-#pragma unroll
-            for (int ch = 0; ch < 4; ch += LPR)
-              cp_async_16(sdst + rr * 64 + ch * 16, sbase + ((size_t)(row0 + rr) * a.N + tile * 32) * 2 + ch * 16);
+      if (lane < 2 * a.count) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.m[lane]) : "memory");
+      if (lane == 0) P_TRACE(1);
+      int s = 0, ph = 0, n = 0;
+      for (int pi = 0; pi < a.count; ++pi) {
+        const W4PProblem& P = a.prob[pi];
+        const int lo = range_lo(P, c), len = range_lo(P, c + 1) - lo;
+        int j = lo + (int)((long long)len * rho / kPWarps);
+        const int jend = lo + (int)((long long)len * (rho + 1) / kPWarps);
+        int tile = j / nb, kb = j - tile * nb;
+        const unsigned char* sbase = reinterpret_cast<const unsigned char*>(P.scales) + sub * 16;
+        const unsigned char* zbase = reinterpret_cast<const unsigned char*>(P.qzeros);
+        for (; j < jend; ++n) {
+          const int nblk = min(BPS, min(jend - j, nb - kb));
+          uint64_t* fb = &full_bar[w * kPMaxRing + s];
+          if (n >= R) mbar_wait(&empty_bar[w * kPMaxRing + s], ph ^ 1);
+          if (sub == 0) {
+            mbar_arrive_expect_tx(fb, (uint32_t)(nblk * Cfg::kBlockBytes));
+            tma_load_2d(wring + (w * R + s) * Cfg::kWSlot, &maps.m[2 * pi + (nblk == 2 ? 0 : 1)], tile * 32, kb * 16, fb, policy);
           }
+          unsigned char* sdst = sring + (w * R + s) * Cfg::kSSlot + sub * 16;
+          unsigned char* zdst = zring + (w * R + s) * Cfg::kZSlot;
+          const int rows = nblk * GPB, row0 = kb * GPB;
 #pragma unroll
-        for (int rr = 0; rr < BPS * GPB; ++rr)
-          if (rr < rows && (rr % LPR) == sub) cp_async_16(zdst + rr * 16, zbase + ((size_t)(row0 + rr) * a.zwords + tile * 4) * 4);
-        cp_async_mbar_arrive_noinc(fb);
-        j += nblk;
-        kb += nblk;
-        if (kb == nb) { kb = 0; ++tile; }
-        if (++s == R) { s = 0; ph ^= 1; }
+          for (int rr = 0; rr < BPS * GPB; ++rr)
+            if (rr < rows) {
+#pragma unroll
+              for (int ch = 0; ch < 4; ch += LPR)
+                cp_async_16(sdst + rr * 64 + ch * 16, sbase + ((size_t)(row0 + rr) * P.N + tile * 32) * 2 + ch * 16);
+            }
+#pragma unroll
+          for (int rr = 0; rr < BPS * GPB; ++rr)
+            if (rr < rows && (rr % LPR) == sub) cp_async_16(zdst + rr * 16, zbase + ((size_t)(row0 + rr) * P.zwords + tile * 4) * 4);
+          cp_async_mbar_arrive_noinc(fb);
+          j += nblk;
+          kb += nblk;
+          if (kb == nb) { kb = 0; ++tile; }
+          if (++s == R) { s = 0; ph ^= 1; }
+        }
       }
       asm volatile("cp.async.wait_all;" ::: "memory");
     }
@@ -463,9 +481,6 @@ gemv_w4p_kernel(const __grid_constant__ CUtensorMap wmap2, const __grid_constant
 
   const int rg = PAIR ? warp >> 1 : warp, hh = PAIR ? warp & 1 : 0;   // ring, and which block of a step this warp takes
   const int rho = slice_of_ring(rg);
-  int j = lo + (int)((long long)len * rho / kPWarps);
-  const int jend = lo + (int)((long long)len * (rho + 1) / kPWarps);
-  int tile = j / nb, kb = j - tile * nb;
   int s = 0, ph = 0;
   uint64_t* const my_full = full_bar + rg * kPMaxRing;
   uint64_t* const my_empty = empty_bar + rg * kPMaxRing;
@@ -615,6 +630,14 @@ gemv_w4p_kernel(const __grid_constant__ CUtensorMap wmap2, const __grid_constant
   bool first_wait = true;
 #endif
 
+  for (int pi = 0; pi < a.count; ++pi) {
+  const W4PProblem& P = a.prob[pi];
+  const int lo = range_lo(P, c), hi = range_lo(P, c + 1), len = hi - lo;
+  const long long U = (long long)P.uq * G + P.ur;
+  int* const bnd = bnd_sm + pi * 32;
+  int j = lo + (int)((long long)len * rho / kPWarps);
+  const int jend = lo + (int)((long long)len * (rho + 1) / kPWarps);
+  int tile = j / nb, kb = j - tile * nb;
   while (j < jend) {
     const int cnt = min(jend - j, nb - kb);         // this warp's blocks of `tile`: [kb, kb + cnt)
     float tot[2][4];
@@ -733,7 +756,7 @@ gemv_w4p_kernel(const __grid_constant__ CUtensorMap wmap2, const __grid_constant
     const bool contributes = !PAIR || hh < cnt;                     // the second warp of a pair has nothing in a one-block piece
     const int par = PAIR ? (tile & 1) : 0;                          // pair partners are at most one piece apart
     auto part_of = [&](int sl, int h, int first) {
-      return part_sm + (size_t)((PAIR ? ((sl * 2 + h) * 2 + first) * 2 + par : sl * 2 + first) * a.M) * 32;
+      return part_sm + (size_t)pi * part_stride + (size_t)((PAIR ? ((sl * 2 + h) * 2 + first) * 2 + par : sl * 2 + first) * a.M) * 32;
     };
     if (contributes) {
       float* mine = part_of(rho, hh, is_first ? 1 : 0);
@@ -771,12 +794,12 @@ gemv_w4p_kernel(const __grid_constant__ CUtensorMap wmap2, const __grid_constant
     int sl_first = 0, sl_last = 0;
 #pragma unroll
     for (int sl = 1; sl < kPWarps; ++sl) {
-      const int b = bnd_sm[sl];
+      const int b = bnd[sl];
       if (b <= p0) sl_first = sl;
       if (b < p1) sl_last = sl;
     }
     // blocks of the portion held by slice sl (<= 0: none)
-    auto slice_cnt = [&](int sl) { return min(bnd_sm[sl + 1], p1) - max(bnd_sm[sl], p0); };
+    auto slice_cnt = [&](int sl) { return min(bnd[sl + 1], p1) - max(bnd[sl], p0); };
     bool finalize = contributes && hh == 0;
     if (finalize && sl_last > sl_first) {
       int expected = 0;
@@ -784,7 +807,7 @@ gemv_w4p_kernel(const __grid_constant__ CUtensorMap wmap2, const __grid_constant
       int old = 0;
       if (lane == 0) {
         __threadfence_block();
-        old = atomicAdd(&cnt_sm[sl_first], 1);
+        old = atomicAdd(&cnt_sm[pi * 16 + sl_first], 1);
       }
       old = __shfl_sync(0xffffffffu, old, 0);
       finalize = (old == expected - 1);
@@ -802,10 +825,10 @@ gemv_w4p_kernel(const __grid_constant__ CUtensorMap wmap2, const __grid_constant
         }
         if (starts_tile && !ends_tile) {
           // finisher: the CTAs after this one that hold the tile's later blocks published their parts (normally long ago)
-          const long long ux = (long long)(t0 + nb - 1) / a.unit;
+          const long long ux = (long long)(t0 + nb - 1) / P.unit;
           const int c_last = (int)(((ux + 1) * G + U - 1) / U) - 1;
           for (int cc = c + 1; cc <= c_last; ++cc) {
-            unsigned long long* slot = a.ws + ((size_t)cc * a.M + m) * 32 + lane;
+            unsigned long long* slot = P.ws + ((size_t)cc * a.M + m) * 32 + lane;
             uint32_t bits, flag;
             const long long c0 = clock64();
             for (unsigned int spin = 1;; ++spin) {
@@ -819,12 +842,12 @@ gemv_w4p_kernel(const __grid_constant__ CUtensorMap wmap2, const __grid_constant
         }
         if (starts_tile) {
           const __half h = __float2half_rn(v);
-          const size_t off = (size_t)m * a.ldo + a.col_offset + n;
-          a.out[0][off] = h;
-          for (int p = 1; p < a.world; ++p) a.out[p][off] = h;      // fused all-gather: NVLink peer stores
+          const size_t off = (size_t)m * P.ldo + P.col_offset + n;
+          P.out[0][off] = h;
+          for (int p = 1; p < a.world; ++p) P.out[p][off] = h;      // fused all-gather: NVLink peer stores
         } else {
           // contributor: this CTA holds later blocks of a tile that starts in an earlier CTA
-          asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(a.ws + ((size_t)c * a.M + m) * 32 + lane), "r"(__float_as_uint(v)), "r"(1u) : "memory");
+          asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(P.ws + ((size_t)c * a.M + m) * 32 + lane), "r"(__float_as_uint(v)), "r"(1u) : "memory");
         }
       }
     }
@@ -833,11 +856,12 @@ gemv_w4p_kernel(const __grid_constant__ CUtensorMap wmap2, const __grid_constant
     kb = 0;
     ++tile;
   }
+  }
 #ifdef XBIT_DEVTOOLS
   if (tid == 0 && a.trace) {
     P_TRACE_VALUE(8, (unsigned long long)(clock64() - loop0));
     P_TRACE_VALUE(9, (unsigned long long)wait_clk);
-    P_TRACE_VALUE(11, (unsigned long long)(jend - (lo + (int)((long long)len * rho / kPWarps))));
+    P_TRACE_VALUE(11, (unsigned long long)((range_lo(a.prob[0], c + 1) - range_lo(a.prob[0], c)) / kPWarps));
     P_TRACE(7);
   }
 #endif
@@ -853,14 +877,14 @@ struct W4PPlan {
   size_t smem;
 };
 
-static size_t w4p_smem_bytes(int upg, int nr, int m, int k, int ring, bool i8, int bps, bool pair) {
+static size_t w4p_smem_bytes(int upg, int nr, int m, int k, int ring, bool i8, int bps, bool pair, int count = 1) {
   const int gpb = 4 / upg;
   const size_t acts = i8 ? (size_t)(k / 128) * 16 + 16 + (size_t)3 * m * (k + 128) + 128      // group table, constants, digit planes
                          : (size_t)(k / 128) * gpb * m * 16 + (size_t)m * (k + 8) * sizeof(__half);   // zt_sm, act_sm
   return 1024                                                        // alignment slack
          + (size_t)nr * ring * bps * (2048 + 80 * gpb)                // rings of bps-block slots
-         + (size_t)2 * nr * kPMaxRing * 8 + 256                      // mbarriers, counters, slice boundaries
-         + (size_t)nr * (pair ? 8 : 2) * m * 32 * sizeof(float)       // part_sm
+         + (size_t)2 * nr * kPMaxRing * 8 + kPMaxProblems * 48 * 4   // mbarriers, counters, slice boundaries
+         + (size_t)count * nr * (pair ? 8 : 2) * m * 32 * sizeof(float)   // part_sm
          + acts;
 }
 
@@ -868,7 +892,7 @@ size_t gemv_w4p_workspace_bytes(int M) {
   return (size_t)device_sm_count() * (size_t)(M < 1 ? 1 : (M > 8 ? 8 : M)) * 32 * sizeof(unsigned long long);
 }
 
-static bool plan_w4p_nw(const GemvArgs& a, bool have_ws, W4PPlan& p, bool allow16) {
+static bool plan_w4p_nw(const GemvArgs& a, bool have_ws, W4PPlan& p, bool allow16, int count, long long share_all) {
   if (!gemv_w4_supported(a) || a.M > 8) return false;
   const int sms = device_sm_count();
   const int upg = p_upg_of(a.groupsize);
@@ -885,7 +909,8 @@ static bool plan_w4p_nw(const GemvArgs& a, bool have_ws, W4PPlan& p, bool allow1
   // XBIT_W4P_WARPS = 8 / 12 / 16 and XBIT_W4P_RING override (tools/ptime.py).
   const long long total_blocks = tiles * nb;
   const long long share = (total_blocks + sms - 1) / sms;           // blocks per CTA
-  const bool small = share <= 8 * 2 * 3;                            // fits 8 rings of 3 two-block slots
+  // (a launch of several matrices, xbit_gemv_f16_multi: the CTA streams the shares of all of them, share_all)
+  const bool small = (share_all > 0 ? share_all : share) <= 8 * 2 * 3;   // fits 8 rings of 3 two-block slots
   // (XBIT_W4P_WARPS: 8 / 32 = 8 / 16 warps with a ring each and two blocks per step; 12 = a ring each, one block at a
   // time; 16 = pairs of warps sharing a ring -- the last two only for tools/ptime.py comparisons)
   const bool large = share >= 100 && a.K <= 8192;                   // 16 warps pay off from about 35 MB (8192 x 8192: 8.6 vs 8.7 us, 8192 x 28672: 22.3 vs 23.0)
@@ -926,17 +951,17 @@ static bool plan_w4p_nw(const GemvArgs& a, bool have_ws, W4PPlan& p, bool allow1
   (void)per_ring;
   if (small)
     for (int r = 3; r >= 2 && !ring; --r)
-      if (w4p_smem_bytes(upg, nr, a.M, a.K, r, i8, 2, pair) <= half) ring = r;
+      if (w4p_smem_bytes(upg, nr, a.M, a.K, r, i8, 2, pair, count) <= half) ring = r;
   for (int r = (nr == 16 ? 2 : 4); r >= 2 && !ring; --r)      // (16 rings: 3 slots measured no better than 2)
-    if (w4p_smem_bytes(upg, nr, a.M, a.K, r, i8, 2, pair) <= kMaxDynSmem) ring = r;
+    if (w4p_smem_bytes(upg, nr, a.M, a.K, r, i8, 2, pair, count) <= kMaxDynSmem) ring = r;
   if (!ring) return false;
   const int env_bps = env_int("XBIT_W4P_BPS", 0), env_ring = env_int("XBIT_W4P_RING", 0);
   if ((env_bps == 1 && !pair) || env_bps == 2) bps = env_bps;
   if (env_ring >= 2 && env_ring <= kPMaxRing) ring = env_ring;
-  if (w4p_smem_bytes(upg, nr, a.M, a.K, ring, i8, bps, pair) > kMaxDynSmem) return false;
+  if (w4p_smem_bytes(upg, nr, a.M, a.K, ring, i8, bps, pair, count) > kMaxDynSmem) return false;
   p.ring = ring;
   p.bps = bps;
-  p.smem = w4p_smem_bytes(upg, nr, a.M, a.K, ring, i8, bps, pair);
+  p.smem = w4p_smem_bytes(upg, nr, a.M, a.K, ring, i8, bps, pair, count);
   p.minb = (p.smem <= half && p.nw != 16) ? 2 : 1;
   // AUTO prefers this kernel where it was measured ahead of the cluster split-K kernel: shares that fit the rings (any
   // block math), and with the integer block math every matrix that gets the 4-slot rings
@@ -944,9 +969,9 @@ static bool plan_w4p_nw(const GemvArgs& a, bool have_ws, W4PPlan& p, bool allow1
   return true;
 }
 
-static bool plan_w4p(const GemvArgs& a, bool have_ws, W4PPlan& p) {
+static bool plan_w4p(const GemvArgs& a, bool have_ws, W4PPlan& p, int count = 1, long long share_all = 0) {
   // sixteen consumer warps where they pay off and their rings fit next to the staged activations, eight otherwise
-  return plan_w4p_nw(a, have_ws, p, true) || plan_w4p_nw(a, have_ws, p, false);
+  return plan_w4p_nw(a, have_ws, p, true, count, share_all) || plan_w4p_nw(a, have_ws, p, false, count, share_all);
 }
 
 bool gemv_w4p_applicable(const GemvArgs& a) {
@@ -959,39 +984,87 @@ bool gemv_w4p_preferred(const GemvArgs& a) {
   return plan_w4p(a, true, p) && p.preferred;
 }
 
-using W4PKernel = void (*)(const CUtensorMap, const CUtensorMap, const W4PArgs);
+using W4PKernel = void (*)(const W4PMaps, const W4PArgs);
 
-cudaError_t launch_gemv_w4p(const GemvArgs& g_in, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
-  GemvArgs g = g_in;
-  apply_debug_knobs(g);
-  const bool have_ws = workspace && (reinterpret_cast<uintptr_t>(workspace) & 255u) == 0 && workspace_bytes >= gemv_w4p_workspace_bytes(g.M);
-  W4PPlan p;
-  if (!plan_w4p(g, have_ws, p)) return cudaErrorInvalidValue;
-  const int upg = p_upg_of(g.groupsize);
+// One launch for `count` weight matrices that share the activations (and M, K, bits, group size, zero bias): every CTA
+// works through its range of each matrix in turn -- exactly the range, the warp slices and therefore the fp32 summation
+// order of a separate call on that matrix, so the results are bit-identical to `count` separate calls -- with one kernel
+// boundary, one activation staging and one prologue for all of them, and the rings running ahead across matrices.
+// cudaErrorNotSupported: the matrices want different CTA shapes (the caller launches them one by one).
+cudaError_t launch_gemv_w4p_multi(const GemvArgs* gs, int count, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  if (count < 1 || count > kPMaxProblems) return cudaErrorInvalidValue;
+  GemvArgs g0 = gs[0];
+  apply_debug_knobs(g0);
+  const size_t region = gemv_w4p_workspace_bytes(g0.M);
+  const bool have_ws = workspace && (reinterpret_cast<uintptr_t>(workspace) & 255u) == 0 && workspace_bytes >= region * count;
+  const int sms = device_sm_count();
+  long long share_all = 0;
+  for (int i = 0; i < count; ++i) {
+    if (gs[i].M != g0.M || gs[i].K != g0.K || gs[i].groupsize != g0.groupsize || gs[i].zero_bias != g0.zero_bias || gs[i].a != g0.a ||
+        gs[i].world != g0.world)
+      return cudaErrorInvalidValue;
+    share_all += ((long long)(gs[i].N / 32) * (g0.K / 128) + sms - 1) / sms;
+  }
+  W4PPlan p;                                         // CTA shape of the launch: from the first matrix and the combined share
+  if (!plan_w4p(g0, have_ws, p, count, count > 1 ? share_all : 0)) return cudaErrorInvalidValue;
+  const int upg = p_upg_of(g0.groupsize);
   W4PArgs a;
   memset(&a, 0, sizeof(a));
-  a.a = g.a;
-  for (int i = 0; i < kMaxPeers; ++i) a.out[i] = g.out[i];
-  a.world = g.world;
-  a.ldo = g.ldo;
-  a.col_offset = g.col_offset;
-  a.M = g.M; a.K = g.K; a.N = g.N; a.zero_bias = g.zero_bias;
-  a.nb = g.K / 128;
-  a.total = (g.N / 32) * a.nb;
-  a.unit = p.unit;
-  a.uq = (a.total / p.unit) / p.grid;
-  a.ur = (a.total / p.unit) % p.grid;
+  alignas(64) W4PMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  a.a = g0.a;
+  a.world = g0.world;
+  a.M = g0.M; a.K = g0.K; a.zero_bias = g0.zero_bias;
+  a.nb = g0.K / 128;
   a.ring = p.ring;
-  a.static_weights = g.static_weights;
+  a.static_weights = g0.static_weights;
   a.all_wait = env_int("XBIT_W4P_ALLWAIT", 0);
   a.prefetch_delay = env_int("XBIT_W4P_DELAY", 0);
   a.stage_redux = env_int("XBIT_W4P_REDUX", 1);
-  a.scales = g.scales;
-  a.qzeros = g.qzeros;
-  a.zwords = g.zwords;
-  a.ws = p.unit == 1 ? reinterpret_cast<unsigned long long*>(workspace) : nullptr;
-  a.trace = g.trace;
-  a.debug_skip = g.debug_skip;
+  a.count = count;
+  a.trace = g0.trace;
+  a.debug_skip = g0.debug_skip;
+  for (int i = 0; i < count; ++i) {
+    const GemvArgs& g = gs[i];
+    W4PPlan pi;                                      // decomposition of this matrix: what a separate call would use
+    if (!plan_w4p(g, have_ws, pi)) return cudaErrorInvalidValue;
+    if (count > 1 && (pi.nw != p.nw || pi.mode != p.mode || pi.i8 != p.i8)) {
+      // the launch's shape came from matrix 0 and the combined share: take matrix i's own warp count if all agree on it
+      if (i == 0) { p.nw = pi.nw; p.mode = pi.mode; }
+      else return cudaErrorNotSupported;
+    }
+    if (count > 1 && pi.grid != (pi.unit == 1 ? (int)std::min<long long>((long long)(g.N / 32) * a.nb, sms) : sms)) return cudaErrorNotSupported;
+    if (i == 0) p.grid = pi.grid;
+    else if (pi.grid != p.grid) return cudaErrorNotSupported;
+    W4PProblem& P = a.prob[i];
+    P.scales = g.scales;
+    P.qzeros = g.qzeros;
+    for (int r = 0; r < kMaxPeers; ++r) P.out[r] = g.out[r];
+    P.ldo = g.ldo;
+    P.col_offset = g.col_offset;
+    P.N = g.N;
+    P.zwords = g.zwords;
+    P.total = (g.N / 32) * a.nb;
+    P.unit = pi.unit;
+    P.uq = (P.total / pi.unit) / p.grid;
+    P.ur = (P.total / pi.unit) % p.grid;
+    P.ws = pi.unit == 1 ? reinterpret_cast<unsigned long long*>(static_cast<unsigned char*>(workspace) + (size_t)i * region) : nullptr;
+    // qweight [qrows, N] u32: box = two blocks (32 word-rows) x 32 columns (128 B), 128-byte swizzle; one block for odd tails
+    cudaError_t e = encode_2d(&maps.m[2 * i], CU_TENSOR_MAP_DATA_TYPE_UINT32, g.qweight, (uint64_t)g.N, (uint64_t)g.qrows, (uint64_t)g.N * 4, 32, 32,
+                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+    if (e != cudaSuccess) return e;
+    e = encode_2d(&maps.m[2 * i + 1], CU_TENSOR_MAP_DATA_TYPE_UINT32, g.qweight, (uint64_t)g.N, (uint64_t)g.qrows, (uint64_t)g.N * 4, 32, 16,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+    if (e != cudaSuccess) return e;
+  }
+  if (count > 1) {
+    // the warp count may have been replaced by the matrices' own: shared memory and register budget follow it
+    W4PPlan q = p;
+    GemvArgs probe = g0;
+    if (!plan_w4p_nw(probe, have_ws, q, p.nw == 16, count, share_all) || q.nw != p.nw) return cudaErrorNotSupported;
+    p.ring = q.ring; p.smem = q.smem; p.minb = q.minb; p.bps = q.bps;
+    a.ring = p.ring;
+  }
   W4PKernel kern = nullptr;
 #define XBIT_W4P_CASE(UPG_, I8_)                                                                        \
   if (upg == UPG_ && (p.i8 != 0) == I8_) {                                                              \
@@ -1002,16 +1075,8 @@ cudaError_t launch_gemv_w4p(const GemvArgs& g_in, void* workspace, size_t worksp
   }
   XBIT_W4P_CASE(1, false) XBIT_W4P_CASE(2, false) XBIT_W4P_CASE(4, false) XBIT_W4P_CASE(4, true)
 #undef XBIT_W4P_CASE
-
-  alignas(64) CUtensorMap wmap2, wmap1;
-  // qweight [qrows, N] u32: box = two blocks (32 word-rows) x 32 columns (128 B), 128-byte swizzle; one block for odd tails
-  cudaError_t e = encode_2d(&wmap2, CU_TENSOR_MAP_DATA_TYPE_UINT32, g.qweight, (uint64_t)g.N, (uint64_t)g.qrows, (uint64_t)g.N * 4, 32, 32,
-                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
-  if (e != cudaSuccess) return e;
-  e = encode_2d(&wmap1, CU_TENSOR_MAP_DATA_TYPE_UINT32, g.qweight, (uint64_t)g.N, (uint64_t)g.qrows, (uint64_t)g.N * 4, 32, 16,
-                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
-  if (e != cudaSuccess) return e;
-  e = ensure_max_dyn_smem(reinterpret_cast<const void*>(kern));
+  if (!kern) return cudaErrorInvalidValue;
+  cudaError_t e = ensure_max_dyn_smem(reinterpret_cast<const void*>(kern));
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)p.grid, 1, 1);
@@ -1023,7 +1088,11 @@ cudaError_t launch_gemv_w4p(const GemvArgs& g_in, void* workspace, size_t worksp
   attrs[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attrs;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kern, wmap2, wmap1, a);
+  return cudaLaunchKernelEx(&cfg, kern, maps, a);
+}
+
+cudaError_t launch_gemv_w4p(const GemvArgs& g, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  return launch_gemv_w4p_multi(&g, 1, workspace, workspace_bytes, stream);
 }
 
 }  // namespace xbit

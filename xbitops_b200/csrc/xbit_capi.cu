@@ -85,7 +85,7 @@ size_t xbit_gemv_workspace_bytes(int M, int, int, int bits, int) {
   const int m = M > 16 ? 16 : (M < 1 ? 1 : M);
   // two disjoint regions: [0, sk) the stream-K kernel's flags + partial tiles, [sk, sk + pp) the persistent kernel's
   // {partial, flag} slots (the former leaves its partial tiles behind, which must never be read as slots)
-  return persist_ws_offset(m) + xbit::gemv_w4p_workspace_bytes(m);
+  return persist_ws_offset(m) + 4 * xbit::gemv_w4p_workspace_bytes(m);
 }
 
 static size_t persist_ws_offset(int m) { return (xbit::gemv_w4_streamk_workspace_bytes(m) + 255) / 256 * 256; }
@@ -261,6 +261,55 @@ int xbit_gemv_f16(const void* a_f16, const int32_t* qweight, const void* scales_
                   size_t workspace_bytes, xbit_stream_t stream) {
   return xbit_gemv_f16_ex(a_f16, qweight, scales_f16, qzeros, out_f16, M, K, N, bits, groupsize, add_zero_bias,
                           out_row_stride, workspace, workspace_bytes, XBIT_GEMV_AUTO, stream);
+}
+
+int xbit_gemv_f16_multi(const void* a_f16, const xbit_gemv_problem* problems, int count, int M, int K, int bits, int groupsize,
+                        int add_zero_bias, void* workspace, size_t workspace_bytes, int family, xbit_stream_t stream) {
+  g_err[0] = 0;
+  if (!problems || count < 1 || count > 4) return fail(XBIT_EINVAL, "count must be in [1, 4] with a non-null problem array, got %d", count);
+  const int family_req = family & XBIT_GEMV_FAMILY_MASK;
+  // the fused launch: every matrix on the persistent schedule (AUTO would pick it, or it was asked for)
+  bool fuse = count > 1 && M >= 1 && M <= 8 && a_f16 && (family_req == XBIT_GEMV_AUTO || family_req == XBIT_GEMV_PERSIST);
+  xbit::GemvArgs gs[4];
+  for (int i = 0; i < count && fuse; ++i) {
+    const xbit_gemv_problem& pr = problems[i];
+    if (check_common(pr.qweight, pr.scales_f16, pr.qzeros, K, pr.N, bits, groupsize, add_zero_bias) != XBIT_OK || !pr.out_f16 ||
+        pr.out_row_stride < pr.N) {
+      fuse = false;                                  // let the per-matrix call report the error
+      break;
+    }
+    xbit::GemvArgs& g = gs[i];
+    memset(&g, 0, sizeof(g));
+    g.a = reinterpret_cast<const __half*>(a_f16);
+    g.out[0] = reinterpret_cast<__half*>(pr.out_f16);
+    g.world = 1;
+    g.qweight = reinterpret_cast<const uint32_t*>(pr.qweight);
+    g.scales = reinterpret_cast<const __half*>(pr.scales_f16);
+    g.qzeros = reinterpret_cast<const uint32_t*>(pr.qzeros);
+    g.M = M; g.K = K; g.N = pr.N; g.bits = bits; g.groupsize = groupsize; g.zero_bias = add_zero_bias;
+    g.ldo = pr.out_row_stride; g.col_offset = 0;
+    g.qrows = ceil_div((long long)K * bits, 32);
+    g.zwords = ceil_div((long long)pr.N * bits, 32);
+    g.groups = ceil_div(K, groupsize);
+    g.static_weights = (family & XBIT_GEMV_FLAG_STATIC_WEIGHTS) ? 1 : 0;
+    if (family_req == XBIT_GEMV_AUTO ? pick_family(g) != XBIT_GEMV_PERSIST : !xbit::gemv_w4p_applicable(g)) fuse = false;
+  }
+  if (fuse) {
+    const size_t off = persist_ws_offset(M);
+    const bool has = workspace && workspace_bytes > off;
+    const cudaError_t e = xbit::launch_gemv_w4p_multi(gs, count, has ? static_cast<unsigned char*>(workspace) + off : nullptr,
+                                                      has ? workspace_bytes - off : 0, reinterpret_cast<cudaStream_t>(stream));
+    if (e == cudaSuccess) return XBIT_OK;
+    (void)cudaGetLastError();
+    if (e != cudaErrorNotSupported && e != cudaErrorInvalidValue) return cuda_fail(e, "xbit_gemv_f16_multi launch");
+  }
+  for (int i = 0; i < count; ++i) {
+    const xbit_gemv_problem& pr = problems[i];
+    if (int rc = xbit_gemv_f16_ex(a_f16, pr.qweight, pr.scales_f16, pr.qzeros, pr.out_f16, M, K, pr.N, bits, groupsize, add_zero_bias,
+                                  pr.out_row_stride, workspace, workspace_bytes, family, stream))
+      return rc;
+  }
+  return XBIT_OK;
 }
 
 int xbit_gemv_pick_family(int M, int K, int N, int bits, int groupsize) {

@@ -74,6 +74,8 @@ bool gemv_w4p_applicable(const GemvArgs& a);
 bool gemv_w4p_preferred(const GemvArgs& a);    // AUTO policy: measured ahead of the cluster split-K kernel here
 size_t gemv_w4p_workspace_bytes(int M);
 cudaError_t launch_gemv_w4p(const GemvArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+// `count` (<= 4) matrices sharing the activations in one launch; cudaErrorNotSupported = launch them one by one
+cudaError_t launch_gemv_w4p_multi(const GemvArgs* gs, int count, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 // tcgen05 + TMEM path (bits 4, groupsize 128, M <= 8)
 bool gemv_w4_tc5_supported(const GemvArgs& a);
 cudaError_t launch_gemv_w4_tc5(GemvArgs a, cudaStream_t stream);

@@ -137,3 +137,39 @@ def gemv(input_a, qweight, scales, qzeros, groupsize, bits, in_features, add_zer
         if scales.dtype == torch.bfloat16:
             return out16.to(torch.bfloat16)
     return out16
+
+
+def gemv_multi(input_a, projections, groupsize, bits, in_features, add_zero_bias, *, family: int = capi.GEMV_AUTO):
+    """Several weight matrices applied to ONE activation tensor (Q/K/V, gate + up): `projections` is a sequence of
+    (qweight, scales, qzeros) triples; returns the list [gemv(input_a, q, s, z, ...) for (q, s, z) in projections],
+    bit-identical to those calls, through ONE launch where the persistent W4 schedule applies to all of them
+    (xbit_gemv_f16_multi).  The reference has one op call per projection (dq_torch_ops.cc:46-78); this is the
+    multi-projection entry of SURVEY.md 8(f)."""
+    import ctypes
+    projections = list(projections)
+    if not 1 <= len(projections) <= 4:
+        raise RuntimeError("gemv_multi takes 1 to 4 projections")
+    _check_input(input_a, "input_a")
+    if input_a.dtype != torch.float16 or input_a.dim() != 2 or input_a.size(1) != in_features:
+        raise RuntimeError("input_a must be a float16 [M, in_features] tensor")
+    dt = projections[0][1].dtype
+    outs, keep = [], []
+    arr = (capi.GemvProblem * len(projections))()
+    m = input_a.size(0)
+    for i, (q, s, z) in enumerate(projections):
+        _check_quant_args(q, s, z, groupsize, bits, in_features)
+        if q.device.index != input_a.device.index or s.dtype != dt:
+            raise RuntimeError("all projections must live on the activation's device and share one scales dtype")
+        s16 = s.to(torch.float16) if s.dtype == torch.bfloat16 else s
+        o = torch.empty((m, q.size(1)), dtype=torch.float16, device=q.device)
+        keep.append(s16)
+        outs.append(o)
+        arr[i] = capi.GemvProblem(q.data_ptr(), s16.data_ptr(), z.data_ptr(), o.data_ptr(), q.size(1), q.size(1))
+    if m > 0:
+        with torch.cuda.device(input_a.device):
+            ws = gemv_workspace(input_a.device)
+            capi.check(capi.load().xbit_gemv_f16_multi(input_a.data_ptr(), ctypes.cast(arr, ctypes.c_void_p), len(projections), m,
+                                                       in_features, bits, groupsize, int(add_zero_bias), ws.data_ptr(), ws.numel(),
+                                                       int(family) | (capi.GEMV_FLAG_STATIC_WEIGHTS if _STATIC_WEIGHTS else 0),
+                                                       _stream_handle()))
+    return [o.to(torch.bfloat16) for o in outs] if dt == torch.bfloat16 else outs
