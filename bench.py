@@ -242,6 +242,9 @@ def run_gpu_arm(args):
     combine = args.combine if world > 1 else "none"
     sig = None
     llctx = None
+    if world > 1:
+        for ss in sets:                       # replicated activations (the N-split shards columns only)
+            dist.broadcast(ss.a, 0)
     if combine == "ll":
         try:
             import torch.distributed._symmetric_memory as symm_mem
@@ -259,11 +262,11 @@ def run_gpu_arm(args):
             if rank == 0:
                 print(f"[bench] symmetric memory unavailable ({ex}); falling back to nccl all-gather", file=sys.stderr)
             combine = "nccl"
-    if combine in ("peers", "signal"):
+    if world > 1:
         try:
-            for ss in sets:
+            for ss in sets:                   # peer-mapped result buffers: the peers / signal forms, and the plain-output figures beside ll
                 ss.make_symmetric(torch, dist)
-            if combine == "signal":
+            if True:
                 import torch.distributed._symmetric_memory as symm_mem
                 sflags = symm_mem.empty((64,), dtype=torch.int32, device=dev)
                 sflags.zero_()
@@ -275,8 +278,11 @@ def run_gpu_arm(args):
         except Exception as ex:  # noqa: BLE001
             if rank == 0:
                 print(f"[bench] symmetric memory unavailable ({ex}); falling back to nccl all-gather", file=sys.stderr)
-            combine = "nccl"
+            if combine in ("peers", "signal"):
+                combine = "nccl"
             sig = None
+            for ss in sets:
+                ss.symm = None
 
     def launch(ss: ShapeSet, j: int, mode: str = None):
         mode = mode or combine
@@ -398,6 +404,53 @@ def run_gpu_arm(args):
             ms = float(t.item())
         return ms
 
+    # ---- N > 1: correctness before speed.  For every exchange form this line reports, the sharded result of every shape
+    # (weight set 0) against the unsharded call on the gathered weights, computed on rank 0 and broadcast.
+    selfcheck = None
+    if world > 1:
+        import xbitops_b200 as X
+        selfcheck = {}
+        modes = [combine] + [m for m in ("none", "nccl", "peers", "signal") if m != combine and not (m in ("peers", "signal") and sets[0].symm is None)
+                             and not (m == "signal" and sig is None)]
+        for ss in sets:
+            parts = [[torch.empty_like(t_) for _ in range(world)] for t_ in (ss.qw[0], ss.sc[0], ss.qz[0])]
+            for lst, t_ in zip(parts, (ss.qw[0], ss.sc[0], ss.qz[0])):
+                dist.all_gather(lst, t_.contiguous())
+            full = torch.empty((1, ss.N_total), dtype=torch.float16, device=dev)
+            if rank == 0:
+                fq, fs, fz = (torch.cat(lst, dim=1).contiguous() for lst in parts)
+                full.copy_(X.gemv(ss.a, fq, fs, fz, GROUP, BITS, ss.K, 0))
+            dist.broadcast(full, 0)
+            del parts
+            ref_max = float(full.double().abs().max())
+            for mode in modes:
+                if mode == "ll" and llctx is None:
+                    continue
+                if mode == "ll":
+                    llctx["calls"], llctx["last_n"] = 0, 0
+                launch(ss, 0, mode)
+                finish_chain(mode)
+                torch.cuda.synchronize()
+                dist.barrier()
+                if mode == "ll":
+                    got = llctx["plain"][:ss.N_total].view(1, -1)
+                elif mode in ("peers", "signal"):
+                    got = ss.symm[0][0]
+                else:
+                    got = ss.out[0]
+                sl = slice(ss.col0, ss.col0 + ss.N) if mode == "none" else slice(0, ss.N_total)
+                err = float((got[:, sl].double() - full[:, sl].double()).abs().max()) / ref_max
+                key = f"{ss.K}x{ss.N_total}:{mode}"
+                selfcheck[key] = err
+        worst = torch.tensor([max(selfcheck.values())], device=dev, dtype=torch.float64)
+        dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+        if float(worst.item()) > 2e-3:
+            raise RuntimeError(f"sharded self-check failed on rank {rank}: {selfcheck}")
+        selfcheck = {"status": "ok", "max_normalised_error": float(worst.item()), "modes": modes,
+                     "how": "sharded call of every shape (weight set 0) in every exchange form vs the unsharded call on the gathered weights, <= 2e-3"}
+        if llctx is not None:
+            llctx["calls"], llctx["last_n"] = 0, 0
+
     graph, calls_per_step = capture(sets)
     step_bytes = sum(ss.bytes_call * ss.R for ss in sets)
     with ClockSampler(local_rank) as clk:
@@ -410,7 +463,9 @@ def run_gpu_arm(args):
     for ss in sets:
         # (flag-in-data mode needs a dependent chain: only a square shape chains with itself; the others are
         # timed kernel-only here and appear with their exchange in the aggregate)
-        solo_mode = "none" if (combine == "ll" and ss.K != ss.N_total) else None
+        # (flag-in-data mode needs a dependent chain, and only a square shape chains with itself: the others are timed here
+        # with the plain-[M, N] fused exchange -- peer stores + barrier -- and appear with the ll exchange in the aggregate)
+        solo_mode = ("peers" if ss.symm is not None else "nccl") if (combine == "ll" and ss.K != ss.N_total) else None
         g1, n1 = capture([ss], solo_mode)
         ms1 = timed(g1, max(3, args.steps // 4), 3) / max(3, args.steps // 4)
         us = ms1 * 1e3 / n1
@@ -420,7 +475,7 @@ def run_gpu_arm(args):
             "frac_of_8TBps_nominal": round(gbs / (8000.0 * world), 4), "algorithmic_bytes": ss.bytes_call,
             "rotating_sets": ss.R, "family": lib.xbit_gemv_pick_family(1, ss.K, ss.N, BITS, GROUP) if family == 0 else family}
         if solo_mode:
-            per_shape[f"{ss.K}x{ss.N_total}"]["us_per_call_is"] = "kernel only (this shape cannot chain with itself)"
+            per_shape[f"{ss.K}x{ss.N_total}"]["us_per_call_is"] = f"{solo_mode} exchange, plain [M, N] output (this shape cannot chain with itself in the ll form)"
         if world == 1:
             # labelled aside: the same calls on ONE weight set (it stays in the 126 MB L2) -- not a roofline figure
             gw, nw = capture([ss], None, same_set=True)
@@ -432,7 +487,7 @@ def run_gpu_arm(args):
             for mode in ("none", "nccl", "peers", "signal"):
                 if mode == (solo_mode or combine) or (mode in ("peers", "signal") and ss.symm is None) or (mode == "signal" and sig is None):
                     continue
-                if combine == "ll" and mode in ("peers", "signal"):
+                if mode == "signal" and sig is None:
                     continue
                 g2, n2 = capture([ss], mode)
                 ms2 = timed(g2, max(3, args.steps // 4), 3) / max(3, args.steps // 4)
@@ -450,14 +505,14 @@ def run_gpu_arm(args):
                        "calls_per_step": calls_per_step,
                        "l2_policy": "inputs larger than L2: every call reads a distinct weight set, >= 1 GiB rotated per shape",
                        "launch": "one CUDA graph per step, programmatic dependent launch" + (" off" if args.no_pdl else ""),
-                       "schedule": "cluster split-K" if args.no_streamk else "auto: cluster split-K; persistent stream-K where the cluster grid fills < 56 % of one wave and the matrix is >= 32 MB",
+                       "schedule": "cluster split-K" if args.no_streamk else "auto: persistent per-SM schedule (per-warp TMA rings, integer block math) where measured ahead, cluster split-K otherwise",
                        "combine": {"ll": "fused, flag-in-data: the kernel's epilogue stores every pair of results into every rank's buffer over NVLink as one 8-byte {results, call number} store; the next call of the dependent chain spins on the slots it needs while staging its activations (no barrier, no fence, no wait launch; one unpack kernel at the end of a step)",
                                    "signal": "fused: the kernel's epilogue stores its slice into every rank's buffer over NVLink and raises a per-rank completion flag; the next call's kernel awaits the flags before it reads its activations (one wait kernel at the end of a step)",
                                    "nccl": "nccl all_gather_into_tensor per call",
                                    "peers": "fused epilogue: NVLink peer stores into every rank's buffer + one symmetric-memory barrier per call",
                                    "none": "none"}[combine],
                        "parallelism": f"n-split x{world}" if world > 1 else "single"},
-            "per_shape": per_shape, "clocks": clk.summary(),
+            "per_shape": per_shape, "selfcheck": selfcheck, "clocks": clk.summary(),
             "gpu_launches": (calls_per_step + (1 if combine in ("signal", "ll") else 0)) * args.steps}
 
     if rank == 0:
@@ -472,9 +527,151 @@ def run_gpu_arm(args):
         avg_us = ms_per_step * 1e3 / calls_per_step
         line["roofline"] = {"bound": "hbm", "achieved": round(value / world, 2), "peak": peak, "unit": "GB/s",
                             "frac": round(value / world / peak, 4), "traffic": traffic, "peak_source": peak_src,
-                            "kernel": "xbit::gemv_w4_kernel", "avg_launch_us": round(avg_us, 3),
+                            "kernel": "xbit::gemv_w4p_kernel (persistent schedule; xbit::gemv_w4_kernel where AUTO keeps the cluster split-K kernel)", "avg_launch_us": round(avg_us, 3),
                             "algorithmic_bytes_per_launch": round(step_bytes / calls_per_step / world),
                             "frac_of_8TBps_nominal": round(value / world / 8000.0, 4)}
+
+    # ---- the other BASELINE.json configs and the op surface, same protocol (N = 1 only; explain the headline, not part of it)
+    if world == 1 and not args.quick:
+        import xbitops_b200 as X
+        from xbitops_b200 import ops
+        reps = max(3, args.steps // 10)
+
+        def graph_us(fn, calls, reps=reps, stream=None):
+            side = stream or torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                fn(0)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                for i in range(calls):
+                    fn(i)
+            for _ in range(3):
+                g.replay()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                g.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) * 1e3 / (reps * calls)
+
+        # (1) the operator surface: XbitOps.gemv as a reference user calls it, static weights asserted once
+        ops.set_static_weights(True)
+        surf = {}
+        tot_us = 0.0
+        for ss in sets:
+            def fn(i, ss=ss):
+                j = i % ss.R
+                ops.gemv(ss.a, ss.qw[j], ss.sc[j], ss.qz[j], GROUP, BITS, ss.K, 0, out=ss.out[j])
+            us = graph_us(fn, ss.R)
+            surf[f"{ss.K}x{ss.N_total}"] = round(us, 3)
+            tot_us += us * ss.R
+        ops.set_static_weights(False)
+        surf_gbs = step_bytes / tot_us / 1e3
+        line["op_surface"] = {"us_per_call": surf, "value": round(surf_gbs, 2), "unit": UNIT, "vs_value": round(surf_gbs / value, 4),
+                              "how": "xbitops_b200.gemv (the reference's op signature) with set_static_weights(True), same rotating sets, one CUDA graph per shape"}
+
+        # (2) multi-projection launches: Q/K/V and gate + up through xbit_gemv_f16_multi
+        fused = {}
+        for name, ss, P in (("qkv_fused", sets[0], 3), ("gate_up_fused", sets[1], 2)):
+            Rm = ss.R - ss.R % P
+            probs = []
+            for j in range(0, Rm, P):
+                arr = (capi.GemvProblem * P)()
+                for i in range(P):
+                    arr[i] = capi.GemvProblem(ss.qw[j + i].data_ptr(), ss.sc[j + i].data_ptr(), ss.qz[j + i].data_ptr(), ss.out[j + i].data_ptr(), ss.N, ss.N_total)
+                probs.append(arr)
+
+            def fn(i, ss=ss, probs=probs, P=P):
+                rc = lib.xbit_gemv_f16_multi(ss.a.data_ptr(), ctypes.cast(probs[i % len(probs)], ctypes.c_void_p), P, 1, ss.K, BITS, GROUP, 0,
+                                             ws_ptr, ws_len, family | flags, torch.cuda.current_stream().cuda_stream)
+                if rc != 0:
+                    raise RuntimeError(capi.last_error())
+            us = graph_us(fn, len(probs))
+            fused[name] = {"matrices": P, "shape": f"{ss.K}x{ss.N_total}", "us_per_launch": round(us, 3), "us_per_matrix": round(us / P, 3),
+                           "GBps": round(ss.bytes_call * P / us / 1e3, 1), "frac_of_measured_peak": round(ss.bytes_call * P / us / 1e3 / peak, 4)}
+        line["fused"] = fused
+
+        # (3) configs[4]: skinny GEMM M = 1..16 on 8192 x 8192
+        sk = ShapeSet(torch, dev, 8192, 8192, 1, 0, gen)
+        a16 = torch.randn((16, 8192), device=dev, generator=gen).to(torch.float16)
+        o16 = torch.empty((sk.R, 16, 8192), device=dev, dtype=torch.float16)
+        skinny = {}
+        for M in (1, 2, 4, 8, 16):
+            def fn(i, M=M):
+                j = i % sk.R
+                rc = lib.xbit_gemv_f16_ex(a16.data_ptr(), sk.qw[j].data_ptr(), sk.sc[j].data_ptr(), sk.qz[j].data_ptr(), o16[j].data_ptr(),
+                                          M, 8192, 8192, BITS, GROUP, 0, 8192, ws_ptr, ws_len, family | flags, torch.cuda.current_stream().cuda_stream)
+                if rc != 0:
+                    raise RuntimeError(capi.last_error())
+            us = graph_us(fn, sk.R)
+            nb = synth.gemv_bytes(8192, 8192, BITS, GROUP, M)
+            skinny[str(M)] = {"us_per_call": round(us, 3), "GBps": round(nb / us / 1e3, 1), "frac_of_measured_peak": round(nb / us / 1e3 / peak, 4),
+                              "family": lib.xbit_gemv_pick_family(M, 8192, 8192, BITS, GROUP)}
+        line["skinny"] = {"shape": "8192x8192", "by_M": skinny}
+        del sk, o16
+
+        # (4) configs[2]: dequant to fp16, bits 2..8 x group size 32 / 64 / 128 on 4096 x 11008
+        Kd, Nd, Rd = 4096, 11008, 3
+        outd = torch.empty((Rd, Kd, Nd), device=dev, dtype=torch.float16)
+        dq = {}
+        for b in range(2, 9):
+            for g in (32, 64, 128):
+                qw = torch.randint(-2**31, 2**31 - 1, (Rd, (Kd * b + 31) // 32, Nd), dtype=torch.int32, device=dev, generator=gen)
+                qz = torch.randint(-2**31, 2**31 - 1, (Rd, Kd // g, (Nd * b + 31) // 32), dtype=torch.int32, device=dev, generator=gen)
+                sc = (torch.rand((Rd, Kd // g, Nd), device=dev, generator=gen) * 0.018 + 0.002).to(torch.float16)
+
+                def fn(i, b=b, g=g, qw=qw, qz=qz, sc=sc):
+                    j = i % Rd
+                    rc = lib.xbit_dequant_f16(qw[j].data_ptr(), sc[j].data_ptr(), qz[j].data_ptr(), outd[j].data_ptr(), Kd, Nd, b, g, 1,
+                                              torch.cuda.current_stream().cuda_stream)
+                    if rc != 0:
+                        raise RuntimeError(capi.last_error())
+                us = graph_us(fn, 2 * Rd)
+                nb = synth.dq_bytes(Kd, Nd, b, g)
+                dq[f"b{b}_g{g}"] = {"us": round(us, 2), "GBps": round(nb / us / 1e3, 1), "frac_of_measured_peak": round(nb / us / 1e3 / peak, 4)}
+                del qw, qz, sc
+        line["dq"] = {"shape": "4096x11008", "by_bits_groupsize": dq,
+                      "note": "algorithmic bytes = packed weights + scales + zeros + fp16 output (80 % of it is the output write)"}
+        del outd
+
+        # (5) the reference's own GPU kernels (unmodified, built for compute_100 into oracle/_ref/refgpu) on the same tensors:
+        #     a reported baseline like cpu_baseline.  They launch on the legacy default stream and cannot be captured,
+        #     so they are timed as back-to-back eager calls between CUDA events, at::zeros of the op included.
+        import glob
+        import importlib.util
+        so = sorted(glob.glob(os.path.join(ROOT, "oracle", "_ref", "refgpu", "XbitOps*.so")))
+        if so:
+            try:
+                spec = importlib.util.spec_from_file_location("XbitOps", so[0])
+                refmod = importlib.util.module_from_spec(spec)
+                spec.loader.exec_module(refmod)
+                refgpu = {}
+                for ss in sets:
+                    if ss.N_total % 64:
+                        continue
+                    n = min(ss.R, 64)
+                    for j in range(3):
+                        refmod.gemv(ss.a, ss.qw[j], ss.sc[j], ss.qz[j], GROUP, BITS, ss.K, 0)
+                    torch.cuda.synchronize()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    for j in range(n):
+                        refmod.gemv(ss.a, ss.qw[j], ss.sc[j], ss.qz[j], GROUP, BITS, ss.K, 0)
+                    e1.record()
+                    torch.cuda.synchronize()
+                    us = e0.elapsed_time(e1) * 1e3 / n
+                    refgpu[f"{ss.K}x{ss.N_total}"] = {"us_per_call": round(us, 2), "GBps": round(ss.bytes_call / us / 1e3, 1)}
+                line["reference_gpu"] = {"per_shape": refgpu, "how": "unmodified reference extension (gemv_w4a16_pt.cu compiled for compute_100), "
+                                         "eager back-to-back calls over the same rotating sets, CUDA events, its at::zeros included"}
+            except Exception as ex:  # noqa: BLE001
+                line["reference_gpu"] = {"unavailable": str(ex)[:200]}
+        else:
+            line["reference_gpu"] = {"unavailable": "oracle/_ref/refgpu not built (oracle/build_ref_gpu.sh)"}
 
     # ---- e2e: the public host-buffer entry point, H2D activations + D2H result inside the timed region
     if world == 1:
@@ -523,13 +720,64 @@ def run_gpu_arm(args):
                               "the step's calls captured once into a CUDA graph and replayed, host wall clock incl. one sync per step; "
                               "weights resident; 'eager' = the same calls issued one by one from Python"}
     else:
-        line["e2e"] = None
+        # N > 1: host buffers in, host buffers out, through the sharded public path with a plain [M, N] result: pinned
+        # activations -> device (copy node), N-split GEMV with the fused peer-store exchange (+ barrier) or NCCL all-gather,
+        # gathered result -> pinned host memory (copy node); every rank does all of it, host wall clock, max over ranks
+        e2e_mode = "peers" if sets[0].symm is not None else "nccl"
+        hs = [(torch.randn((1, ss.K)).to(torch.float16).pin_memory(), torch.empty((1, ss.N_total), dtype=torch.float16).pin_memory()) for ss in sets]
+        saved_a = [ss.a for ss in sets]
+        stage = [torch.empty_like(ss.a) for ss in sets]
+
+        def e2e_calls():
+            for ss, (ha, ho), da in zip(sets, hs, stage):
+                ss.a = da
+                for j in range(ss.R):
+                    da.copy_(ha, non_blocking=True)
+                    launch(ss, j, e2e_mode)
+                    res = ss.symm[0][j] if e2e_mode == "peers" else ss.out[j]
+                    ho.copy_(res, non_blocking=True)
+
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            e2e_calls()
+        torch.cuda.current_stream().wait_stream(side)
+        sync_all()
+        ge = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(ge):
+            e2e_calls()
+        e2e_steps = max(3, min(args.steps, 20))
+        for _ in range(3):
+            ge.replay()
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            ge.replay()
+            torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / e2e_steps
+        tt = torch.tensor([dt], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        for ss, sa in zip(sets, saved_a):
+            ss.a = sa
+        line["e2e"] = {"value": round(step_bytes / dt / 1e9, 2), "unit": UNIT,
+                       "h2d_bytes_per_step": int(sum(ss.K * 2 * ss.R for ss in sets)) * world,
+                       "d2h_bytes_per_step": int(sum(ss.N_total * 2 * ss.R for ss in sets)) * world,
+                       "us_per_call": round(dt * 1e6 / calls_per_step, 3),
+                       "how": f"per call and rank: pinned activations -> device copy, N-split GEMV with the {e2e_mode} exchange (plain [M, N] output), "
+                              "gathered result -> pinned host copy; the step's calls captured into one CUDA graph per rank, host wall clock incl. "
+                              "one sync per step, max over ranks"}
+        del ge
 
     # ---- cpu baseline beside it (rank 0, N=1 only): bounded sample, single thread, stated
     if world == 1 and rank == 0 and not args.no_cpu:
         secs, nbytes, kind = cpu_reference_run([shapes[0]], 1)
         line["cpu_baseline"] = {"value": round(nbytes / secs / 1e9, 5), "unit": UNIT, "cores": 1, "kind": kind,
                                 "sample": f"1 call of {shapes[0][0]}x{shapes[0][1]} (dequant via cpp_simulate.cc + fp64 dot), {secs:.2f} s"}
+    elif rank == 0 and not args.no_cpu:
+        secs, nbytes, kind = cpu_reference_run([shapes[0]], 1)
+        line["cpu_baseline"] = {"value": round(nbytes / secs / 1e9, 5), "unit": UNIT, "cores": 1, "kind": kind,
+                                "sample": f"1 call of {shapes[0][0]}x{shapes[0][1]} (dequant via cpp_simulate.cc + fp64 dot), {secs:.2f} s, rank 0"}
     elif rank == 0:
         line["cpu_baseline"] = None
 
@@ -575,8 +823,10 @@ def run_gpu_arm(args):
             torch.cuda.synchronize()
             ms1 = e0.elapsed_time(e1) / reps
             b1 = sum(ss.bytes_call * ss.R for ss in sets_single)
-            line["single_gpu_same_workload"] = {"value": round(b1 / (ms1 * 1e-3) / 1e9, 2), "unit": UNIT,
+            v1 = b1 / (ms1 * 1e-3) / 1e9
+            line["single_gpu_same_workload"] = {"value": round(v1, 2), "unit": UNIT,
                                                 "ms_per_step": round(ms1, 5), "calls_per_step": sum(ss.R for ss in sets_single)}
+            line["efficiency_same_workload"] = round(value / (world * v1), 4)
             del g1
     if rank == 0:
         print(json.dumps(line), flush=True)
@@ -604,6 +854,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-streamk", action="store_true", help="no workspace: cluster split-K kernel instead of the persistent stream-K schedule")
     ap.add_argument("--no-single", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="headline, roofline, e2e and cpu_baseline only (skip the op-surface, fused, skinny, dq and reference-GPU legs)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

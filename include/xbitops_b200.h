@@ -94,6 +94,13 @@ enum {
 XBIT_API int xbit_version(void);                 /* major*10000 + minor*100 + patch */
 XBIT_API const char* xbit_last_error(void);      /* thread-local; "" when no error */
 
+/* Policy switches for tests and the developer tools (kernel family, decomposition, ring depth ...: XBIT_GEMV_FAMILY,
+ * XBIT_GEMV_STREAMK, XBIT_W4P_FINE, XBIT_W4P_RING, XBIT_DQ_SMEM_KB, ... -- the list is in csrc/gemv_sm100.cu).
+ * Each is read from the environment ONCE, when the library first needs one, and can be changed afterwards only here;
+ * value INT_MIN restores the built-in policy.  Results never depend on them beyond fp32 summation order.
+ * Thread-safe (atomics); XBIT_EINVAL for an unknown name. */
+XBIT_API int xbit_set_option(const char* name, int value);
+
 /* Dequantise to fp16.  bits in [2, 8]; groupsize >= 16; N even.  out is fully overwritten
  * (no pre-zeroing needed, unlike the reference's at::zeros, src/dq_torch_ops.cc:38). */
 XBIT_API int xbit_dequant_f16(const int32_t* qweight, const void* scales_f16, const int32_t* qzeros,

@@ -178,7 +178,7 @@ def test_gemv_streamk_schedule(dev, c_oracle, monkeypatch):
     """The opt-in persistent stream-K schedule (XBIT_GEMV_STREAMK=1 + workspace): same results, and the
     workspace is left zeroed (flags cleared) so that consecutive calls can share it."""
     from xbitops_b200 import ops
-    monkeypatch.setenv("XBIT_GEMV_STREAMK", "1")
+    capi.set_option("XBIT_GEMV_STREAMK", 1)
     # (K, N, M, g, bias): whole tiles per CTA and tiles shared by several CTAs, a half-empty last stage
     # (K = 4224 = 33 blocks), a partial last tile (N = 4128), fewer units than SMs (N = 96), every
     # groupsize of the fast path, both tensor-core tile heights (M <= 8, M <= 16)
@@ -194,11 +194,12 @@ def test_gemv_streamk_schedule(dev, c_oracle, monkeypatch):
         y2 = X.gemv(ta, tq, ts, tz, g, 4, K, bias, family=capi.GEMV_MMA)
         assert torch.equal(y1, y2)                           # deterministic, workspace reusable
         assert_gemv_close(y1.cpu().numpy(), y64, f"stream-K {K}x{N} M={M} g={g}")
-        monkeypatch.setenv("XBIT_GEMV_STREAMK", "0")         # the cluster split-K kernel on the same inputs
+        capi.set_option("XBIT_GEMV_STREAMK", 0)         # the cluster split-K kernel on the same inputs
         y3 = X.gemv(ta, tq, ts, tz, g, 4, K, bias, family=capi.GEMV_MMA)
-        monkeypatch.setenv("XBIT_GEMV_STREAMK", "1")
+        capi.set_option("XBIT_GEMV_STREAMK", 1)
         assert_gemv_close(y3.cpu().numpy(), y64, f"cluster {K}x{N} M={M} g={g}")
         assert float((y1.double() - y3.double()).abs().max()) <= 2e-3 * float(np.abs(y64).max())
+    capi.set_option("XBIT_GEMV_STREAMK")
     torch.cuda.synchronize()
     ws = ops.gemv_workspace(dev)
     assert int(ws[: 148 * 4].view(torch.int32).abs().sum()) == 0      # ready flags cleared
@@ -221,14 +222,14 @@ def test_gemv_persistent_schedule(dev, c_oracle, monkeypatch):
         tq, ts, tz, ta = ti(qw, dev), t16(s, dev), ti(qz, dev), t16(a, dev)
         ys = {}
         for fine in ("1", "0"):
-            monkeypatch.setenv("XBIT_W4P_FINE", fine)
+            capi.set_option("XBIT_W4P_FINE", int(fine))
             y1 = X.gemv(ta, tq, ts, tz, g, 4, K, bias, family=capi.GEMV_PERSIST)
             y2 = X.gemv(ta, tq, ts, tz, g, 4, K, bias, family=capi.GEMV_PERSIST)
             assert torch.equal(y1, y2), f"persist fine={fine} {K}x{N} M={M}: not deterministic"
             assert_gemv_close(y1.cpu().numpy(), y64, f"persist fine={fine} {K}x{N} M={M} g={g}")
             ys[fine] = y1
         assert float((ys["1"].double() - ys["0"].double()).abs().max()) <= 2e-3 * float(np.abs(y64).max())
-    monkeypatch.delenv("XBIT_W4P_FINE")
+    capi.set_option("XBIT_W4P_FINE")
     torch.cuda.synchronize()
     ws = ops.gemv_workspace(dev)
     lib = capi.load()

@@ -16,8 +16,8 @@ for (K, N) in ((4096, 11008), (8192, 8192), (8192, 28672), (28672, 8192)):
     for skip in (0, 1):
         row = f"   skip_math={skip}:"
         for ring in (2, 3, 4, 5, 6, 8):
-            os.environ["XBIT_GEMV_RING"] = str(ring)
-            os.environ["XBIT_GEMV_DEBUG_SKIP"] = str(skip)
+            capi.set_option("XBIT_GEMV_RING", int(str(ring)))
+            capi.set_option("XBIT_GEMV_DEBUG_SKIP", int(str(skip)))
 
             def fn(i):
                 j = i % R

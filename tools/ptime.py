@@ -40,23 +40,23 @@ def main():
                 assert rc == 0, capi.last_error()
             return sweep.time_graph(fn, R)
 
-        os.environ["XBIT_GEMV_STREAMK"] = "0"
+        capi.set_option("XBIT_GEMV_STREAMK", int("0"))
         us = run(capi.GEMV_MMA, ws=False)
         print(f"   cluster split-K (round 1)      {us:6.2f} us  {nbytes/us/1e3/PEAK*100:3.0f}%", flush=True)
         for var in variants:
             fine, ring, grid = var[:3]
             warps = var[3] if len(var) > 3 else 0
-            os.environ["XBIT_W4P_FINE"] = str(fine)
-            os.environ["XBIT_W4P_RING"] = str(ring)
-            os.environ["XBIT_W4P_GRID"] = str(grid)
-            os.environ["XBIT_W4P_WARPS"] = str(warps)
+            capi.set_option("XBIT_W4P_FINE", int(str(fine)))
+            capi.set_option("XBIT_W4P_RING", int(str(ring)))
+            capi.set_option("XBIT_W4P_GRID", int(str(grid)))
+            capi.set_option("XBIT_W4P_WARPS", int(str(warps)))
             try:
                 us = run(capi.GEMV_PERSIST)
                 print(f"   persist fine={fine} ring={ring or 'A'} grid={grid or 'A'} warps={warps or 'A'}   {us:6.2f} us  {nbytes/us/1e3/PEAK*100:3.0f}%", flush=True)
             except AssertionError as ex:
                 print(f"   persist fine={fine} ring={ring} grid={grid} warps={warps}: {ex}")
         for k in ("XBIT_W4P_FINE", "XBIT_W4P_RING", "XBIT_W4P_GRID", "XBIT_W4P_WARPS"):
-            os.environ.pop(k, None)
+            capi.set_option(k)
         # correctness spot check against a @ dequant
         import xbitops_b200 as X
         w = X.dequant(qw[0], sc[0], qz[0], 128, 4, K, 0)

@@ -21,8 +21,8 @@ def main():
         for fam, name in ((capi.GEMV_MMA, "mma"),):
             row = f"   {name}:"
             for label, sk, ring in (("cluster", 0, 0), ("stream-K", 1, 0), ("stream-K ring 4", 1, 4), ("stream-K ring 6", 1, 6)):
-                os.environ["XBIT_GEMV_STREAMK"] = str(sk)
-                os.environ["XBIT_GEMV_RING"] = str(ring)
+                capi.set_option("XBIT_GEMV_STREAMK", int(str(sk)))
+                capi.set_option("XBIT_GEMV_RING", int(str(ring)))
 
                 def fn(i):
                     j = i % R
@@ -36,8 +36,8 @@ def main():
                 except AssertionError as e:
                     row += f"  {label} n/a"
             print(row, flush=True)
-        os.environ["XBIT_GEMV_STREAMK"] = "0"
-        os.environ["XBIT_GEMV_RING"] = "0"
+        capi.set_option("XBIT_GEMV_STREAMK", int("0"))
+        capi.set_option("XBIT_GEMV_RING", int("0"))
         del qw, sc, qz, out
 
 

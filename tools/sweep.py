@@ -72,18 +72,18 @@ def main():
     for (K, N) in shapes:
         R, qw, sc, qz, a, out, nbytes = make(K, N)
         print(f"== {K}x{N} {nbytes/1e6:.1f} MB R={R} roofline {nbytes/PEAK/1e3:.2f} us")
-        os.environ["XBIT_GEMV_STREAMK"] = "0"
+        capi.set_option("XBIT_GEMV_STREAMK", int("0"))
         fams = ((capi.GEMV_SIMT, "simt      ", 0), (capi.GEMV_MMA, "mma       ", 0))
         if os.environ.get("SWEEP_MMA_ONLY"):
             fams = fams[1:2]
         ring_env = os.environ.get("SWEEP_RING", "0")
         for fam, name, hyb in fams:
-            os.environ["XBIT_GEMV_RING"] = ring_env
+            capi.set_option("XBIT_GEMV_RING", int(ring_env))
             for wc in (0, 2, 4, 8):
                 row = f"   {name} wc={wc if wc else 'A'}:"
                 for splits in ((0,) if wc == 0 else (1, 2, 3, 4, 5, 6, 7, 8)):
-                    os.environ["XBIT_GEMV_SPLITS"] = str(splits)
-                    os.environ["XBIT_GEMV_WC"] = str(wc)
+                    capi.set_option("XBIT_GEMV_SPLITS", int(str(splits)))
+                    capi.set_option("XBIT_GEMV_WC", int(str(wc)))
                     flags = capi.GEMV_FLAG_STATIC_WEIGHTS
 
                     def fn(i):
@@ -98,11 +98,11 @@ def main():
                     except AssertionError:
                         row += f"  s{splits} n/a"
                 print(row, flush=True)
-        os.environ["XBIT_GEMV_WC"] = "0"
-        os.environ["XBIT_GEMV_SPLITS"] = "0"
-        os.environ["XBIT_GEMV_RING"] = "0"
-        os.environ["XBIT_GEMV_WC"] = "0"
-        os.environ["XBIT_GEMV_SPLITS"] = "0"
+        capi.set_option("XBIT_GEMV_WC", int("0"))
+        capi.set_option("XBIT_GEMV_SPLITS", int("0"))
+        capi.set_option("XBIT_GEMV_RING", int("0"))
+        capi.set_option("XBIT_GEMV_WC", int("0"))
+        capi.set_option("XBIT_GEMV_SPLITS", int("0"))
         del qw, sc, qz, out
 
 

@@ -43,7 +43,7 @@ if stage in ("time", "all"):
         row = f"== {K}x{N}: roofline {nbytes/6549.8/1e3:.2f} us |"
         for fam, name in ((capi.GEMV_MMA, "mma"), (capi.GEMV_TCGEN05, "tc5")):
             for ring in ((4,) if fam == capi.GEMV_MMA else (3, 4, 5, 6)):
-                os.environ["XBIT_GEMV_RING"] = str(ring)
+                capi.set_option("XBIT_GEMV_RING", int(str(ring)))
 
                 def fn(i):
                     j = i % R

@@ -20,6 +20,7 @@ _vp, _i, _i64, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_siz
 SIGNATURES = {
     "xbit_version": (_i, []),
     "xbit_last_error": (ctypes.c_char_p, []),
+    "xbit_set_option": (_i, [ctypes.c_char_p, _i]),
     "xbit_dequant_f16": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "xbit_gemv_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "xbit_gemv_f16": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i64, _vp, _sz, _vp]),
@@ -76,6 +77,13 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
         fn.restype, fn.argtypes = res, args
     _lib = lib
     return lib
+
+
+UNSET = -2**31          # xbit_set_option(name, UNSET): back to the built-in policy
+
+
+def set_option(name: str, value: int = UNSET) -> None:
+    check(load().xbit_set_option(name.encode(), int(value)))
 
 
 def last_error() -> str:

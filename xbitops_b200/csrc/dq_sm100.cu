@@ -22,6 +22,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <type_traits>
 #include <utility>
 
@@ -169,6 +170,14 @@ dq_element_kernel(const uint32_t* __restrict__ qweight, const __half* __restrict
   out[idx] = __hfma(__ushort2half_rn((unsigned short)wv), s, __hneg(sz));
 }
 
+// Occupancy cap of the block kernel in KiB of (unused) dynamic shared memory per 128-thread block: 48 KiB = 4 blocks per
+// SM, measured best on 4096 x 11008 (profiles/r02_pdq_occupancy_cap.log: 74-80 % -> 81-86 % of the copy peak);
+// option XBIT_DQ_SMEM_KB overrides it (tools/pdq.py).
+static int dq_smem_cap_kb() {
+  const int v = env_int("XBIT_DQ_SMEM_KB", 48);
+  return (v < 0 || v > 200) ? 48 : v;
+}
+
 template <int B>
 static cudaError_t launch_block32(const DqArgs& a, cudaStream_t stream) {
   const int rblocks = (a.K + 31) / 32;
@@ -178,6 +187,20 @@ static cudaError_t launch_block32(const DqArgs& a, cudaStream_t stream) {
   cfg.gridDim = dim3(grid, 1, 1);
   cfg.blockDim = dim3(128, 1, 1);
   cfg.stream = stream;
+  // Occupancy cap (unused dynamic shared memory): with every block resident at once (10 per SM hold a whole 4096 x 11008
+  // matrix in one wave) all threads read first and all write afterwards, DRAM is busy a third of the time
+  // (profiles/r02_ncu_dq_*); a few waves of blocks stagger, and the loads of one wave overlap the stores of the previous.
+  // (only when the grid still makes at least two such waves; small matrices keep every block resident)
+  const int cap_kb = grid >= 8u * (unsigned)device_sm_count() ? dq_smem_cap_kb() : 0;
+  if (cap_kb > 48) {
+    static bool done[8] = {false, false, false, false, false, false, false, false};
+    if (!done[B - 1]) {
+      cudaError_t e = cudaFuncSetAttribute(dq_block32_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (e != cudaSuccess) return e;
+      done[B - 1] = true;
+    }
+  }
+  cfg.dynamicSmemBytes = (size_t)cap_kb * 1024;
   cudaLaunchAttribute attrs[1];
   attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attrs[0].val.programmaticStreamSerializationAllowed = 1;

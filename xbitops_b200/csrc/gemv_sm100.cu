@@ -45,6 +45,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <limits.h>
 #include <math.h>
 #include <string.h>
 
@@ -1529,9 +1530,56 @@ bool gemv_w4_supported(const GemvArgs& a) {
   return a.bits == 4 && group_ok && a.K % 128 == 0 && a.N % 32 == 0 && (al & 15u) == 0 && a.M >= 1;
 }
 
+// Policy switches (XBIT_GEMV_* / XBIT_W4P_* / XBIT_DQ_*): a fixed table of atomics, initialised ONCE from the
+// environment and changed at run time only through xbit_set_option (tests, tools/*.py).  No getenv on the launch path,
+// no unsynchronised lazy statics.
+namespace {
+struct Option {
+  const char* name;
+  std::atomic<int> value;
+  std::atomic<bool> set;
+};
+Option g_options[] = {
+    {"XBIT_GEMV_FAMILY", {0}, {false}},  {"XBIT_GEMV_STREAMK", {0}, {false}}, {"XBIT_GEMV_WC", {0}, {false}},
+    {"XBIT_GEMV_SPLITS", {0}, {false}},  {"XBIT_GEMV_RING", {0}, {false}},    {"XBIT_W4P_WARPS", {0}, {false}},
+    {"XBIT_W4P_I8", {0}, {false}},       {"XBIT_W4P_FINE", {0}, {false}},     {"XBIT_W4P_GRID", {0}, {false}},
+    {"XBIT_W4P_BPS", {0}, {false}},      {"XBIT_W4P_RING", {0}, {false}},     {"XBIT_W4P_ALLWAIT", {0}, {false}},
+    {"XBIT_W4P_DELAY", {0}, {false}},    {"XBIT_W4P_REDUX", {0}, {false}},    {"XBIT_DQ_SMEM_KB", {0}, {false}},
+    {"XBIT_GEMV_DEBUG_SKIP", {0}, {false}},
+};
+std::once_flag g_options_once;
+void load_options_from_env() {
+  for (Option& o : g_options) {
+    const char* v = getenv(o.name);
+    if (v && *v) {
+      o.value.store(atoi(v));
+      o.set.store(true);
+    }
+  }
+}
+Option* find_option(const char* name) {
+  std::call_once(g_options_once, load_options_from_env);
+  for (Option& o : g_options)
+    if (strcmp(o.name, name) == 0) return &o;
+  return nullptr;
+}
+}  // namespace
+
 int env_int(const char* name, int dflt) {
-  const char* v = getenv(name);
-  return (v && *v) ? atoi(v) : dflt;
+  const Option* o = find_option(name);
+  return (o && o->set.load(std::memory_order_relaxed)) ? o->value.load(std::memory_order_relaxed) : dflt;
+}
+
+// value == INT_MIN: back to "unset" (the built-in policy).  false: unknown option name.
+bool set_option(const char* name, int value) {
+  Option* o = find_option(name);
+  if (!o) return false;
+  if (value == INT_MIN) o->set.store(false);
+  else {
+    o->value.store(value);
+    o->set.store(true);
+  }
+  return true;
 }
 
 

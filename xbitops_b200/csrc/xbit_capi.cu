@@ -49,7 +49,13 @@ int check_common(const void* qweight, const void* scales, const void* qzeros, in
 
 extern "C" {
 
-int xbit_version(void) { return 100; /* 0.1.0 */ }
+int xbit_version(void) { return 200; /* 0.2.0 */ }
+
+int xbit_set_option(const char* name, int value) {
+  g_err[0] = 0;
+  if (!name || !xbit::set_option(name, value)) return fail(XBIT_EINVAL, "unknown option %s", name ? name : "(null)");
+  return XBIT_OK;
+}
 
 const char* xbit_last_error(void) { return g_err; }
 
@@ -96,11 +102,7 @@ static int pick_family(const xbit::GemvArgs& a) {
   // bits fed to the tensor core as fp16 subnormals the mma.sync kernel needs one ALU op per weight
   // pair and accumulates in fp32, so it is at least as fast as the SIMT half2-FMA kernel already
   // at M = 1 and strictly more accurate.  SIMT stays selectable (family / XBIT_GEMV_FAMILY).
-  static int forced = -1;
-  if (forced < 0) {
-    const char* v = getenv("XBIT_GEMV_FAMILY");
-    forced = (v && *v) ? atoi(v) : 0;
-  }
+  const int forced = xbit::env_int("XBIT_GEMV_FAMILY", 0);
   if (forced == XBIT_GEMV_SIMT && a.M == 1) return XBIT_GEMV_SIMT;
   if (forced == XBIT_GEMV_MMA) return XBIT_GEMV_MMA;
   if (forced == XBIT_GEMV_GENERIC) return XBIT_GEMV_GENERIC;
@@ -114,9 +116,9 @@ static bool use_streamk(const xbit::GemvArgs& g, int family, void* workspace, si
   // wherever it applies, =0 off; otherwise the measured policy of gemv_w4_prefers_streamk decides.
   if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255u)) return false;
   if (workspace_bytes < xbit::gemv_w4_streamk_workspace_bytes(g.M)) return false;
-  const char* v = getenv("XBIT_GEMV_STREAMK");
-  if (v && *v == '0') return false;
-  if (v && *v == '1') return xbit::gemv_w4_streamk_applicable(g, family);
+  const int v = xbit::env_int("XBIT_GEMV_STREAMK", -1);
+  if (v == 0) return false;
+  if (v == 1) return xbit::gemv_w4_streamk_applicable(g, family);
   return xbit::gemv_w4_prefers_streamk(g, family);
 }
 

@@ -83,7 +83,8 @@ cudaError_t launch_gemv_w4_tc5(GemvArgs a, cudaStream_t stream);
 cudaError_t launch_gemv_generic(GemvArgs a, cudaStream_t stream);
 
 int device_sm_count();
-int env_int(const char* name, int dflt);
+int env_int(const char* name, int dflt);     // policy switch: environment at load time, xbit_set_option afterwards
+bool set_option(const char* name, int value);
 void apply_debug_knobs(GemvArgs& a);   // no-op unless built with -DXBIT_DEVTOOLS
 constexpr size_t kMaxDynSmem = 220 * 1024;
 // cached cuTensorMapEncodeTiled (a pure function of its arguments) and the one-time dynamic shared memory opt-in
