@@ -343,6 +343,60 @@ def test_gemv_full_size_properties(K, N, dev):
         assert_gemv_close(ysl.cpu().numpy(), truth[:1, half:], f"{K}x{N} column shard, family {fam}", floor_of(fam))
 
 
+@pytest.mark.parametrize("bits", range(2, 9))
+def test_dequant_full_size_bands_vs_oracle(bits, dev, c_oracle):
+    """BASELINE config 3 at its real size (4096 x 11008), every bit width and group size: three 256-row bands of the
+    output (first, one that straddles group and word-row boundaries of every width, last) bit for bit against the C
+    oracle (oracle.dequant with k_range restates only the band, so the CPU side stays a few seconds)."""
+    K, N = 4096, 11008
+    for g in (32, 64, 128):
+        qw, s, qz, _ = synth.make_inputs(K, N, bits, g, seed=100 + bits + g)
+        got = X.dequant(ti(qw, dev), t16(s, dev), ti(qz, dev), g, bits, K, 1).cpu().numpy().view(np.uint16)
+        for k0 in (0, 1888, K - 256):
+            want = c_oracle.dequant(qw, s, qz, g, bits, K, 1, k_range=(k0, k0 + 256)).view(np.uint16)
+            assert (got[k0:k0 + 256] == want[k0:k0 + 256]).all(), f"bits={bits} g={g} rows {k0}..{k0 + 256}"
+
+
+def test_gemv_auto_never_fails_for_large_m_times_k(dev, c_oracle):
+    """M = 16 / 17 with K = 32768 has no K split that stages the activations in shared memory for the
+    tensor-core kernels; AUTO must fall back to smaller row slabs (or the generic kernel), not fail."""
+    K, N, g = 32768, 64, 128
+    qw, s, qz, a = synth.make_inputs(K, N, 4, g, M=17, seed=11)
+    w = c_oracle.dequant(qw, s, qz, g, 4, K, 1)
+    tq, ts, tz = ti(qw, dev), t16(s, dev), ti(qz, dev)
+    for M in (16, 17, 8):
+        y64 = a[:M].astype(np.float64) @ w.astype(np.float64)
+        got = X.gemv(t16(a[:M], dev), tq, ts, tz, g, 4, K, 1).cpu().numpy()
+        assert_gemv_close(got, y64, f"AUTO M={M} K={K}")
+
+
+def test_gemv_persistent_schedule_is_race_free_under_repetition(dev):
+    """compute-sanitizer is closed on the GPU pool (tools/sanitize.sh documents the attempt), so the shared-memory and
+    cross-CTA hand-offs of the persistent kernel are checked by repetition instead: 60 back-to-back launches per shape
+    (programmatic dependent launch, the workspace and the rings reused by overlapping launches) must reproduce the
+    first result bit for bit -- any race in the partial-tile protocol shows up as a differing sum."""
+    gen = torch.Generator(device=dev).manual_seed(5)
+    for (K, N, M, g, fine) in ((4096, 4096, 1, 128, 0), (4096, 11008, 1, 128, 1), (11008, 4096, 2, 128, 1), (2048, 4736, 3, 64, 1),
+                              (8192, 8192, 1, 128, 1)):
+        qw = torch.randint(-2**31, 2**31 - 1, (K // 8, N), dtype=torch.int32, device=dev, generator=gen)
+        qz = torch.randint(-2**31, 2**31 - 1, (K // g, N // 8), dtype=torch.int32, device=dev, generator=gen)
+        s = (torch.rand((K // g, N), device=dev, generator=gen) * 0.018 + 0.002).to(torch.float16)
+        a = torch.randn((M, K), device=dev, generator=gen).to(torch.float16)
+        capi.set_option("XBIT_W4P_FINE", fine)
+        X.set_static_weights(True)
+        try:
+            outs = torch.empty((60, M, N), dtype=torch.float16, device=dev)
+            for i in range(60):
+                X.gemv(a, qw, s, qz, g, 4, K, 1, family=capi.GEMV_PERSIST, out=outs[i])
+            torch.cuda.synchronize()
+        finally:
+            X.set_static_weights(False)
+            capi.set_option("XBIT_W4P_FINE")
+        assert bool((outs == outs[0]).all()), f"{K}x{N} M={M} fine={fine}: repeated launches differ"
+        truth = a.double() @ X.dequant(qw, s, qz, g, 4, K, 1).double()
+        assert_gemv_close(outs[0].cpu().numpy(), truth.cpu().numpy(), f"{K}x{N} M={M}")
+
+
 def test_gemv_runs_on_current_stream_and_is_graph_capturable(dev):
     """The reference launches gemv on the legacy default stream (gemv_w4a16_pt.cu:162); ours must
     follow torch's current stream and be capturable (no sync, no allocation inside the C ABI)."""
@@ -443,6 +497,12 @@ def test_flag_in_data_chain_single_gpu(dev):
     got1 = slots[..., 0].contiguous().view(torch.float16).view(M, N)
     assert float((got1.double() - y1.double()).abs().max()) <= 2e-3 * float(y1.double().abs().max())
     assert float((out.double() - y2.double()).abs().max()) <= 4e-3 * float(y2.double().abs().max())
+    # and against the oracle-defined truth (fp64 dot over the bit-exact dequantised weights), call by call
+    w64 = X.dequant(tq, ts, tz, 128, 4, K, 1).double()
+    t1 = ta.double() @ w64
+    assert_gemv_close(got1.cpu().numpy(), t1.cpu().numpy(), "LL chain call 0")
+    t2 = got1.double() @ w64                                    # the second call's input is the first call's fp16 output
+    assert_gemv_close(out.cpu().numpy(), t2.cpu().numpy(), "LL chain call 1")
     # restrictions are reported, not executed
     rc = lib.xbit_gemv_f16_peers_ll(ta.data_ptr(), tq.data_ptr(), ts.data_ptr(), tz.data_ptr(), (ctypes.c_void_p * 1)(ll[0].data_ptr()),
                                     state.data_ptr(), 0, 1, 0, M, K, N, 3, 128, 1, N, 0, capi.GEMV_AUTO, st)

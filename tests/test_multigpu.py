@@ -186,13 +186,16 @@ def _worker(rank, world, port, combine, ret):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("world", (2, 4, 8))
 @pytest.mark.parametrize("combine", ("nccl", "peers", "signal", "ll"))
-def test_sharded_gemv_two_gpus(combine):
+def test_sharded_gemv_multi_gpu(combine, world):
+    """N-split over 2 / 4 / 8 GPUs of one box in every exchange form: against a @ dequant, identical on every rank, and
+    against the unsharded call (skipped where the box has fewer GPUs; bench.py --gpus N repeats the check before timing)."""
     if not torch.cuda.is_available():
         pytest.fail("gpu-marked test without a CUDA device")
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
     with mp.Manager() as mgr:
         ret = mgr.dict()
-        mp.spawn(_worker, args=(2, _free_port(), combine, ret), nprocs=2, join=True)
-        assert ret.get(0) is True and ret.get(1) is True, dict(ret)
+        mp.spawn(_worker, args=(world, _free_port(), combine, ret), nprocs=world, join=True)
+        assert all(ret.get(r) is True for r in range(world)), dict(ret)
