@@ -20,6 +20,9 @@ def __getattr__(name):
     if name in ("dequant", "gemv", "gemv_multi", "set_static_weights", "get_static_weights"):
         from . import ops
         return getattr(ops, name)
+    if name in ("QLinear", "pack_qweight", "pack_qzeros", "quantize_rtn"):
+        from . import qlinear
+        return getattr(qlinear, name)
     if name in ("ShardedQLinear", "shard_columns"):
         from . import sharded
         return getattr(sharded, name)

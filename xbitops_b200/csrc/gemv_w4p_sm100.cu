@@ -69,6 +69,12 @@ struct W4PArgs {
   int all_wait;             // every consumer warp executes griddepcontrol.wait (comparison knob)
   int stage_redux;          // group reductions of the activation staging with REDUX instead of shuffle trees (A/B knob)
   int prefetch_delay;       // SM clocks the producer waits before its first request (only when it starts ahead of the wait)
+  // flag-in-data ("LL") form of the N-split exchange (xbit_gemv_f16_peers_ll, see gemv_sm100.cu): results leave as 8-byte
+  // {two fp16 results, call number} stores into every rank's buffer; activations may arrive the same way
+  int ll_out;               // prob[].out[] are LL buffers ([M][ldo/2] 8-byte slots); call number = ll_state[2] + ll_chain_index + 1
+  int a_is_ll;              // `a` is the LL buffer the previous call filled (K/2 slots per row): no wait for the previous grid
+  int ll_chain_index;       // position of this call in its chain (0 = first)
+  unsigned int* ll_state;   // local: [2] chain base, [3] timeout flag
   int count;                // weight matrices: the CTA works through its range of each, one after the other
   W4PProblem prob[kPMaxProblems];
   unsigned long long* trace;
@@ -301,6 +307,25 @@ __device__ __forceinline__ void w4p_consume_i8(const unsigned char* const (&wp)[
   }
 }
 
+__device__ __forceinline__ void p_ll_store(unsigned long long* slot, uint32_t data, uint32_t epoch) {
+  asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(slot), "r"(data), "r"(epoch) : "memory");
+}
+// 8 consecutive halves = 4 slots; spins until all four carry `epoch` (guard: reports in ll_state[3])
+__device__ __forceinline__ uint4 p_ll_load8(const unsigned long long* slots, uint32_t epoch, unsigned int* timeout_flag) {
+  uint4 q0, q1;
+  const long long c0 = clock64();
+  for (unsigned int n = 1;; ++n) {
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q0.x), "=r"(q0.y), "=r"(q0.z), "=r"(q0.w) : "l"(slots) : "memory");
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q1.x), "=r"(q1.y), "=r"(q1.z), "=r"(q1.w) : "l"(slots + 2) : "memory");
+    if (q0.y == epoch && q0.w == epoch && q1.y == epoch && q1.w == epoch) break;
+    if ((n & 1023u) == 0 && clock64() - c0 > kPSpinGuardClocks) {
+      *timeout_flag = 1u;
+      break;
+    }
+  }
+  return make_uint4(q0.x, q0.z, q1.x, q1.z);
+}
+
 // slice (eighth of the CTA's range) of consumer warp w: warps w and w + 4 share an SM sub-partition and adjacent
 // slices differ by at most one block, so every sub-partition gets two ADJACENT slices
 template <int NW>
@@ -385,8 +410,12 @@ gemv_w4p_kernel(const __grid_constant__ W4PMaps maps, const __grid_constant__ W4
     }
   }
   __syncthreads();
-  // the next kernel in the stream may become resident now: its producer streams ITS weights while this one runs
-  griddep_launch_dependents();
+  // the next kernel in the stream may become resident now: its producer streams ITS weights while this one runs.
+  // Exception: the FIRST call of an LL chain releases its dependents only after its own griddepcontrol.wait has returned
+  // (the calls behind it do not wait for the grid before them and read the chain base that the previous chain's unpack
+  // advances; see gemv_w4_kernel)
+  const bool defer_dependents = a.ll_out && !a.a_is_ll;
+  if (!defer_dependents) griddep_launch_dependents();
 
   if (warp == NW) {
     // =========================== producer: LPR lanes drive each consumer warp's ring ===========================
@@ -491,8 +520,13 @@ gemv_w4p_kernel(const __grid_constant__ W4PMaps maps, const __grid_constant__ W4
   // The activations are the only data produced by the previous kernel.  ONE warp waits for it; the others block on a
   // hardware barrier behind that warp: warps parked in griddepcontrol.wait were measured to slow the co-resident CTA of
   // the previous launch down (XBIT_W4P_ALLWAIT=1 restores the plain form for the comparison).
-  if (a.all_wait || warp == 0) griddep_wait();
-  if (!a.all_wait) asm volatile("bar.sync 1, %0;" ::"n"(kPConsumerThreads) : "memory");
+  // (a call fed from an LL buffer carries its dependency in the data: every slot is validated by its own call number)
+  if (!a.a_is_ll) {
+    if (a.all_wait || warp == 0) griddep_wait();
+    if (!a.all_wait) asm volatile("bar.sync 1, %0;" ::"n"(kPConsumerThreads) : "memory");
+  }
+  if (defer_dependents) griddep_launch_dependents();
+  const uint32_t ll_in_epoch = a.a_is_ll ? a.ll_state[2] + (uint32_t)a.ll_chain_index : 0u;     // the previous call's number
   if (tid == 0) P_TRACE(2);
   if constexpr (I8) {
     // stage the activations once per CTA as three unsigned byte planes of 24-bit fixed point relative to the largest |a|
@@ -512,7 +546,8 @@ gemv_w4p_kernel(const __grid_constant__ W4PMaps maps, const __grid_constant__ W4
         for (int b = 0; b < kBatch; ++b) {
           const int v = v0 + b * kPConsumerThreads + lane;
           val[b] = make_uint4(0, 0, 0, 0);
-          if (v < vecs) val[b] = __ldcg(arow + v);
+          if (v < vecs) val[b] = a.a_is_ll ? p_ll_load8(reinterpret_cast<const unsigned long long*>(a.a) + (((size_t)m * a.K) >> 1) + 4 * (size_t)v, ll_in_epoch, a.ll_state + 3)
+                                           : __ldcg(arow + v);
         }
 #pragma unroll
         for (int b = 0; b < kBatch; ++b) {
@@ -595,7 +630,8 @@ gemv_w4p_kernel(const __grid_constant__ W4PMaps maps, const __grid_constant__ W4
         for (int b = 0; b < kBatch; ++b) {
           const int v = v0 + b * kPConsumerThreads + lane;
           val[b] = make_uint4(0, 0, 0, 0);
-          if (v < vecs) val[b] = __ldcg(arow + v);  // L2 only: may just have been written by the previous kernel or a peer GPU
+          if (v < vecs) val[b] = a.a_is_ll ? p_ll_load8(reinterpret_cast<const unsigned long long*>(a.a) + (((size_t)m * a.K) >> 1) + 4 * (size_t)v, ll_in_epoch, a.ll_state + 3)
+                                           : __ldcg(arow + v);  // L2 only: may just have been written by the previous kernel or a peer GPU
         }
 #pragma unroll
         for (int b = 0; b < kBatch; ++b) {
@@ -843,8 +879,18 @@ gemv_w4p_kernel(const __grid_constant__ W4PMaps maps, const __grid_constant__ W4
         if (starts_tile) {
           const __half h = __float2half_rn(v);
           const size_t off = (size_t)m * P.ldo + P.col_offset + n;
-          P.out[0][off] = h;
-          for (int p = 1; p < a.world; ++p) P.out[p][off] = h;      // fused all-gather: NVLink peer stores
+          if (a.ll_out) {
+            // flag-in-data all-gather: each PAIR of results goes to every rank as one {half2, call number} store
+            const uint32_t lo16 = (uint32_t)__half_as_ushort(h);
+            const uint32_t hi16 = __shfl_down_sync(0xffffffffu, lo16, 1);
+            if ((lane & 1) == 0) {
+              const uint32_t epoch = a.ll_state[2] + (uint32_t)a.ll_chain_index + 1u;
+              for (int p = 0; p < a.world; ++p) p_ll_store(reinterpret_cast<unsigned long long*>(P.out[p]) + (off >> 1), lo16 | (hi16 << 16), epoch);
+            }
+          } else {
+            P.out[0][off] = h;
+            for (int p = 1; p < a.world; ++p) P.out[p][off] = h;    // fused all-gather: NVLink peer stores
+          }
         } else {
           // contributor: this CTA holds later blocks of a tile that starts in an earlier CTA
           asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(P.ws + ((size_t)c * a.M + m) * 32 + lane), "r"(__float_as_uint(v)), "r"(1u) : "memory");
@@ -1022,6 +1068,10 @@ cudaError_t launch_gemv_w4p_multi(const GemvArgs* gs, int count, void* workspace
   a.prefetch_delay = env_int("XBIT_W4P_DELAY", 0);
   a.stage_redux = env_int("XBIT_W4P_REDUX", 1);
   a.count = count;
+  a.ll_out = g0.ll_out;
+  a.a_is_ll = g0.a_is_ll;
+  a.ll_chain_index = g0.ll_chain_index;
+  a.ll_state = g0.sig_state;
   a.trace = g0.trace;
   a.debug_skip = g0.debug_skip;
   for (int i = 0; i < count; ++i) {

@@ -168,7 +168,12 @@ static int gemv_impl(const void* a_f16, const int32_t* qweight, const void* scal
     g.M = M;
     if (M > 16 || !xbit::gemv_w4_supported(g))
       return fail(XBIT_EINVAL, "the fused signal needs the W4 fast path (bits 4, groupsize 32/64/128, K%%128=0, N%%32=0) and M <= 16");
-    family_req = XBIT_GEMV_MMA;
+    // The flag-in-data form is also spoken by the persistent kernel (option XBIT_LL_PERSIST=1; tile-aligned CTA ranges:
+    // consecutive calls of a chain overlap, so they must not share workspace slots), but measured behind the cluster kernel
+    // there: 6.02 vs 7.85 TB/s aggregate on 4 GPUs, 6.42 vs 6.49 on 2 (profiles/r02_bench_n4_ll_*.json) -- with one CTA per
+    // SM the next call of a chain cannot spin on its slots while this one computes.  The completion-flag form is raised by
+    // the cluster kernel only.
+    family_req = (sig->ll && M <= 8 && xbit::env_int("XBIT_LL_PERSIST", 0) != 0 && pick_family(g) == XBIT_GEMV_PERSIST) ? XBIT_GEMV_PERSIST : XBIT_GEMV_MMA;
     workspace = nullptr;          // no stream-K here: its tiles are not stored by one CTA each
     workspace_bytes = 0;
     for (int p = 0; p < world && !sig->ll; ++p) {
