@@ -157,12 +157,9 @@ struct W4Lane {
 // One 128-k block (GPB scale groups of UPG 32-k units) of one stage: `st` = stage base, `ablk` = this
 // lane's activations of the block (act_sm + block offset + lane word-row), `asum_blk` = group sums of
 // the block ([GPB][MROWS], mma only).  Accumulates into tot.
-// HYB (mma path, M == 1 only): every second 32-k unit is computed with FHFMA on the FMA pipe
-// instead of HMMA.  Legacy mma.sync issues one m16n8k16 per 8 cycles per SM on B200 (measured,
-// profiles/r01_v3_ncu_gemv_mma_8192x28672.txt), i.e. at most 16 B/clk/SM of packed W4 -- 69 % of the
-// HBM rate -- when 7/8 of every MMA is wasted on batch columns that do not exist at M = 1; splitting
-// the units between the tensor pipe and the FMA pipe lifts that cap.  Same exact products, same
-// fp32 accumulation; the FHFMA partial sums live in tot_s (per lane: 4 columns, this lane's k-rows).
+// SIMT family only (MT == 0); the tensor-core families use w4_consume_block_v2 below.  (HYB is a leftover template
+// parameter of the kernel: the FHFMA / HMMA hybrid it selected was measured in round 1, did not reduce issue slots, and
+// has been removed together with the first tensor-core block math.)
 template <int MT, int UPG, int WC, int HYB>
 __device__ __forceinline__ void w4_consume_block(const unsigned char* __restrict__ st, const __half* __restrict__ ablk,
                                                  const float* __restrict__ asum_blk, const W4Lane<MT>& L,
@@ -186,85 +183,10 @@ __device__ __forceinline__ void w4_consume_block(const unsigned char* __restrict
       const float2 s23 = __half22float2(u2h2(sraw.y));
       sf[0] = s01.x; sf[1] = s01.y; sf[2] = s23.x; sf[3] = s23.y;
     }
-    if constexpr (kMma) {
-      float grp[2 * MT][4];
-      float grp_s[4] = {0.f, 0.f, 0.f, 0.f};
-      // which units of the block go to the FMA pipe: HYB = 2: the odd ones (half), HYB = 1: the last one (a quarter)
-      constexpr bool kHyb = (HYB != 0) && (MT == 1);
-      auto simt_unit = [](int u) constexpr { return kHyb && (HYB == 2 ? (u & 1) == 1 : (u & 3) == 3); };
-      bool group_has_mma = false, group_has_simt = false;
-#pragma unroll
-      for (int uu = 0; uu < UPG; ++uu) {
-        if (simt_unit(q * UPG + uu)) group_has_simt = true; else group_has_mma = true;
-      }
-      bool first_mma = true;
-#pragma unroll
-      for (int uu = 0; uu < UPG; ++uu) {
-        const int u = q * UPG + uu;
-        const uint4 wv = *reinterpret_cast<const uint4*>(st + ((u & 1) ? w_x1 : w_x0) + unit_row(u) * 128);
-        // batch rows >= M read a clamped (valid) row: their accumulators are never stored
-        uint4 bfrag[MT];
-#pragma unroll
-        for (int mt = 0; mt < MT; ++mt)
-          bfrag[mt] = *reinterpret_cast<const uint4*>(ablk + L.brow_off[mt] + unit_row(u) * 8);
-        const uint32_t w4[4] = {wv.x, wv.y, wv.z, wv.w};
-        if (simt_unit(u)) {
-          // M == 1: every lane's bfrag is row 0, i.e. the activations of this lane's word-row
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint32_t e[4];
-            unpack_w4_subnormal(w4[j], e);
-            float c = grp_s[j];
-            c = fhfma_pair(e[0], bfrag[0].x, c);
-            c = fhfma_pair(e[1], bfrag[0].y, c);
-            c = fhfma_pair(e[2], bfrag[0].z, c);
-            c = fhfma_pair(e[3], bfrag[0].w, c);
-            grp_s[j] = c;
-          }
-        } else {
-#pragma unroll
-          for (int tt = 0; tt < 2; ++tt) {
-            uint32_t ea[4], eb[4];
-            unpack_w4_subnormal(w4[2 * tt], ea);
-            unpack_w4_subnormal(w4[2 * tt + 1], eb);
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {
-              if (first_mma) mma_m16n8k16_zero(grp[tt * MT + mt], ea[0], eb[0], ea[1], eb[1], bfrag[mt].x, bfrag[mt].y);
-              else           mma_m16n8k16(grp[tt * MT + mt], ea[0], eb[0], ea[1], eb[1], bfrag[mt].x, bfrag[mt].y);
-              mma_m16n8k16(grp[tt * MT + mt], ea[2], eb[2], ea[3], eb[3], bfrag[mt].z, bfrag[mt].w);
-            }
-          }
-          first_mma = false;
-        }
-      }
-      // grp = 2^-24 * sum_k a_k w_k (exact products, fp32 accumulation).  y += s * (2^24 grp - z * sum_k a_k).
-      // accumulators 0,1 belong to column 2*tt (rows m = 2r, 2r+1), accumulators 2,3 to column 2*tt+1.
-      float s24[4], nsz[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        s24[j] = sf[j] * 16777216.f;
-        nsz[j] = -sf[j] * ((float)((zraw >> (4 * j)) & 0xFu) + zbias);
-      }
-      const float* asum = asum_blk + q * MROWS + 2 * r;
-#pragma unroll
-      for (int mt = 0; mt < MT; ++mt) {
-        const float2 as = *reinterpret_cast<const float2*>(asum + 8 * mt);
-#pragma unroll
-        for (int tt = 0; tt < 2; ++tt)
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int j = 2 * tt + (i >> 1);
-            float acc = tot[tt * MT + mt][i];
-            if (group_has_mma) acc = fmaf(s24[j], grp[tt * MT + mt][i], acc);
-            acc = fmaf(nsz[j], (i & 1) ? as.y : as.x, acc);
-            tot[tt * MT + mt][i] = acc;
-          }
-      }
-      if (group_has_simt) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) tot_s[j] = fmaf(s24[j], grp_s[j], tot_s[j]);
-      }
-    } else {
+    // (the first tensor-core block math -- IMAD.HI + 4 LOP3 per word, zero point in the epilogue, and its FHFMA / HMMA
+    // hybrid -- lived here in round 1; w4_consume_block_v2 replaced it everywhere, so only the SIMT family is left)
+    static_assert(!kMma, "tensor-core families use w4_consume_block_v2");
+    {
       uint32_t zlo[4], zhi[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
