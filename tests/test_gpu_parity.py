@@ -214,7 +214,9 @@ def test_gemv_persistent_schedule(dev, c_oracle, monkeypatch):
     # SMs, every groupsize of the fast path, odd block counts (K = 4224: 33 blocks)
     cases = ((4096, 4096, 1, 128, 1), (11008, 4096, 1, 128, 1), (4096, 11008, 2, 128, 0), (28672, 1024, 1, 128, 1),
              (4224, 4128, 1, 128, 1), (1024, 96, 3, 64, 0), (2048, 2048, 8, 32, 1), (128, 32, 1, 32, 0),
-             (256, 64, 2, 128, 1), (8192, 8192, 4, 64, 0), (384, 4736, 1, 128, 1))
+             (256, 64, 2, 128, 1), (8192, 8192, 4, 64, 0), (384, 4736, 1, 128, 1),
+             # tall N-split shards: a CTA's range is shorter than a tile, so only a window of the activations is staged
+             (8192, 1024, 2, 128, 1), (8192, 1024, 3, 64, 0), (16384, 512, 1, 128, 1))
     for (K, N, M, g, bias) in cases:
         qw, s, qz, a = synth.make_inputs(K, N, 4, g, M=M, seed=K + N + M)
         w = c_oracle.dequant(qw, s, qz, g, 4, K, bias)

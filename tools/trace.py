@@ -14,7 +14,10 @@ from sweep import make, PEAK, WS  # noqa: E402
 dev = torch.device("cuda:0")
 lib = capi.load()
 NAMES = ["cta start", "producer: first TMA issue", "consumers past griddep wait", "activations staged",
-         "first stage landed", "last block consumed", "cluster reduce done", "results stored"]
+         "first stage landed", "last block consumed", "cluster reduce done", "results stored", "", "", "loop entered (before the first wait)"]
+if os.environ.get("TRACE_EXTRA"):      # library built with -DW4P_TRACE_EXTRA: slots 8 / 9 / 11 are stamps inside the tile epilogue
+    NAMES[8:10] = ["  partial tile written", "  slices found (ballot)"]
+    NAMES.append("  handshake done")
 
 
 def run(K, N, fam, pdl=True, calls=48):
@@ -50,6 +53,16 @@ def run(K, N, fam, pdl=True, calls=48):
     us = e0.elapsed_time(e1) * 1e3 / calls
     del os.environ["XBIT_GEMV_TRACE"]
     t = trace.cpu().numpy().astype(np.int64)
+    if t[:, :, 13].max() > 0:
+        # persistent kernel: slots 0..7 are SM clock values; 13 / 14 = %globaltimer at CTA start / at the dump, 15 = the
+        # clock at the dump.  One ns-per-clock rate for the run (median over the CTAs), anchored at each CTA's start.
+        live = (t[:, :, 13] > 0) & (t[:, :, 15] > t[:, :, 0])
+        rate = float(np.median((t[:, :, 14] - t[:, :, 13])[live] / (t[:, :, 15] - t[:, :, 0])[live]))
+        print(f"   (SM clock {1e3 / rate:.0f} MHz from the stamps)")
+        c0 = t[:, :, 0].copy()
+        for k in (0, 1, 2, 3, 4, 5, 6, 7, 10) + ((8, 9, 11) if os.environ.get('TRACE_EXTRA') else ()):
+            has = live & (t[:, :, k] > 0)
+            t[:, :, k] = np.where(has, t[:, :, 13] + ((t[:, :, k] - c0) * rate).astype(np.int64), 0)
     # launch l (0 = the eager call) used slot l % 64; graph launches are 1..calls -> slots (1..calls) % 64
     slots = [(1 + i) % 64 for i in range(calls)][-40:]        # the last 40 graph launches (not overwritten)
     print(f"== {K}x{N} family {fam} pdl={int(pdl)}: {us:.2f} us/call by events ({nbytes/us/1e3/PEAK*100:.0f}% of peak), roofline {nbytes/PEAK/1e3:.2f} us")
@@ -73,7 +86,7 @@ def run(K, N, fam, pdl=True, calls=48):
     per = loop / np.maximum(nt, 1)
     print(f"   clk/stage percentiles 5/25/50/75/95: " + " ".join(f"{np.percentile(per, q):.0f}" for q in (5, 25, 50, 75, 95)))
     print(f"   consumer warp 0: loop {np.median(loop):.0f} clk for {np.median(nt):.0f} stages ({np.median(loop / np.maximum(nt, 1)):.0f} clk/stage), "
-          f"waiting for data {100 * cwait.sum() / loop.sum():.0f}% of it; producer waiting for free slots {np.median(pwait):.0f} clk")
+          f"waiting for data {100 * cwait.sum() / loop.sum():.0f}% of it; (slot 10: {np.median(pwait):.0f})")
     # CTAs per SM within one launch (slot 12 = smid + 1, persistent kernel only)
     if t[slots[10]][:, 12].max() > 0:
         import collections
@@ -99,6 +112,8 @@ def run(K, N, fam, pdl=True, calls=48):
         else:
             print(f"   staged -> consumed: alone on the SM median {np.median(fast)/1e3:.2f} us p95 {np.percentile(fast, 95)/1e3:.2f} (n={len(fast)}); no SM ever holds two CTAs of a launch")
     for k, name in enumerate(NAMES):
+        if not name:
+            continue
         med, mx, mn = [], [], []
         for rel in rows:
             v = rel[:, k]

@@ -53,6 +53,8 @@ _lib = None
 def lib_path() -> Path:
     # XBIT_DEVTOOLS_LIB=1 (tools/*.py only): the -DXBIT_DEVTOOLS build with phase stamps and skip-math knobs
     import os
+    if os.environ.get("XBIT_B200_LIB"):            # tools/*.py only: an experimental build of the same ABI
+        return Path(os.environ["XBIT_B200_LIB"])
     return _build.LIB_DEV if os.environ.get("XBIT_DEVTOOLS_LIB") else _build.LIB
 
 
@@ -62,7 +64,7 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
     if _lib is not None:
         return _lib
     path = lib_path()
-    if build_if_missing:
+    if build_if_missing and path in (_build.LIB, _build.LIB_DEV):
         try:
             _build.build_lib(dev=(path == _build.LIB_DEV))
         except Exception:

@@ -28,6 +28,7 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 #include <string.h>
 
@@ -59,7 +60,10 @@ struct W4PProblem {
   unsigned long long* ws;   // [grid][M][32] {fp32 partial, flag} slots, zero outside a launch
 };
 
-struct W4PArgs {
+// NP = matrices the parameter block has room for: the single-matrix instantiation takes the short form (kernel
+// parameters of 0.5 instead of 1.7 KB)
+template <int NP>
+struct W4PArgsN {
   const __half* a;          // [M, K]
   int world;
   int M, K, zero_bias;
@@ -76,15 +80,23 @@ struct W4PArgs {
   int ll_chain_index;       // position of this call in its chain (0 = first)
   unsigned int* ll_state;   // local: [2] chain base, [3] timeout flag
   int count;                // weight matrices: the CTA works through its range of each, one after the other
-  W4PProblem prob[kPMaxProblems];
-  unsigned long long* trace;
+  // division by multiplication (exact for the ranges involved, see range_lo / tile_of): the integer divisions of the
+  // CTA prologue sat between CTA start and the first TMA request
+  unsigned int g_magic;     // ceil(2^32 / grid):  n / grid = umulhi(n, g_magic)         for n * grid < 2^32
+  unsigned int nb_magic;    // ceil(2^nb_shift / nb): j / nb = (j * nb_magic) >> nb_shift  for j * nb < 2^nb_shift
+  int nb_shift;
   int debug_skip;
+  unsigned long long* trace;
+  W4PProblem prob[NP];      // last: the short form is a prefix of the long one
 };
+using W4PArgs = W4PArgsN<kPMaxProblems>;
 
 // tensor maps of the launch: [problem][0] = box of two blocks, [problem][1] = box of one block
-struct W4PMaps {
-  CUtensorMap m[2 * kPMaxProblems];
+template <int NP>
+struct W4PMapsN {
+  CUtensorMap m[2 * NP];
 };
+using W4PMaps = W4PMapsN<kPMaxProblems>;
 
 template <int UPG, int BPS>
 struct W4PCfg {
@@ -112,15 +124,34 @@ struct W4PLane {
 };
 
 #ifdef XBIT_DEVTOOLS
-__device__ __forceinline__ void p_trace_stamp(const W4PArgs& a, int slot) {
+// Phase stamps of tools/trace.py: SM clock values parked in shared memory and written out once, by thread 0 as it leaves
+// (a %globaltimer read and a global store per stamp cost 0.4 us per call and sat in front of every fence).  Slots 0..7:
+// clock64 at the phase; 13 / 14: %globaltimer at CTA start / at the dump; 15: clock64 at the dump (the host converts).
+__shared__ unsigned long long p_trace_sm[16];
+template <typename Args>
+__device__ __forceinline__ void p_trace_stamp(const Args& a, int slot) {
+  if (a.trace) {
+    p_trace_sm[slot] = (unsigned long long)clock64();
+    if (slot == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      p_trace_sm[13] = t;
+    }
+  }
+}
+template <typename Args>
+__device__ __forceinline__ void p_trace_value(const Args& a, int slot, unsigned long long v) {
+  if (a.trace) p_trace_sm[slot] = v;
+}
+template <typename Args>
+__device__ __forceinline__ void p_trace_dump(const Args& a) {
   if (a.trace) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    a.trace[(size_t)blockIdx.x * 16 + slot] = t;
+    p_trace_sm[14] = t;
+    p_trace_sm[15] = (unsigned long long)clock64();
+    for (int i = 0; i < 16; ++i) a.trace[(size_t)blockIdx.x * 16 + i] = p_trace_sm[i];
   }
-}
-__device__ __forceinline__ void p_trace_value(const W4PArgs& a, int slot, unsigned long long v) {
-  if (a.trace) a.trace[(size_t)blockIdx.x * 16 + slot] = v;
 }
 #define P_TRACE(slot) p_trace_stamp(a, slot)
 #define P_TRACE_VALUE(slot, v) p_trace_value(a, slot, v)
@@ -331,28 +362,31 @@ __device__ __forceinline__ uint4 p_ll_load8(const unsigned long long* slots, uin
 template <int NW>
 __device__ __forceinline__ int p_slice_of(int w) { return (w & 3) * (NW / 4) + (w >> 2); }
 
-// NW consumer warps + one producer warp.  MODE 0: a ring per warp, the two blocks of a step one after the other;
-// MODE 1 (DUAL): a ring per warp, the two blocks together (two accumulator sets); MODE 2 (PAIR): a ring per PAIR of
-// warps, warp 2p takes the first block of every step and warp 2p+1 the second -- 16 consumer warps at 56 registers
-// share the 8 rings (and the shared memory) of the 8-warp forms.  Two CTAs (of consecutive launches) per SM.
-// BPS: blocks per ring slot.  2 = one TMA request per step of two blocks; 1 = one request per block, which keeps more
-// requests in flight per byte of shared memory (a consumer holds ONE 2 KiB slot while it computes, not two blocks'
-// worth): the form for matrices that do not fit the rings whole and keep streaming while the CTA computes.
+// NW consumer warps + one producer warp, a ring per consumer warp.  DUAL: the two blocks of a step are taken together
+// (two accumulator sets; the form every instantiation uses -- one block at a time, 12 warps at a time, 16 warps sharing
+// rings in pairs and 16 warps on half an SM were all measured slower).
+// BPS: blocks per ring slot (2 = one TMA request per step of two blocks).
 // MINB: CTAs per SM the register budget is cut for: 2 = two launches co-resident (the whole share of a CTA fits its
-// rings and is prefetched while the previous launch computes), 1 = one CTA per SM with 16 consumer warps and deeper rings
+// rings and is prefetched while the previous launch computes), 1 = one CTA per SM with deeper rings or 16 consumer warps
 // (larger matrices, which keep streaming while they compute: what counts there is the compute rate and bytes in flight).
-template <int UPG, int NW, int MODE, bool I8, int BPS, int MINB>
+// GEN: what the instantiation covers.  0 = one weight matrix, plain loads and stores (the form every single call takes:
+// the loops over matrices fold away and the activation loads of the staging phase are issued back to back; measured
+// 3.37 against 3.96 us on 4096 x 4096 and 6.97 against 8.25 us on 11008 x 4096 for the general form, profiles/r02_ab.log);
+// 1 = several matrices (xbit_gemv_f16_multi); 2 = also the flag-in-data (LL) input / output forms.
+template <int UPG, int NW, int MODE, bool I8, int BPS, int MINB, int GEN>
 __global__ void __launch_bounds__((NW + 1) * 32, MINB)
-gemv_w4p_kernel(const __grid_constant__ W4PMaps maps, const __grid_constant__ W4PArgs a) {
+gemv_w4p_kernel(const __grid_constant__ W4PMapsN<(GEN ? kPMaxProblems : 1)> maps, const __grid_constant__ W4PArgsN<(GEN ? kPMaxProblems : 1)> a) {
   using Cfg = W4PCfg<UPG, BPS>;
+  const int count = GEN >= 1 ? a.count : 1;
+  const bool ll_out = GEN == 2 && a.ll_out, a_is_ll = GEN == 2 && a.a_is_ll;
   constexpr int GPB = Cfg::GPB;
-  constexpr bool DUAL = MODE == 1, PAIR = MODE == 2;
-  static_assert(!PAIR || BPS == 2, "a pair of warps shares the two blocks of a slot");
+  constexpr bool DUAL = MODE == 1;
+  static_assert(MODE == 0 || MODE == 1, "MODE: 0 = one block at a time, 1 = two blocks together");
   static_assert(!I8 || UPG == 4, "the integer block math covers groupsize 128");
-  constexpr int kPWarps = PAIR ? NW / 2 : NW;       // rings = slices of the CTA's range
+  constexpr int kPWarps = NW;                       // rings = slices of the CTA's range
   constexpr int kPConsumerThreads = NW * 32;
   constexpr int LPR = kPWarps <= 8 ? 4 : 2;         // producer lanes per ring
-  auto slice_of_ring = [](int rg) { return PAIR ? (rg & 1) * (kPWarps / 2) + (rg >> 1) : p_slice_of<kPWarps>(rg); };
+  auto slice_of_ring = [](int rg) { return p_slice_of<kPWarps>(rg); };
   extern __shared__ __align__(1024) unsigned char smem_raw[];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -369,10 +403,10 @@ gemv_w4p_kernel(const __grid_constant__ W4PMaps maps, const __grid_constant__ W4
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(zring + kPWarps * R * Cfg::kZSlot);     // [8][kPMaxRing]
   uint64_t* empty_bar = full_bar + kPWarps * kPMaxRing;
   int* cnt_sm = reinterpret_cast<int*>(empty_bar + kPWarps * kPMaxRing);              // [problems][16] arrival counters of shared tiles
-  int* bnd_sm = cnt_sm + kPMaxProblems * 16;                                          // [problems][32] first block of every slice
-  float* part_sm = reinterpret_cast<float*>(bnd_sm + kPMaxProblems * 32);             // [problems][slices]([2 warps])[2]([2])[M][32] partial tiles
-  const int part_stride = kPWarps * (PAIR ? 8 : 2) * a.M * 32;                        // floats per problem
-  uint32_t* zt_sm = reinterpret_cast<uint32_t*>(part_sm + a.count * part_stride);    // [groups][M][4]: (hi, lo) of sum_k a_k / 64, 3 zero words
+  int* bnd_sm = cnt_sm + kPMaxProblems * 16;                                        // [problems][32] first block of every slice
+  float* part_sm = reinterpret_cast<float*>(bnd_sm + kPMaxProblems * 32);           // [problems][slices]([2 warps])[2]([2])[M][32] partial tiles
+  const int part_stride = kPWarps * 2 * a.M * 32;                        // floats per problem
+  uint32_t* zt_sm = reinterpret_cast<uint32_t*>(part_sm + count * part_stride);    // [groups][M][4]: (hi, lo) of sum_k a_k / 64, 3 zero words
   __half* act_sm = reinterpret_cast<__half*>(zt_sm + (size_t)nb * GPB * a.M * 4);     // [M][pitch]
   // integer block math instead: group table {2^(E-22) row 0, row 1, sum_k a_k row 0, row 1}, the ones / zero constants,
   // and three digit planes per activation row ([K/8 word-rows][even k x4, odd k x4] bytes each; plane p starts
@@ -384,10 +418,16 @@ gemv_w4p_kernel(const __grid_constant__ W4PMaps maps, const __grid_constant__ W4
 
   // this CTA's range of a matrix' tile-major block list: units [U*c/G, U*(c+1)/G) with U = uq*G + ur (no 64-bit division
   // here: the time from CTA start to the first TMA request is on the critical path whenever the CTA could not start early)
-  auto range_lo = [&](const W4PProblem& P, int cc) { return (P.uq * cc + (P.ur * cc) / G) * P.unit; };
+  auto range_lo = [&](const W4PProblem& P, int cc) { return (P.uq * cc + (int)__umulhi((unsigned)(P.ur * cc), a.g_magic)) * P.unit; };
+  auto tile_of = [&](int jj) { return (int)(((unsigned long long)(unsigned)jj * a.nb_magic) >> a.nb_shift); };
+  // (the first matrix' range: worked out by every thread while the barriers are being initialised)
+  const int lo0 = range_lo(a.prob[0], c), hi0 = range_lo(a.prob[0], c + 1);
 
   if (tid < kPWarps * kPMaxRing) {
     if (tid == 0) {
+#ifdef XBIT_DEVTOOLS
+      for (int i = 0; i < 16; ++i) p_trace_sm[i] = 0;
+#endif
       P_TRACE(0);
 #ifdef XBIT_DEVTOOLS
       unsigned int smid;
@@ -397,24 +437,40 @@ gemv_w4p_kernel(const __grid_constant__ W4PMaps maps, const __grid_constant__ W4
     }
     if ((tid & (kPMaxRing - 1)) < R) {
       mbar_init(&full_bar[tid], 1 + LPR);           // the TMA issuer's expect_tx arrival + LPR cp.async arrivals
-      mbar_init(&empty_bar[tid], PAIR ? 2 : 1);
+      mbar_init(&empty_bar[tid], 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
   }
-  if (tid < kPMaxProblems * 32) {
+  if constexpr (GEN == 0) {
+    if (tid < 32) {
+      if (tid < 16) cnt_sm[tid] = 0;
+      if (tid <= kPWarps) bnd_sm[tid] = lo0 + (int)(((long long)(hi0 - lo0) * tid) / kPWarps);
+    }
+  } else if (tid < kPMaxProblems * 32) {
     const int pi = tid >> 5, i = tid & 31;
     if (i < 16) cnt_sm[pi * 16 + i] = 0;
-    if (pi < a.count && i <= kPWarps) {
-      const int plo = range_lo(a.prob[pi], c), plen = range_lo(a.prob[pi], c + 1) - plo;
+    if (pi < count && i <= kPWarps) {
+      const int plo = pi == 0 ? lo0 : range_lo(a.prob[pi], c), plen = (pi == 0 ? hi0 : range_lo(a.prob[pi], c + 1)) - plo;
       bnd_sm[pi * 32 + i] = plo + (int)(((long long)plen * i) / kPWarps);
     }
+  }
+  // the producer lanes' slices of the first matrix, worked out before anything else, while the barriers are initialised:
+  // the time from CTA start to the first TMA request is on the critical path whenever the CTA could not start early
+  // (7.00 against 7.19 us on 11008 x 4096 with these divisions behind the barrier, profiles/r02_ab.log)
+  int j0 = 0, jend0 = 0, tile0 = 0, kb0 = 0;
+  if (warp == NW && lane < kPWarps * LPR) {
+    const int rho = slice_of_ring(lane / LPR);
+    j0 = lo0 + (int)((long long)(hi0 - lo0) * rho / kPWarps);
+    jend0 = lo0 + (int)((long long)(hi0 - lo0) * (rho + 1) / kPWarps);
+    tile0 = tile_of(j0);
+    kb0 = j0 - tile0 * nb;
   }
   __syncthreads();
   // the next kernel in the stream may become resident now: its producer streams ITS weights while this one runs.
   // Exception: the FIRST call of an LL chain releases its dependents only after its own griddepcontrol.wait has returned
   // (the calls behind it do not wait for the grid before them and read the chain base that the previous chain's unpack
   // advances; see gemv_w4_kernel)
-  const bool defer_dependents = a.ll_out && !a.a_is_ll;
+  const bool defer_dependents = ll_out && !a_is_ll;
   if (!defer_dependents) griddep_launch_dependents();
 
   if (warp == NW) {
@@ -431,15 +487,19 @@ gemv_w4p_kernel(const __grid_constant__ W4PMaps maps, const __grid_constant__ W4
       const int w = lane / LPR, sub = lane % LPR, rho = slice_of_ring(w);
       uint64_t policy = 0;
       if (sub == 0) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-      if (lane < 2 * a.count) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.m[lane]) : "memory");
+      if (lane < 2 * count) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.m[lane]) : "memory");
       if (lane == 0) P_TRACE(1);
       int s = 0, ph = 0, n = 0;
-      for (int pi = 0; pi < a.count; ++pi) {
+      for (int pi = 0; pi < count; ++pi) {
         const W4PProblem& P = a.prob[pi];
-        const int lo = range_lo(P, c), len = range_lo(P, c + 1) - lo;
-        int j = lo + (int)((long long)len * rho / kPWarps);
-        const int jend = lo + (int)((long long)len * (rho + 1) / kPWarps);
-        int tile = j / nb, kb = j - tile * nb;
+        int j = j0, jend = jend0, tile = tile0, kb = kb0;
+        if (pi > 0) {
+          const int lo = range_lo(P, c), len = range_lo(P, c + 1) - lo;
+          j = lo + (int)((long long)len * rho / kPWarps);
+          jend = lo + (int)((long long)len * (rho + 1) / kPWarps);
+          tile = tile_of(j);
+          kb = j - tile * nb;
+        }
         const unsigned char* sbase = reinterpret_cast<const unsigned char*>(P.scales) + sub * 16;
         const unsigned char* zbase = reinterpret_cast<const unsigned char*>(P.qzeros);
         for (; j < jend; ++n) {
@@ -508,25 +568,42 @@ gemv_w4p_kernel(const __grid_constant__ W4PMaps maps, const __grid_constant__ W4
     LI.zbias = (float)a.zero_bias;
   }
 
-  const int rg = PAIR ? warp >> 1 : warp, hh = PAIR ? warp & 1 : 0;   // ring, and which block of a step this warp takes
+  const int rg = warp;                              // ring
   const int rho = slice_of_ring(rg);
   int s = 0, ph = 0;
+  // this warp's slice of the CTA's range of a matrix: the first matrix' is worked out here, BEFORE the wait (integer
+  // divisions: 0.2 us when they sat between the activation staging and the first block)
+  int lo, hi, j, jend, tile, kb;
+  auto slice_range = [&](const W4PProblem& P, bool first) {
+    lo = first ? lo0 : range_lo(P, c);
+    hi = first ? hi0 : range_lo(P, c + 1);
+    const int len = hi - lo;
+    j = lo + (int)((long long)len * rho / kPWarps);
+    jend = lo + (int)((long long)len * (rho + 1) / kPWarps);
+    tile = tile_of(j);
+    kb = j - tile * nb;
+  };
+  slice_range(a.prob[0], true);
   uint64_t* const my_full = full_bar + rg * kPMaxRing;
   uint64_t* const my_empty = empty_bar + rg * kPMaxRing;
   const unsigned char* const my_w = wring + rg * R * Cfg::kWSlot;
   const unsigned char* const my_s = sring + rg * R * Cfg::kSSlot;
   const unsigned char* const my_z = zring + rg * R * Cfg::kZSlot;
   const unsigned char* const zt_bytes = reinterpret_cast<const unsigned char*>(zt_sm);
+  // (Measured: forcing all of the above to be computed HERE, ahead of the wait -- the compiler sinks most of it behind the
+  // wait and the staging barrier, 60 + 70 instructions -- gains 0.02 us where the CTA starts early (half SM) and LOSES
+  // 0.2 us where it starts late (full SM): there the consumer warps' set-up competes with the producer warp for issue
+  // slots on its way to the first TMA request.  Left to the compiler; profiles/r02_ab.log.)
   // The activations are the only data produced by the previous kernel.  ONE warp waits for it; the others block on a
   // hardware barrier behind that warp: warps parked in griddepcontrol.wait were measured to slow the co-resident CTA of
   // the previous launch down (XBIT_W4P_ALLWAIT=1 restores the plain form for the comparison).
   // (a call fed from an LL buffer carries its dependency in the data: every slot is validated by its own call number)
-  if (!a.a_is_ll) {
+  if (!a_is_ll) {
     if (a.all_wait || warp == 0) griddep_wait();
     if (!a.all_wait) asm volatile("bar.sync 1, %0;" ::"n"(kPConsumerThreads) : "memory");
   }
   if (defer_dependents) griddep_launch_dependents();
-  const uint32_t ll_in_epoch = a.a_is_ll ? a.ll_state[2] + (uint32_t)a.ll_chain_index : 0u;     // the previous call's number
+  const uint32_t ll_in_epoch = a_is_ll ? a.ll_state[2] + (uint32_t)a.ll_chain_index : 0u;     // the previous call's number
   if (tid == 0) P_TRACE(2);
   if constexpr (I8) {
     // stage the activations once per CTA as three unsigned byte planes of 24-bit fixed point relative to the largest |a|
@@ -546,7 +623,7 @@ gemv_w4p_kernel(const __grid_constant__ W4PMaps maps, const __grid_constant__ W4
         for (int b = 0; b < kBatch; ++b) {
           const int v = v0 + b * kPConsumerThreads + lane;
           val[b] = make_uint4(0, 0, 0, 0);
-          if (v < vecs) val[b] = a.a_is_ll ? p_ll_load8(reinterpret_cast<const unsigned long long*>(a.a) + (((size_t)m * a.K) >> 1) + 4 * (size_t)v, ll_in_epoch, a.ll_state + 3)
+          if (v < vecs) val[b] = a_is_ll ? p_ll_load8(reinterpret_cast<const unsigned long long*>(a.a) + (((size_t)m * a.K) >> 1) + 4 * (size_t)v, ll_in_epoch, a.ll_state + 3)
                                            : __ldcg(arow + v);
         }
 #pragma unroll
@@ -630,7 +707,7 @@ gemv_w4p_kernel(const __grid_constant__ W4PMaps maps, const __grid_constant__ W4
         for (int b = 0; b < kBatch; ++b) {
           const int v = v0 + b * kPConsumerThreads + lane;
           val[b] = make_uint4(0, 0, 0, 0);
-          if (v < vecs) val[b] = a.a_is_ll ? p_ll_load8(reinterpret_cast<const unsigned long long*>(a.a) + (((size_t)m * a.K) >> 1) + 4 * (size_t)v, ll_in_epoch, a.ll_state + 3)
+          if (v < vecs) val[b] = a_is_ll ? p_ll_load8(reinterpret_cast<const unsigned long long*>(a.a) + (((size_t)m * a.K) >> 1) + 4 * (size_t)v, ll_in_epoch, a.ll_state + 3)
                                            : __ldcg(arow + v);  // L2 only: may just have been written by the previous kernel or a peer GPU
         }
 #pragma unroll
@@ -666,14 +743,10 @@ gemv_w4p_kernel(const __grid_constant__ W4PMaps maps, const __grid_constant__ W4
   bool first_wait = true;
 #endif
 
-  for (int pi = 0; pi < a.count; ++pi) {
+  for (int pi = 0; pi < count; ++pi) {
   const W4PProblem& P = a.prob[pi];
-  const int lo = range_lo(P, c), hi = range_lo(P, c + 1), len = hi - lo;
-  const long long U = (long long)P.uq * G + P.ur;
+  if (pi > 0) slice_range(P, false);
   int* const bnd = bnd_sm + pi * 32;
-  int j = lo + (int)((long long)len * rho / kPWarps);
-  const int jend = lo + (int)((long long)len * (rho + 1) / kPWarps);
-  int tile = j / nb, kb = j - tile * nb;
   while (j < jend) {
     const int cnt = min(jend - j, nb - kb);         // this warp's blocks of `tile`: [kb, kb + cnt)
     float tot[2][4];
@@ -691,6 +764,7 @@ gemv_w4p_kernel(const __grid_constant__ W4PMaps maps, const __grid_constant__ W4
       if (two_slots) { if (++s == R) { s = 0; ph ^= 1; } }
 #ifdef XBIT_DEVTOOLS
       const long long w0c = a.trace ? clock64() : 0;
+      if (first_wait && tid == 0) P_TRACE(10);
 #endif
       mbar_wait(&my_full[s0], ph0);
       if (two_slots) mbar_wait(&my_full[s1], ph1);
@@ -711,16 +785,7 @@ gemv_w4p_kernel(const __grid_constant__ W4PMaps maps, const __grid_constant__ W4
         const unsigned char* const zt0 = zt_bytes + (size_t)(kb + i) * GPB * zt_group_bytes;
         if constexpr (I8) {
           const float* const g0 = gt_sm + (size_t)(kb + i) * 4;
-          if (PAIR) {
-            if (i + hh < cnt) {
-              const unsigned char* const wp[1] = {w0 + hh * Cfg::kBlockBytes};
-              const unsigned char* const sp[1] = {sc0 + hh * 64};
-              const unsigned char* const zp[1] = {z0 + hh * 16};
-              const int wr[1] = {(kb + i + hh) * 16};
-              const float* const gp[1] = {g0 + hh * 4};
-              w4p_consume_i8<1>(wp, sp, zp, wr, gp, LI, toti, zci);
-            }
-          } else if (DUAL && i + 2 <= cnt) {
+          if (DUAL && i + 2 <= cnt) {
             const unsigned char* const wp[2] = {w0, w1};
             const unsigned char* const sp[2] = {sc0, sc1};
             const unsigned char* const zp[2] = {z0, z1};
@@ -742,15 +807,6 @@ gemv_w4p_kernel(const __grid_constant__ W4PMaps maps, const __grid_constant__ W4
               const float* const gp1[1] = {g0 + 4};
               w4p_consume_i8<1>(wp1, sp1, zp1, wr1, gp1, LI, toti, zci);
             }
-          }
-        } else if (PAIR) {
-          if (i + hh < cnt) {
-            const unsigned char* const wp[1] = {w0 + hh * Cfg::kBlockBytes};
-            const unsigned char* const sp[1] = {sc0 + hh * GPB * 64};
-            const unsigned char* const zp[1] = {z0 + hh * GPB * 16};
-            const __half* const ap[1] = {a0 + hh * 128};
-            const unsigned char* const ztp[1] = {zt0 + hh * GPB * zt_group_bytes};
-            w4p_consume<UPG, 1>(wp, sp, zp, ap, ztp, zt_group_bytes, L, tot);
           }
         } else if (DUAL && i + 2 <= cnt) {
           const unsigned char* const wp[2] = {w0, w1};
@@ -789,16 +845,13 @@ gemv_w4p_kernel(const __grid_constant__ W4PMaps maps, const __grid_constant__ W4
     const int t0 = tile * nb;
     const int p0 = max(lo, t0), p1 = min(hi, t0 + nb);              // the CTA's portion of the tile
     const bool is_first = (j == p0);                                // this piece starts the portion
-    const bool contributes = !PAIR || hh < cnt;                     // the second warp of a pair has nothing in a one-block piece
-    const int par = PAIR ? (tile & 1) : 0;                          // pair partners are at most one piece apart
-    auto part_of = [&](int sl, int h, int first) {
-      return part_sm + (size_t)pi * part_stride + (size_t)((PAIR ? ((sl * 2 + h) * 2 + first) * 2 + par : sl * 2 + first) * a.M) * 32;
-    };
-    if (contributes) {
-      float* mine = part_of(rho, hh, is_first ? 1 : 0);
+    auto part_of = [&](int sl, int first) { return part_sm + (size_t)pi * part_stride + (size_t)((sl * 2 + first) * a.M) * 32; };
+    {
+      float* mine = part_of(rho, is_first ? 1 : 0);
       if constexpr (I8) {
-        // lanes (t, t ^ 1) hold (D0 + 256 D1) and 65536 (D2 - 64 S) of activation row t / 2: the even one stores the sum;
-        // then every lane takes the zero-point term of ITS column 4g + t off both rows
+        // lanes (t, t ^ 1) hold (D0 + 256 D1) and 65536 (D2 - 64 S) of activation row t / 2: the even one stores the sum,
+        // less the zero-point term of that column and row, which lane (g, 2 tt + h) holds (no read-modify-write of the
+        // partial tile in shared memory: this runs once per piece, on the critical path of every call)
         const int row = r >> 1;
 #pragma unroll
         for (int tt = 0; tt < 2; ++tt)
@@ -806,12 +859,11 @@ gemv_w4p_kernel(const __grid_constant__ W4PMaps maps, const __grid_constant__ W4
           for (int h = 0; h < 2; ++h) {
             const float v = (r & 1) ? toti[tt][h] * 65536.f : toti[tt][h];
             const float y = v + __shfl_xor_sync(0xffffffffu, v, 1);
-            if ((r & 1) == 0 && row < a.M) mine[row * 32 + 4 * c8 + 2 * tt + h] = y;
+            const int src = (lane & ~3) | (2 * tt + h);
+            const float z0 = __shfl_sync(0xffffffffu, zci[0], src);
+            const float z1 = a.M > 1 ? __shfl_sync(0xffffffffu, zci[1], src) : 0.f;
+            if ((r & 1) == 0 && row < a.M) mine[row * 32 + 4 * c8 + 2 * tt + h] = y - (row ? z1 : z0);
           }
-        __syncwarp();
-#pragma unroll
-        for (int m = 0; m < 2; ++m)
-          if (m < a.M) mine[m * 32 + 4 * c8 + r] -= zci[m];
       } else {
 #pragma unroll
         for (int tt = 0; tt < 2; ++tt)
@@ -823,47 +875,47 @@ gemv_w4p_kernel(const __grid_constant__ W4PMaps maps, const __grid_constant__ W4
           }
       }
     }
-    if (PAIR) asm volatile("bar.sync %0, 64;" ::"r"(2 + rg) : "memory");   // both warps of the pair have written their parts
-    else __syncwarp();
-    // slices of the CTA that hold blocks of the portion (a slice can be empty when the CTA has fewer blocks than slices:
-    // the LAST slice that begins at or before a block holds it)
-    int sl_first = 0, sl_last = 0;
-#pragma unroll
-    for (int sl = 1; sl < kPWarps; ++sl) {
-      const int b = bnd[sl];
-      if (b <= p0) sl_first = sl;
-      if (b < p1) sl_last = sl;
-    }
-    // blocks of the portion held by slice sl (<= 0: none)
-    auto slice_cnt = [&](int sl) { return min(bnd[sl + 1], p1) - max(bnd[sl], p0); };
-    bool finalize = contributes && hh == 0;
-    if (finalize && sl_last > sl_first) {
-      int expected = 0;
-      for (int sl = sl_first; sl <= sl_last; ++sl) expected += slice_cnt(sl) > 0 ? 1 : 0;
-      int old = 0;
-      if (lane == 0) {
-        __threadfence_block();
-        old = atomicAdd(&cnt_sm[pi * 16 + sl_first], 1);
-      }
+    __syncwarp();
+#ifdef W4P_TRACE_EXTRA
+    if (tid == 0) P_TRACE(8);
+#endif
+    // slices of the CTA that hold blocks of the portion (a slice can be empty when the CTA has fewer blocks than slices):
+    // lane l looks at slice l -- one round of shared-memory loads and a ballot instead of loops over the slices
+    const int b_lo = bnd[min(lane, kPWarps)], b_hi = bnd[min(lane + 1, kPWarps)];
+    const unsigned int held = __ballot_sync(0xffffffffu, lane < kPWarps && min(b_hi, p1) > max(b_lo, p0));
+    const int sl_first = __ffs((int)held) - 1;
+#ifdef W4P_TRACE_EXTRA
+    if (tid == 0) P_TRACE(9);
+#endif
+    bool finalize = true;
+    if (held & (held - 1u)) {                                       // more than one slice: the last to arrive finalizes
+      // (one acquire-release atomic at CTA scope instead of fence.sc + atomic + fence.sc: the __syncwarp before it orders
+      // this warp's partial tile ahead of lane 0's release, the one after it orders the other lanes' loads behind its acquire)
+      uint32_t old = 0;
+      if (lane == 0)
+        asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(&cnt_sm[pi * 16 + sl_first])) : "memory");
       old = __shfl_sync(0xffffffffu, old, 0);
-      finalize = (old == expected - 1);
-      __threadfence_block();
+      __syncwarp();
+      finalize = ((int)old == __popc(held) - 1);
     }
+#ifdef W4P_TRACE_EXTRA
+    if (tid == 0) P_TRACE(11);
+#endif
     if (finalize) {
       const bool starts_tile = (p0 == t0), ends_tile = (p1 == t0 + nb);
       const int n = tile * 32 + lane;                               // this lane's output column
       for (int m = 0; m < a.M; ++m) {
+        // the slices' partial tiles in slice order; all loads issued together (slices outside the portion add 0)
         float v = 0.f;
-        for (int sl = sl_first; sl <= sl_last; ++sl) {
-          const int n = slice_cnt(sl);
-          if (n > 0) v += part_of(sl, 0, sl == sl_first ? 1 : 0)[m * 32 + lane];
-          if (PAIR && n >= 2) v += part_of(sl, 1, sl == sl_first ? 1 : 0)[m * 32 + lane];
+#pragma unroll
+        for (int sl = 0; sl < kPWarps; ++sl) {
+          float x = 0.f;
+          if ((held >> sl) & 1u) x = part_of(sl, sl == sl_first ? 1 : 0)[m * 32 + lane];
+          v += x;
         }
         if (starts_tile && !ends_tile) {
           // finisher: the CTAs after this one that hold the tile's later blocks published their parts (normally long ago)
-          const long long ux = (long long)(t0 + nb - 1) / P.unit;
-          const int c_last = (int)(((ux + 1) * G + U - 1) / U) - 1;
-          for (int cc = c + 1; cc <= c_last; ++cc) {
+          for (int cc = c + 1; cc < G && range_lo(P, cc) < t0 + nb; ++cc) {
             unsigned long long* slot = P.ws + ((size_t)cc * a.M + m) * 32 + lane;
             uint32_t bits, flag;
             const long long c0 = clock64();
@@ -879,8 +931,8 @@ gemv_w4p_kernel(const __grid_constant__ W4PMaps maps, const __grid_constant__ W4
         if (starts_tile) {
           const __half h = __float2half_rn(v);
           const size_t off = (size_t)m * P.ldo + P.col_offset + n;
-          if (a.ll_out) {
-            // flag-in-data all-gather: each PAIR of results goes to every rank as one {half2, call number} store
+          if (ll_out) {
+            // flag-in-data all-gather: each pair of results goes to every rank as one {half2, call number} store
             const uint32_t lo16 = (uint32_t)__half_as_ushort(h);
             const uint32_t hi16 = __shfl_down_sync(0xffffffffu, lo16, 1);
             if ((lane & 1) == 0) {
@@ -905,10 +957,13 @@ gemv_w4p_kernel(const __grid_constant__ W4PMaps maps, const __grid_constant__ W4
   }
 #ifdef XBIT_DEVTOOLS
   if (tid == 0 && a.trace) {
+#ifndef W4P_TRACE_EXTRA
     P_TRACE_VALUE(8, (unsigned long long)(clock64() - loop0));
     P_TRACE_VALUE(9, (unsigned long long)wait_clk);
     P_TRACE_VALUE(11, (unsigned long long)((range_lo(a.prob[0], c + 1) - range_lo(a.prob[0], c)) / kPWarps));
+#endif
     P_TRACE(7);
+    p_trace_dump(a);
   }
 #endif
 }
@@ -918,19 +973,19 @@ gemv_w4p_kernel(const __grid_constant__ W4PMaps maps, const __grid_constant__ W4
 static int p_upg_of(int groupsize) { return groupsize == 32 ? 1 : (groupsize == 64 ? 2 : 4); }
 
 struct W4PPlan {
-  int grid, unit, ring, nw, mode, i8, bps, minb;
+  int grid, unit, ring, nw, i8, minb;
   bool preferred;
   size_t smem;
 };
 
-static size_t w4p_smem_bytes(int upg, int nr, int m, int k, int ring, bool i8, int bps, bool pair, int count = 1) {
+static size_t w4p_smem_bytes(int upg, int nr, int m, int k, int ring, bool i8, int bps, int count = 1) {
   const int gpb = 4 / upg;
   const size_t acts = i8 ? (size_t)(k / 128) * 16 + 16 + (size_t)3 * m * (k + 128) + 128      // group table, constants, digit planes
                          : (size_t)(k / 128) * gpb * m * 16 + (size_t)m * (k + 8) * sizeof(__half);   // zt_sm, act_sm
   return 1024                                                        // alignment slack
          + (size_t)nr * ring * bps * (2048 + 80 * gpb)                // rings of bps-block slots
          + (size_t)2 * nr * kPMaxRing * 8 + kPMaxProblems * 48 * 4   // mbarriers, counters, slice boundaries
-         + (size_t)count * nr * (pair ? 8 : 2) * m * 32 * sizeof(float)   // part_sm
+         + (size_t)count * nr * 2 * m * 32 * sizeof(float)            // part_sm
          + acts;
 }
 
@@ -944,26 +999,23 @@ static bool plan_w4p_nw(const GemvArgs& a, bool have_ws, W4PPlan& p, bool allow1
   const int upg = p_upg_of(a.groupsize);
   const long long tiles = a.N / 32, nb = a.K / 128;
   if (tiles * nb > 0x3fffffffLL) return false;
-  // Two shapes of CTA, both 8 consumer warps that take two blocks per step (measured on the Llama shapes,
-  // profiles/r02_ptime_*; 12 warps with a ring each and 16 warps in pairs were slower everywhere):
-  //   half SM:  rings of 2..3 two-block slots, two launches co-resident: a matrix whose per-CTA share fits the rings is
-  //             prefetched whole while the previous call computes (4096 x 4096: 3.4 us against 4.3 us for the cluster
-  //             kernel);
-  //   full SM:  rings of 4 slots, one CTA per SM and the register budget of one: larger matrices keep streaming while
-  //             they compute, and what counts is the compute rate and the bytes in flight (8192 x 28672: 23.4 against
-  //             26.0 us).
-  // XBIT_W4P_WARPS = 8 / 12 / 16 and XBIT_W4P_RING override (tools/ptime.py).
+  // Two shapes of CTA, consumer warps with a ring each that take two blocks per step (measured on the Llama shapes,
+  // profiles/r02_ptime_*; one block at a time, 12 warps, 16 warps sharing rings in pairs and 16 warps on half an SM
+  // were slower everywhere they were tried):
+  //   half SM:  8 warps, rings of 2..3 two-block slots, two launches co-resident: a matrix whose per-CTA share fits the
+  //             rings is prefetched whole while the previous call computes (4096 x 4096: 3.4 us against 4.3 us for the
+  //             cluster kernel);
+  //   full SM:  rings of 4 slots (16 warps: 2), one CTA per SM and the register budget of one: larger matrices keep
+  //             streaming while they compute, and what counts is the compute rate and the bytes in flight
+  //             (8192 x 28672: 22.3 against 26.0 us).
   const long long total_blocks = tiles * nb;
   const long long share = (total_blocks + sms - 1) / sms;           // blocks per CTA
   // (a launch of several matrices, xbit_gemv_f16_multi: the CTA streams the shares of all of them, share_all)
   const bool small = (share_all > 0 ? share_all : share) <= 8 * 2 * 3;   // fits 8 rings of 3 two-block slots
-  // (XBIT_W4P_WARPS: 8 / 32 = 8 / 16 warps with a ring each and two blocks per step; 12 = a ring each, one block at a
-  // time; 16 = pairs of warps sharing a ring -- the last two only for tools/ptime.py comparisons)
   const bool large = share >= 100 && a.K <= 8192;                   // 16 warps pay off from about 35 MB (8192 x 8192: 8.6 vs 8.7 us, 8192 x 28672: 22.3 vs 23.0)
-  const int env_nw = env_int("XBIT_W4P_WARPS", 0);
-  p.nw = (env_nw == 16 || env_nw == 32) ? 16 : (env_nw == 12 ? 12 : (env_nw == 8 ? 8 : (large && allow16 ? 16 : 8)));
-  p.mode = (p.nw == 8 || env_nw == 32 || env_nw == 0) ? 1 : (p.nw == 12 ? 0 : 2);
-  const int nr = p.mode == 2 ? p.nw / 2 : p.nw;     // rings
+  const int env_nw = env_int("XBIT_W4P_WARPS", 0);                  // 8 / 16: override (tools/ptime.py)
+  p.nw = env_nw == 16 ? 16 : (env_nw == 8 ? 8 : (large && allow16 ? 16 : 8));
+  const int nr = p.nw;                               // rings
   // integer block math: groupsize 128, M <= 2 (XBIT_W4P_I8=0: the fp16 exact-product math everywhere)
   const bool i8 = a.groupsize == 128 && a.M <= 2 && env_int("XBIT_W4P_I8", 1) != 0;
   p.i8 = i8 ? 1 : 0;
@@ -985,29 +1037,21 @@ static bool plan_w4p_nw(const GemvArgs& a, bool have_ws, W4PPlan& p, bool allow1
   p.grid = (int)(fine ? g_fine : sms);
   const int env_grid = env_int("XBIT_W4P_GRID", 0);
   if (env_grid > 0 && (env_grid <= total || !fine)) p.grid = env_grid;
-  // Rings: at most half an SM, so that the next call's CTA is co-resident.  If a warp's whole share fits its ring, slots
-  // of two blocks (one TMA request per step); otherwise slots of one block, as many as fit: the warp then holds one
-  // 2 KiB slot while it computes and everything else can be in flight.  A large M * K that leaves no room for that takes
-  // one CTA per SM with whatever fits.
-  const long long per_cta = fine ? (total + p.grid - 1) / p.grid : (tiles + p.grid - 1) / p.grid * nb;
-  const long long per_ring = (per_cta + nr - 1) / nr + 1;
+  // Rings: a share that fits 8 rings of 2..3 slots gets them on half an SM (the next call's CTA is co-resident);
+  // everything else one CTA per SM with the deepest rings that fit (XBIT_W4P_RING overrides, tools/ptime.py)
   const size_t half = 113 * 1024;
-  const bool pair = p.mode == 2;
-  int bps = 2, ring = 0;
-  (void)per_ring;
-  if (small)
+  int ring = 0;
+  if (small && nr == 8)
     for (int r = 3; r >= 2 && !ring; --r)
-      if (w4p_smem_bytes(upg, nr, a.M, a.K, r, i8, 2, pair, count) <= half) ring = r;
+      if (w4p_smem_bytes(upg, nr, a.M, a.K, r, i8, 2, count) <= half) ring = r;
   for (int r = (nr == 16 ? 2 : 4); r >= 2 && !ring; --r)      // (16 rings: 3 slots measured no better than 2)
-    if (w4p_smem_bytes(upg, nr, a.M, a.K, r, i8, 2, pair, count) <= kMaxDynSmem) ring = r;
+    if (w4p_smem_bytes(upg, nr, a.M, a.K, r, i8, 2, count) <= kMaxDynSmem) ring = r;
   if (!ring) return false;
-  const int env_bps = env_int("XBIT_W4P_BPS", 0), env_ring = env_int("XBIT_W4P_RING", 0);
-  if ((env_bps == 1 && !pair) || env_bps == 2) bps = env_bps;
+  const int env_ring = env_int("XBIT_W4P_RING", 0);
   if (env_ring >= 2 && env_ring <= kPMaxRing) ring = env_ring;
-  if (w4p_smem_bytes(upg, nr, a.M, a.K, ring, i8, bps, pair, count) > kMaxDynSmem) return false;
+  if (w4p_smem_bytes(upg, nr, a.M, a.K, ring, i8, 2, count) > kMaxDynSmem) return false;
   p.ring = ring;
-  p.bps = bps;
-  p.smem = w4p_smem_bytes(upg, nr, a.M, a.K, ring, i8, bps, pair, count);
+  p.smem = w4p_smem_bytes(upg, nr, a.M, a.K, ring, i8, 2, count);
   p.minb = (p.smem <= half && p.nw != 16) ? 2 : 1;
   // AUTO prefers this kernel where it was measured ahead of the cluster split-K kernel: shares that fit the rings (any
   // block math), and with the integer block math every matrix that gets the 4-slot rings
@@ -1030,7 +1074,6 @@ bool gemv_w4p_preferred(const GemvArgs& a) {
   return plan_w4p(a, true, p) && p.preferred;
 }
 
-using W4PKernel = void (*)(const W4PMaps, const W4PArgs);
 
 // One launch for `count` weight matrices that share the activations (and M, K, bits, group size, zero bias): every CTA
 // works through its range of each matrix in turn -- exactly the range, the warp slices and therefore the fp32 summation
@@ -1068,6 +1111,9 @@ cudaError_t launch_gemv_w4p_multi(const GemvArgs* gs, int count, void* workspace
   a.prefetch_delay = env_int("XBIT_W4P_DELAY", 0);
   a.stage_redux = env_int("XBIT_W4P_REDUX", 1);
   a.count = count;
+  a.nb_shift = 31;
+  while ((1ll << (a.nb_shift - 31)) < a.nb) ++a.nb_shift;          // 2^nb_shift > 2^30 * nb >= j * nb
+  a.nb_magic = (unsigned int)(((1ull << a.nb_shift) + (unsigned)a.nb - 1) / (unsigned)a.nb);
   a.ll_out = g0.ll_out;
   a.a_is_ll = g0.a_is_ll;
   a.ll_chain_index = g0.ll_chain_index;
@@ -1078,9 +1124,9 @@ cudaError_t launch_gemv_w4p_multi(const GemvArgs* gs, int count, void* workspace
     const GemvArgs& g = gs[i];
     W4PPlan pi;                                      // decomposition of this matrix: what a separate call would use
     if (!plan_w4p(g, have_ws, pi)) return cudaErrorInvalidValue;
-    if (count > 1 && (pi.nw != p.nw || pi.mode != p.mode || pi.i8 != p.i8)) {
+    if (count > 1 && (pi.nw != p.nw || pi.i8 != p.i8)) {
       // the launch's shape came from matrix 0 and the combined share: take matrix i's own warp count if all agree on it
-      if (i == 0) { p.nw = pi.nw; p.mode = pi.mode; }
+      if (i == 0) p.nw = pi.nw;
       else return cudaErrorNotSupported;
     }
     if (count > 1 && pi.grid != (pi.unit == 1 ? (int)std::min<long long>((long long)(g.N / 32) * a.nb, sms) : sms)) return cudaErrorNotSupported;
@@ -1112,21 +1158,27 @@ cudaError_t launch_gemv_w4p_multi(const GemvArgs* gs, int count, void* workspace
     W4PPlan q = p;
     GemvArgs probe = g0;
     if (!plan_w4p_nw(probe, have_ws, q, p.nw == 16, count, share_all) || q.nw != p.nw) return cudaErrorNotSupported;
-    p.ring = q.ring; p.smem = q.smem; p.minb = q.minb; p.bps = q.bps;
+    p.ring = q.ring; p.smem = q.smem; p.minb = q.minb;
     a.ring = p.ring;
   }
-  W4PKernel kern = nullptr;
-#define XBIT_W4P_CASE(UPG_, I8_)                                                                        \
+  a.g_magic = p.grid <= 1 ? 0xffffffffu : (unsigned int)(((1ull << 32) + (unsigned)p.grid - 1) / (unsigned)p.grid);
+  const void* kern = nullptr;
+#define XBIT_W4P_CASE(UPG_, I8_, GEN_)                                                                  \
   if (upg == UPG_ && (p.i8 != 0) == I8_) {                                                              \
-    if (p.nw == 16 && p.mode == 1) kern = gemv_w4p_kernel<UPG_, 16, 1, I8_, 2, 1>;                      \
-    else if (p.nw == 16) kern = gemv_w4p_kernel<UPG_, 16, 2, I8_, 2, 1>;                                \
-    else if (p.nw == 12) kern = gemv_w4p_kernel<UPG_, 12, 0, I8_, 2, 2>;                                \
-    else kern = p.minb == 2 ? gemv_w4p_kernel<UPG_, 8, 1, I8_, 2, 2> : gemv_w4p_kernel<UPG_, 8, 1, I8_, 2, 1>; \
+    if (p.nw == 16) kern = (const void*)gemv_w4p_kernel<UPG_, 16, 1, I8_, 2, 1, GEN_>;                  \
+    else if (p.minb == 2) kern = (const void*)gemv_w4p_kernel<UPG_, 8, 1, I8_, 2, 2, GEN_>;             \
+    else kern = (const void*)gemv_w4p_kernel<UPG_, 8, 1, I8_, 2, 1, GEN_>;                              \
   }
-  XBIT_W4P_CASE(1, false) XBIT_W4P_CASE(2, false) XBIT_W4P_CASE(4, false) XBIT_W4P_CASE(4, true)
+#define XBIT_W4P_GEN(GEN_)                                                                              \
+  XBIT_W4P_CASE(1, false, GEN_) XBIT_W4P_CASE(2, false, GEN_) XBIT_W4P_CASE(4, false, GEN_) XBIT_W4P_CASE(4, true, GEN_)
+  const int gen = (a.ll_out || a.a_is_ll) ? 2 : (count > 1 ? 1 : 0);
+  if (gen == 0) { XBIT_W4P_GEN(0) }
+  else if (gen == 1) { XBIT_W4P_GEN(1) }
+  else { XBIT_W4P_GEN(2) }
+#undef XBIT_W4P_GEN
 #undef XBIT_W4P_CASE
   if (!kern) return cudaErrorInvalidValue;
-  cudaError_t e = ensure_max_dyn_smem(reinterpret_cast<const void*>(kern));
+  cudaError_t e = ensure_max_dyn_smem(kern);
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)p.grid, 1, 1);
@@ -1138,7 +1190,18 @@ cudaError_t launch_gemv_w4p_multi(const GemvArgs* gs, int count, void* workspace
   attrs[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attrs;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kern, maps, a);
+  // the single-matrix instantiation takes the short parameter forms: prefixes of the long ones
+  static_assert(offsetof(W4PArgsN<1>, prob) == offsetof(W4PArgs, prob), "short form must be a prefix");
+  alignas(64) W4PMapsN<1> maps1;
+  W4PArgsN<1> a1;
+  void* params[2] = {&maps, &a};
+  if (gen == 0) {
+    memcpy(&maps1, &maps, sizeof(maps1));
+    memcpy(&a1, &a, sizeof(a1));
+    params[0] = &maps1;
+    params[1] = &a1;
+  }
+  return cudaLaunchKernelExC(&cfg, kern, params);
 }
 
 cudaError_t launch_gemv_w4p(const GemvArgs& g, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
