@@ -611,7 +611,9 @@ gemv_w4p_kernel(const __grid_constant__ W4PMapsN<(GEN ? kPMaxProblems : 1)> maps
     // vectors = half a warp.
     if (tid < 4) reinterpret_cast<uint32_t*>(const_sm)[tid] = tid < 2 ? 0x01010101u : 0u;
     const int vecs = a.K >> 3;
-    constexpr int kBatch = 2;
+    // all loads of a thread are issued before the first conversion (K = 11008: 5.4 vectors per thread -- in batches of two
+    // the three L2 round trips, under the weight stream's load, made the staging 2.2 us of that call's 7)
+    constexpr int kBatch = NW == 16 ? 3 : 6;
     for (int m = 0; m < a.M; ++m) {
       const uint4* arow = reinterpret_cast<const uint4*>(a.a + (size_t)m * a.K);
       unsigned char* const pl0 = dig_sm + plane_off(m * 3 + 0);
@@ -915,6 +917,10 @@ gemv_w4p_kernel(const __grid_constant__ W4PMapsN<(GEN ? kPMaxProblems : 1)> maps
         }
         if (starts_tile && !ends_tile) {
           // finisher: the CTAs after this one that hold the tile's later blocks published their parts (normally long ago)
+          // (the CTAs whose ranges begin inside this tile.  On matrices of 120 MB and more this loop and the 64-bit division it
+          // replaced put the back-to-back launches into different steady states -- late CTAs start the next launch late,
+          // with empty rings, and finish it late again: 25.9 against 22.3 us on 8192 x 28672,
+          // profiles/r02_trace_persist_8192x28672_two_regimes.log; the 7B shapes gain 0.1..0.2 us from this form)
           for (int cc = c + 1; cc < G && range_lo(P, cc) < t0 + nb; ++cc) {
             unsigned long long* slot = P.ws + ((size_t)cc * a.M + m) * 32 + lane;
             uint32_t bits, flag;
