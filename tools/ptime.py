@@ -57,6 +57,9 @@ def main():
                 print(f"   persist fine={fine} ring={ring} grid={grid} warps={warps}: {ex}")
         for k in ("XBIT_W4P_FINE", "XBIT_W4P_RING", "XBIT_W4P_GRID", "XBIT_W4P_WARPS"):
             capi.set_option(k)
+        capi.set_option("XBIT_GEMV_STREAMK")
+        us = run(capi.GEMV_AUTO)
+        print(f"   AUTO (what the op runs)        {us:6.2f} us  {nbytes/us/1e3/PEAK*100:3.0f}%   family {lib.xbit_gemv_pick_family(M, K, N, 4, 128)}", flush=True)
         # correctness spot check against a @ dequant
         import xbitops_b200 as X
         w = X.dequant(qw[0], sc[0], qz[0], 128, 4, K, 0)

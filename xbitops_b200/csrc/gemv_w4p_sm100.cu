@@ -748,6 +748,8 @@ gemv_w4p_kernel(const __grid_constant__ W4PMapsN<(GEN ? kPMaxProblems : 1)> maps
   for (int pi = 0; pi < count; ++pi) {
   const W4PProblem& P = a.prob[pi];
   if (pi > 0) slice_range(P, false);
+  // (every slice non-empty and all of them in one tile: see the tile epilogue)
+  const bool one_tile = hi - lo >= kPWarps && tile_of(lo) == tile_of(hi - 1);
   int* const bnd = bnd_sm + pi * 32;
   while (j < jend) {
     const int cnt = min(jend - j, nb - kb);         // this warp's blocks of `tile`: [kb, kb + cnt)
@@ -881,24 +883,40 @@ gemv_w4p_kernel(const __grid_constant__ W4PMapsN<(GEN ? kPMaxProblems : 1)> maps
 #ifdef W4P_TRACE_EXTRA
     if (tid == 0) P_TRACE(8);
 #endif
-    // slices of the CTA that hold blocks of the portion (a slice can be empty when the CTA has fewer blocks than slices):
-    // lane l looks at slice l -- one round of shared-memory loads and a ballot instead of loops over the slices
-    const int b_lo = bnd[min(lane, kPWarps)], b_hi = bnd[min(lane + 1, kPWarps)];
-    const unsigned int held = __ballot_sync(0xffffffffu, lane < kPWarps && min(b_hi, p1) > max(b_lo, p0));
-    const int sl_first = __ffs((int)held) - 1;
-#ifdef W4P_TRACE_EXTRA
-    if (tid == 0) P_TRACE(9);
-#endif
+    unsigned int held;
+    int sl_first;
     bool finalize = true;
-    if (held & (held - 1u)) {                                       // more than one slice: the last to arrive finalizes
-      // (one acquire-release atomic at CTA scope instead of fence.sc + atomic + fence.sc: the __syncwarp before it orders
-      // this warp's partial tile ahead of lane 0's release, the one after it orders the other lanes' loads behind its acquire)
-      uint32_t old = 0;
-      if (lane == 0)
-        asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(&cnt_sm[pi * 16 + sl_first])) : "memory");
-      old = __shfl_sync(0xffffffffu, old, 0);
-      __syncwarp();
-      finalize = ((int)old == __popc(held) - 1);
+    if (one_tile) {
+      // The CTA's whole range lies in this tile and every warp holds a piece of it (the tile-aligned schedule with one tile
+      // per CTA: five of the seven matrices of a Llama-2-7B layer): the warp of slice 0 waits on a named barrier for the
+      // others' arrivals and sums -- no slice search, no counter (0.2 us of every call before)
+      held = (1u << kPWarps) - 1u;
+      sl_first = 0;
+      if (rho != 0) {
+        asm volatile("bar.arrive %0, %1;" ::"r"(2 + (pi & 3)), "n"(kPConsumerThreads) : "memory");
+        finalize = false;
+      } else {
+        asm volatile("bar.sync %0, %1;" ::"r"(2 + (pi & 3)), "n"(kPConsumerThreads) : "memory");
+      }
+    } else {
+      // slices of the CTA that hold blocks of the portion (a slice can be empty when the CTA has fewer blocks than
+      // slices): lane l looks at slice l -- one round of shared-memory loads and a ballot instead of loops over the slices
+      const int b_lo = bnd[min(lane, kPWarps)], b_hi = bnd[min(lane + 1, kPWarps)];
+      held = __ballot_sync(0xffffffffu, lane < kPWarps && min(b_hi, p1) > max(b_lo, p0));
+      sl_first = __ffs((int)held) - 1;
+#ifdef W4P_TRACE_EXTRA
+      if (tid == 0) P_TRACE(9);
+#endif
+      if (held & (held - 1u)) {                                     // more than one slice: the last to arrive finalizes
+        // (one acquire-release atomic at CTA scope instead of fence.sc + atomic + fence.sc: the __syncwarp before it orders
+        // this warp's partial tile ahead of lane 0's release, the one after it orders the other lanes' loads behind its acquire)
+        uint32_t old = 0;
+        if (lane == 0)
+          asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(&cnt_sm[pi * 16 + sl_first])) : "memory");
+        old = __shfl_sync(0xffffffffu, old, 0);
+        __syncwarp();
+        finalize = ((int)old == __popc(held) - 1);
+      }
     }
 #ifdef W4P_TRACE_EXTRA
     if (tid == 0) P_TRACE(11);
@@ -1032,9 +1050,16 @@ static bool plan_w4p_nw(const GemvArgs& a, bool have_ws, W4PPlan& p, bool allow1
   // 2.7 us against 1.7 us for the stacked ones, profiles/r02_*trace*)
   const long long total = tiles * nb;
   const long long g_fine = total < sms ? total : sms;
-  // (the finisher of a shared tile waits for CTAs that finish when it does: worth about 4 blocks + a quarter of a tile)
-  const long long cost_fine = (total + g_fine - 1) / g_fine + (total % g_fine == 0 && (total / g_fine) % nb == 0 ? 0 : 4 + nb / 4);
-  const long long cost_tile = (tiles + sms - 1) / sms * nb;
+  // Cost model in blocks per CTA (8 warps x 4 blocks ~ 1 us), fitted to profiles/r02_ptime_shard_shapes.log:
+  //   * a tile shared between CTAs costs its finisher a round trip through the workspace: ~1.3 us (42 blocks) when the
+  //     CTA ranges are shorter than a tile -- the contributor's piece is then its WHOLE range and lands when the finisher
+  //     is already waiting -- and ~0.6 us (20 blocks) when they are longer (the contributor does that piece first);
+  //   * tile-aligned with fewer tiles than SMs leaves the stream to few SMs: whatever exceeds the rings of a half-SM CTA
+  //     (48 blocks, prefetched during the previous call) arrives at one SM's share of the bandwidth.
+  const long long per_cta_fine = (total + g_fine - 1) / g_fine;
+  const bool fine_is_aligned = total % g_fine == 0 && (total / g_fine) % nb == 0;
+  const long long cost_fine = per_cta_fine + (fine_is_aligned ? 0 : (per_cta_fine < nb ? 42 : 20));
+  const long long cost_tile = (tiles + sms - 1) / sms * nb + ((tiles * 4 < sms * 3 && nb > 48) ? nb - 48 : 0);
   bool fine = have_ws && cost_fine < cost_tile;
   const int env_unit = env_int("XBIT_W4P_FINE", -1);
   if (env_unit == 0) fine = false;
@@ -1062,6 +1087,11 @@ static bool plan_w4p_nw(const GemvArgs& a, bool have_ws, W4PPlan& p, bool allow1
   // AUTO prefers this kernel where it was measured ahead of the cluster split-K kernel: shares that fit the rings (any
   // block math), and with the integer block math every matrix that gets the 4-slot rings
   p.preferred = (small && p.minb == 2) || (i8 && (ring >= 4 || (nr == 16 && ring >= 2)));
+  // ... and NOT where the cluster kernel (split-K across a cluster, every SM streaming) stayed ahead: few tiles of a long
+  // K (the column shards of a tensor-parallel layer: 8192 x 1024 3.8 against 5.6 us, 11008 x 1024 4.4 against 6.3), and
+  // K beyond 16384, where staging the whole activation row per CTA costs more than it saves (28672 x 8192: 23.9 / 27.7)
+  if (fine ? tiles < 64 : (nb > 32 && tiles < 100)) p.preferred = false;
+  if (a.K > 16384) p.preferred = false;
   return true;
 }
 
