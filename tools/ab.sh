@@ -1,2 +1,2 @@
 export PTIME_VARIANTS="1 0 0;0 0 0"
-python tools/ptime.py 4096 4096 4096 11008 11008 4096 8192 8192 4096 2048 4096 5504 11008 2048 4096 1024 4096 2752 11008 1024 4096 512 4096 1376 11008 512 8192 1024 8192 2048 8192 3584 28672 1024 28672 8192 8192 28672 | grep "persist fine\|==\|cluster\|AUTO"
+for m in 2 4 8; do python tools/ptime.py --m $m 4096 4096 4096 11008 8192 8192 | grep "persist fine\|==\|cluster\|AUTO"; done

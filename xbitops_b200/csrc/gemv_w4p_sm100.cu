@@ -1058,7 +1058,9 @@ static bool plan_w4p_nw(const GemvArgs& a, bool have_ws, W4PPlan& p, bool allow1
   //     (48 blocks, prefetched during the previous call) arrives at one SM's share of the bandwidth.
   const long long per_cta_fine = (total + g_fine - 1) / g_fine;
   const bool fine_is_aligned = total % g_fine == 0 && (total / g_fine) % nb == 0;
-  const long long cost_fine = per_cta_fine + (fine_is_aligned ? 0 : (per_cta_fine < nb ? 42 : 20));
+  //   * with the fp16 block math (M > 2, or group sizes 32 / 64) every shared tile also moves M rows of partial sums:
+  //     8 blocks per row (4096 x 11008, M = 4: 8.9 us tile-aligned against 10.3 us; M = 8: 11.8 against 14.8)
+  const long long cost_fine = per_cta_fine + (fine_is_aligned ? 0 : (per_cta_fine < nb ? 42 : 20) + (a.M > 2 ? 8 * a.M : 0));
   const long long cost_tile = (tiles + sms - 1) / sms * nb + ((tiles * 4 < sms * 3 && nb > 48) ? nb - 48 : 0);
   bool fine = have_ws && cost_fine < cost_tile;
   const int env_unit = env_int("XBIT_W4P_FINE", -1);
@@ -1091,6 +1093,9 @@ static bool plan_w4p_nw(const GemvArgs& a, bool have_ws, W4PPlan& p, bool allow1
   // K (the column shards of a tensor-parallel layer: 8192 x 1024 3.8 against 5.6 us, 11008 x 1024 4.4 against 6.3), and
   // K beyond 16384, where staging the whole activation row per CTA costs more than it saves (28672 x 8192: 23.9 / 27.7)
   if (fine ? tiles < 64 : (nb > 32 && tiles < 100)) p.preferred = false;
+  // batches of 3..8 rows (fp16 block math): ahead only where a CTA works through several whole tiles of a short K
+  // (4096 x 11008: M = 4 8.9 against 10.0 us, M = 8 11.8 against 18.0 us; 4096 x 4096 and 8192 x 8192: behind or level)
+  if (a.M > 2) p.preferred = !fine && nb <= 32 && tiles >= 2 * sms;
   if (a.K > 16384) p.preferred = false;
   return true;
 }
