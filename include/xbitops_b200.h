@@ -107,6 +107,13 @@ XBIT_API int xbit_dequant_f16(const int32_t* qweight, const void* scales_f16, co
                               void* out_f16, int K, int N, int bits, int groupsize, int add_zero_bias,
                               xbit_stream_t stream);
 
+/* bf16-native dequantisation (no reference counterpart: the reference converts bf16 scales to
+ * fp16 and the fp16 result back, /root/reference/src/dq_torch_ops.cc:33-42, losing bf16's range):
+ * scales and out are bf16, out = RN_bf16((w - z) * s) with (w - z) * s exact in fp32 -- one rounding. */
+XBIT_API int xbit_dequant_bf16(const int32_t* qweight, const void* scales_bf16, const int32_t* qzeros,
+                               void* out_bf16, int K, int N, int bits, int groupsize, int add_zero_bias,
+                               xbit_stream_t stream);
+
 /* Bytes of OPTIONAL scratch for xbit_gemv_f16 (0 when none is useful).  With a workspace of at
  * least this size the W4 path MAY run a persistent, perfectly balanced stream-K schedule (fp32
  * partial tiles + ready flags) where that is measured to be faster (large matrices whose column
@@ -144,6 +151,17 @@ typedef struct xbit_gemv_problem {
   int N;
   int64_t out_row_stride;
 } xbit_gemv_problem;
+
+/* bf16-native GEMV (no reference counterpart: the reference computes in fp16 whatever the scales'
+ * type, /root/reference/src/dq_torch_ops.cc:65-76): activations, scales and output bf16, fp32 accumulation, ONE rounding
+ * of the result to bf16 -- nothing passes through fp16, so scales and activations keep bf16's range.
+ * Covers bits = 4, groupsize = 128, K % 128 = 0, N % 32 = 0 (the persistent kernel's integer block math; rows are taken
+ * two per launch); XBIT_EINVAL otherwise -- the caller then converts to fp16 as the reference does.
+ * `flags`: XBIT_GEMV_FLAG_STATIC_WEIGHTS or 0.  Workspace as for xbit_gemv_f16. */
+XBIT_API int xbit_gemv_bf16(const void* a_bf16, const int32_t* qweight, const void* scales_bf16,
+                            const int32_t* qzeros, void* out_bf16, int M, int K, int N, int bits,
+                            int groupsize, int add_zero_bias, int64_t out_row_stride,
+                            void* workspace, size_t workspace_bytes, int flags, xbit_stream_t stream);
 
 /* Multi-projection GEMV: `count` (1..4) weight matrices applied to ONE activation matrix, e.g. the Q, K and V
  * projections or gate + up of a decoder layer:  out_p[m, n] = RN16( sum_k a[m, k] * DQ_p[k, n] )  for every p.

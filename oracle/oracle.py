@@ -206,6 +206,32 @@ def np_dequant(qweight, scales, qzeros, groupsize, bits, K, add_zero_bias, round
     return np_sim_float_to_half(res).view(np.float16)
 
 
+def np_f32_to_bf16_bits(x: np.ndarray) -> np.ndarray:
+    """IEEE round-to-nearest-even fp32 -> bf16 (uint16 bit patterns); inf / nan pass through."""
+    u = np.ascontiguousarray(x, np.float32).view(np.uint32).astype(np.uint64)
+    rounded = (u + np.uint64(0x7FFF) + ((u >> np.uint64(16)) & np.uint64(1))) >> np.uint64(16)
+    special = (u & np.uint64(0x7F800000)) == np.uint64(0x7F800000)
+    return np.where(special, u >> np.uint64(16), rounded).astype(np.uint16)
+
+
+def np_bf16_bits_to_f32(b: np.ndarray) -> np.ndarray:
+    return (np.ascontiguousarray(b).view(np.uint16).astype(np.uint32) << np.uint32(16)).view(np.float32)
+
+
+def np_dequant_bf16_native(qweight, scales_bf16_bits, qzeros, groupsize, bits, K, add_zero_bias) -> np.ndarray:
+    """The bf16-native arithmetic of xbit_dequant_bf16 (NOT the reference's, which rounds through fp16,
+    dq_torch_ops.cc:33-42): out = RN_bf16((w - z) * s).  (w - z) * s has at most 9 + 8 significant bits: exact in
+    fp32 and in float64, so one rounding.  Returns uint16 bf16 bit patterns [K, N]."""
+    N = qweight.shape[1]
+    w = np_unpack_qweight(qweight, K, bits).astype(np.int64)
+    z = np_unpack_qzeros(qzeros, N, bits).astype(np.int64) + int(add_zero_bias)
+    grp = np.arange(K) // groupsize
+    s = np_bf16_bits_to_f32(scales_bf16_bits).astype(np.float64)
+    with np.errstate(over="ignore", invalid="ignore"):
+        prod = ((w - z[grp]).astype(np.float64) * s[grp]).astype(np.float32)        # exact unless it overflows fp32
+    return np_f32_to_bf16_bits(prod)
+
+
 def np_gemv_truth(a: np.ndarray, w_f16: np.ndarray):
     y64 = a.astype(np.float64) @ w_f16.astype(np.float64)
     return y64, y64.astype(np.float16)

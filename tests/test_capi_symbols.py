@@ -16,7 +16,7 @@ def _declared():
 
 def test_header_declares_expected_entry_points():
     names = _declared()
-    for must in ("xbit_dequant_f16", "xbit_gemv_f16", "xbit_gemv_f16_ex", "xbit_gemv_f16_peers", "xbit_gemv_f16_host",
+    for must in ("xbit_dequant_f16", "xbit_dequant_bf16", "xbit_gemv_bf16", "xbit_gemv_f16", "xbit_gemv_f16_ex", "xbit_gemv_f16_peers", "xbit_gemv_f16_host",
                  "xbit_gemv_workspace_bytes", "xbit_last_error", "xbit_version"):
         assert must in names
 

@@ -570,3 +570,59 @@ def test_peer_entry_point_single_process(dev, c_oracle):
     torch.cuda.synchronize()
     assert torch.equal(bufs[0], bufs[1])
     assert_gemv_close(bufs[0].cpu().numpy(), y64, "peers")
+
+
+# ------------------------------------------------------------------ bf16-native
+
+def _bf16_bits(t: torch.Tensor) -> np.ndarray:
+    return t.contiguous().view(torch.int16).cpu().numpy().view(np.uint16)
+
+
+@pytest.mark.parametrize("bits", range(2, 9))
+def test_dequant_bf16_native_bit_exact_vs_oracle(bits, dev):
+    """xbit_dequant_bf16: out = RN_bf16((w - z) * s), bit for bit against the numpy restatement, block kernel and element
+    fallback, incl. scales beyond fp16's range (where the reference's fp16 round trip returns inf)."""
+    from oracle import oracle as orc
+    X.set_native_bf16(True)
+    try:
+        for (K, N, g) in ((256, 64, 128), (416, 136, 32), (1024 + 32, 1000, 64), (300, 50, 100)):
+            for bias in (0, 1):
+                qw, s, qz, _ = synth.make_inputs(K, N, bits, g, seed=bits * 7 + g)
+                sb = torch.from_numpy(s.astype(np.float32)).to(torch.bfloat16)
+                if bias:
+                    sb = sb * 2.0 ** 20                                   # far outside fp16
+                want = orc.np_dequant_bf16_native(qw, _bf16_bits(sb), qz, g, bits, K, bias)
+                got = X.dequant(ti(qw, dev), sb.to(dev), ti(qz, dev), g, bits, K, bias)
+                assert got.dtype == torch.bfloat16 and tuple(got.shape) == (K, N)
+                assert (_bf16_bits(got) == want).all(), (bits, K, N, g, bias)
+                assert torch.isfinite(got.float()).all()
+    finally:
+        X.set_native_bf16(False)
+
+
+@pytest.mark.parametrize("M", (1, 2, 5))
+def test_gemv_bf16_native_vs_fp64_truth(M, dev):
+    """xbit_gemv_bf16 (bits 4, groupsize 128): against the fp64 product of the bf16 inputs.  Tolerance: one bf16 rounding
+    of the result (2^-9 relative) plus the kernel's accumulation error -> 4e-3 of the largest |y|; and the
+    same call with scales far outside fp16's range stays finite where the reference's fp16 arithmetic overflows."""
+    from oracle import oracle as orc
+    X.set_native_bf16(True)
+    try:
+        for (K, N) in ((512, 256), (4096, 4096), (4096, 11008), (11008, 4096)):
+            for boost in (1.0, 2.0 ** 18):
+                qw, s, qz, _ = synth.make_inputs(K, N, 4, 128, seed=K + N + M)
+                sb = (torch.from_numpy(s.astype(np.float32)) * boost).to(torch.bfloat16)
+                gen = torch.Generator().manual_seed(K)
+                a = torch.randn((M, K), generator=gen).to(torch.bfloat16)
+                y = X.gemv(a.to(dev), ti(qw, dev), sb.to(dev), ti(qz, dev), 128, 4, K, 1)
+                assert y.dtype == torch.bfloat16 and tuple(y.shape) == (M, N)
+                w = orc.np_unpack_qweight(qw, K, 4).astype(np.float64)
+                z = orc.np_unpack_qzeros(qz, N, 4).astype(np.float64) + 1
+                grp = np.arange(K) // 128
+                truth = a.double().numpy() @ ((w - z[grp]) * sb.double().numpy()[grp])
+                got = y.double().cpu().numpy()
+                assert np.isfinite(got).all()
+                err = np.abs(got - truth).max() / np.abs(truth).max()
+                assert err <= 4e-3, (K, N, M, boost, err)
+    finally:
+        X.set_native_bf16(False)

@@ -17,7 +17,7 @@ __version__ = "0.1.0"
 
 def __getattr__(name):
     # torch is imported lazily so that `import xbitops_b200.synth` stays light
-    if name in ("dequant", "gemv", "gemv_multi", "set_static_weights", "get_static_weights"):
+    if name in ("dequant", "gemv", "gemv_multi", "set_static_weights", "get_static_weights", "set_native_bf16", "get_native_bf16"):
         from . import ops
         return getattr(ops, name)
     if name in ("QLinear", "pack_qweight", "pack_qzeros", "quantize_rtn"):

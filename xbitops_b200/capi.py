@@ -22,6 +22,8 @@ SIGNATURES = {
     "xbit_last_error": (ctypes.c_char_p, []),
     "xbit_set_option": (_i, [ctypes.c_char_p, _i]),
     "xbit_dequant_f16": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "xbit_dequant_bf16": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "xbit_gemv_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i64, _vp, _sz, _i, _vp]),
     "xbit_gemv_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "xbit_gemv_f16": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i64, _vp, _sz, _vp]),
     "xbit_gemv_f16_ex": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i64, _vp, _sz, _i, _vp]),

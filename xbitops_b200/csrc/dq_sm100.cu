@@ -19,6 +19,7 @@
 //     HFMA2 sees exactly half(w) as the reference does.
 //   * out is fully overwritten: callers allocate with empty(), not zeros() (reference: at::zeros,
 //     src/dq_torch_ops.cc:38 -> an extra K*N*2-byte memset).
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -88,7 +89,10 @@ __device__ __forceinline__ __half2 neg_scaled_zero(uint32_t z0, uint32_t z1, __h
   return __hneg2(__hmul2(hz, s));
 }
 
-template <int B>
+// BF: bf16-native arithmetic (the reference converts bf16 scales to fp16 and the result back,
+// src/dq_torch_ops.cc:33-42, which loses bf16's range): scales and output are bf16 and
+//     out = RN_bf16((w - z) * s)      -- (w - z) * s is exact in fp32 (9 x 8 significant bits): ONE rounding.
+template <int B, bool BF>
 __global__ void __launch_bounds__(128)
 dq_block32_kernel(const uint32_t* __restrict__ qweight, const __half* __restrict__ scales,
                   const uint32_t* __restrict__ qzeros, __half* __restrict__ out,
@@ -126,22 +130,49 @@ dq_block32_kernel(const uint32_t* __restrict__ qweight, const __half* __restrict
   const __half2 s[4] = {u2h2(sv.x), u2h2(sv.y), u2h2(sv.z), u2h2(sv.w)};
   uint32_t z[8];
   load_zero_octet<B>(qzeros + (size_t)g * zwords, zwords, cx, zero_bias, z);
-  __half2 nsz[4];
-#pragma unroll
-  for (int p = 0; p < 4; ++p) nsz[p] = neg_scaled_zero(z[2 * p], z[2 * p + 1], s[p]);
-
-  // ---- 32 output rows, one 16-byte streaming store each
-  __half* orow = out + (size_t)k0 * N + n0;
+  __half* orow = out + (size_t)k0 * N + n0;          // (bf16 elements when BF: same size)
   const int rows_left = K - k0;
-  static_for<0, 32>([&](auto ic) {
-    constexpr int i = decltype(ic)::value;
-    uint4 r;
-    r.x = h22u(__hfma2(field_pair_exact<B, i>(w[0], w[1]), s[0], nsz[0]));
-    r.y = h22u(__hfma2(field_pair_exact<B, i>(w[2], w[3]), s[1], nsz[1]));
-    r.z = h22u(__hfma2(field_pair_exact<B, i>(w[4], w[5]), s[2], nsz[2]));
-    r.w = h22u(__hfma2(field_pair_exact<B, i>(w[6], w[7]), s[3], nsz[3]));
-    if (i < rows_left) stg_stream_v4(orow + (size_t)i * N, r);
-  });
+  if constexpr (BF) {
+    // the 16 bits of each scale are bf16: fp32 = bits << 16;  -(z * s) is exact in fp32, and so is fma(w, s, -(z * s))
+    float sf[8], nzs[8];
+    const uint32_t sw[4] = {sv.x, sv.y, sv.z, sv.w};
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      sf[2 * p] = __uint_as_float(sw[p] << 16);
+      sf[2 * p + 1] = __uint_as_float(sw[p] & 0xffff0000u);
+      nzs[2 * p] = -(float)z[2 * p] * sf[2 * p];
+      nzs[2 * p + 1] = -(float)z[2 * p + 1] * sf[2 * p + 1];
+    }
+    auto pair_bf16 = [&](__half2 wh, int p) {
+      const float2 wf = __half22float2(wh);
+      const __nv_bfloat162 o = __floats2bfloat162_rn(fmaf(wf.x, sf[2 * p], nzs[2 * p]), fmaf(wf.y, sf[2 * p + 1], nzs[2 * p + 1]));
+      return *reinterpret_cast<const uint32_t*>(&o);
+    };
+    static_for<0, 32>([&](auto ic) {
+      constexpr int i = decltype(ic)::value;
+      uint4 r;
+      r.x = pair_bf16(field_pair_exact<B, i>(w[0], w[1]), 0);
+      r.y = pair_bf16(field_pair_exact<B, i>(w[2], w[3]), 1);
+      r.z = pair_bf16(field_pair_exact<B, i>(w[4], w[5]), 2);
+      r.w = pair_bf16(field_pair_exact<B, i>(w[6], w[7]), 3);
+      if (i < rows_left) stg_stream_v4(orow + (size_t)i * N, r);
+    });
+  } else {
+    __half2 nsz[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) nsz[p] = neg_scaled_zero(z[2 * p], z[2 * p + 1], s[p]);
+
+    // ---- 32 output rows, one 16-byte streaming store each
+    static_for<0, 32>([&](auto ic) {
+      constexpr int i = decltype(ic)::value;
+      uint4 r;
+      r.x = h22u(__hfma2(field_pair_exact<B, i>(w[0], w[1]), s[0], nsz[0]));
+      r.y = h22u(__hfma2(field_pair_exact<B, i>(w[2], w[3]), s[1], nsz[1]));
+      r.z = h22u(__hfma2(field_pair_exact<B, i>(w[4], w[5]), s[2], nsz[2]));
+      r.w = h22u(__hfma2(field_pair_exact<B, i>(w[6], w[7]), s[3], nsz[3]));
+      if (i < rows_left) stg_stream_v4(orow + (size_t)i * N, r);
+    });
+  }
 }
 
 // Fallback for shapes the block kernel cannot take (N % 8 != 0, groupsize % 32 != 0, unaligned
@@ -149,7 +180,7 @@ dq_block32_kernel(const uint32_t* __restrict__ qweight, const __half* __restrict
 __global__ void __launch_bounds__(256)
 dq_element_kernel(const uint32_t* __restrict__ qweight, const __half* __restrict__ scales,
                   const uint32_t* __restrict__ qzeros, __half* __restrict__ out,
-                  int K, int N, int bits, int groupsize, int zero_bias, int qrows, int zwords) {
+                  int K, int N, int bits, int groupsize, int zero_bias, int qrows, int zwords, int bf16) {
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
   if (idx >= (long long)K * N) return;
   const int k = (int)(idx / N), n = (int)(idx % N);
@@ -165,6 +196,11 @@ dq_element_kernel(const uint32_t* __restrict__ qweight, const __half* __restrict
   const uint32_t zlo = __ldg(qzeros + (size_t)g * zwords + zi);
   const uint32_t zhi = (zsh + bits > 32 && zi + 1 < zwords) ? __ldg(qzeros + (size_t)g * zwords + zi + 1) : 0u;
   const uint32_t zv = (__funnelshift_r(zlo, zhi, zsh) & mask) + (uint32_t)zero_bias;
+  if (bf16) {
+    const float sf = __uint_as_float((uint32_t)reinterpret_cast<const unsigned short*>(scales)[(size_t)g * N + n] << 16);
+    reinterpret_cast<__nv_bfloat16*>(out)[idx] = __float2bfloat16_rn(fmaf((float)wv, sf, -(float)zv * sf));
+    return;
+  }
   const __half s = scales[(size_t)g * N + n];
   const __half sz = __hmul(__ushort2half_rn((unsigned short)zv), s);
   out[idx] = __hfma(__ushort2half_rn((unsigned short)wv), s, __hneg(sz));
@@ -178,7 +214,7 @@ static int dq_smem_cap_kb() {
   return (v < 0 || v > 200) ? 48 : v;
 }
 
-template <int B>
+template <int B, bool BF>
 static cudaError_t launch_block32(const DqArgs& a, cudaStream_t stream) {
   const int rblocks = (a.K + 31) / 32;
   const long long threads = (long long)rblocks * (a.N >> 3);
@@ -195,7 +231,7 @@ static cudaError_t launch_block32(const DqArgs& a, cudaStream_t stream) {
   if (cap_kb > 48) {
     static bool done[8] = {false, false, false, false, false, false, false, false};
     if (!done[B - 1]) {
-      cudaError_t e = cudaFuncSetAttribute(dq_block32_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      cudaError_t e = cudaFuncSetAttribute(dq_block32_kernel<B, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       if (e != cudaSuccess) return e;
       done[B - 1] = true;
     }
@@ -206,7 +242,7 @@ static cudaError_t launch_block32(const DqArgs& a, cudaStream_t stream) {
   attrs[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attrs;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, dq_block32_kernel<B>, a.qweight, a.scales, a.qzeros, a.out, a.K, a.N, a.groupsize,
+  return cudaLaunchKernelEx(&cfg, dq_block32_kernel<B, BF>, a.qweight, a.scales, a.qzeros, a.out, a.K, a.N, a.groupsize,
                             a.zero_bias, a.qrows, a.zwords, rblocks);
 }
 
@@ -217,20 +253,16 @@ cudaError_t launch_dequant(const DqArgs& a, cudaStream_t stream, int* path_taken
   if (path_taken) *path_taken = block_ok ? 1 : 0;
   if (block_ok) {
     switch (a.bits) {
-      case 2: return launch_block32<2>(a, stream);
-      case 3: return launch_block32<3>(a, stream);
-      case 4: return launch_block32<4>(a, stream);
-      case 5: return launch_block32<5>(a, stream);
-      case 6: return launch_block32<6>(a, stream);
-      case 7: return launch_block32<7>(a, stream);
-      case 8: return launch_block32<8>(a, stream);
+#define XBIT_DQ_CASE(B_) case B_: return a.bf16 ? launch_block32<B_, true>(a, stream) : launch_block32<B_, false>(a, stream);
+      XBIT_DQ_CASE(2) XBIT_DQ_CASE(3) XBIT_DQ_CASE(4) XBIT_DQ_CASE(5) XBIT_DQ_CASE(6) XBIT_DQ_CASE(7) XBIT_DQ_CASE(8)
+#undef XBIT_DQ_CASE
       default: return cudaErrorInvalidValue;
     }
   }
   const long long total = (long long)a.K * a.N;
   const unsigned grid = (unsigned)((total + 255) / 256);
   dq_element_kernel<<<grid, 256, 0, stream>>>(a.qweight, a.scales, a.qzeros, a.out, a.K, a.N, a.bits,
-                                              a.groupsize, a.zero_bias, a.qrows, a.zwords);
+                                              a.groupsize, a.zero_bias, a.qrows, a.zwords, a.bf16);
   return cudaGetLastError();
 }
 

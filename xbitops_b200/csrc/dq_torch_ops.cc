@@ -71,6 +71,13 @@ std::atomic<bool> g_static_weights{[] {
   return v && *v && *v != '0';
 }()};
 
+// bf16 without the fp16 round trip (default off = the reference's behaviour, :33-42, :65-76):
+// dequant with bf16 scales -> xbit_dequant_bf16; gemv with bf16 activations and scales -> xbit_gemv_bf16 where it exists
+std::atomic<bool> g_native_bf16{[] {
+  const char* v = std::getenv("XBIT_NATIVE_BF16");
+  return v && *v && *v != '0';
+}()};
+
 void raise_if(int rc) { TORCH_CHECK(rc == XBIT_OK, "xbitops_b200: ", xbit_last_error()); }
 
 // Scratch for the persistent stream-K schedule (include/xbitops_b200.h: xbit_gemv_workspace_bytes):
@@ -97,11 +104,18 @@ torch::Tensor dequant_any_bit(const torch::Tensor& qweight, const torch::Tensor&
                               int groupsize, int bits, int in_features, uint8_t add_zero_bias) {
   check_quant_args(qweight, scales, qzeros, groupsize, bits, in_features);
   const c10::cuda::CUDAGuard guard(qweight.device());
+  auto stream = at::cuda::getCurrentCUDAStream().stream();
+  if (g_native_bf16.load() && scales.scalar_type() == torch::kBFloat16) {
+    at::Tensor out = at::empty({in_features, qweight.size(1)}, scales.options());
+    raise_if(xbit_dequant_bf16(qweight.data_ptr<int32_t>(), scales.data_ptr(), qzeros.data_ptr<int32_t>(), out.data_ptr(),
+                               in_features, (int)qweight.size(1), bits, groupsize, add_zero_bias,
+                               reinterpret_cast<xbit_stream_t>(stream)));
+    return out;
+  }
   auto f16_scale = scales;
   const auto ori_dtype = scales.scalar_type();
   if (ori_dtype == torch::kBFloat16) f16_scale = scales.to(torch::kFloat16);
   at::Tensor output = at::empty({in_features, qweight.size(1)}, f16_scale.options());
-  auto stream = at::cuda::getCurrentCUDAStream().stream();
   raise_if(xbit_dequant_f16(qweight.data_ptr<int32_t>(), f16_scale.data_ptr(), qzeros.data_ptr<int32_t>(),
                             output.data_ptr(), in_features, (int)qweight.size(1), bits, groupsize, add_zero_bias,
                             reinterpret_cast<xbit_stream_t>(stream)));
@@ -114,7 +128,9 @@ torch::Tensor op_gemv(const torch::Tensor& input_a, const torch::Tensor& qweight
   CHECK_INPUT(input_a);
   check_quant_args(qweight, scales, qzeros, groupsize, bits, in_features);
   TORCH_CHECK(qweight.device().index() == input_a.device().index(), "input and weight must be on the same device");
-  TORCH_CHECK(input_a.scalar_type() == torch::kFloat16, "input_a must be float16");
+  const bool native = g_native_bf16.load() && input_a.scalar_type() == torch::kBFloat16 && scales.scalar_type() == torch::kBFloat16 &&
+                      bits == 4 && groupsize == 128 && in_features % 128 == 0 && qweight.size(1) % 32 == 0 && in_features <= 16384;
+  TORCH_CHECK(native || input_a.scalar_type() == torch::kFloat16, "input_a must be float16");
   TORCH_CHECK(input_a.dim() >= 2 && input_a.size(-1) == in_features, "input_a must be [..., in_features]");
   const c10::cuda::CUDAGuard guard(qweight.device());
   std::vector<int64_t> outputshape = {input_a.size(0), qweight.size(1)};
@@ -122,6 +138,19 @@ torch::Tensor op_gemv(const torch::Tensor& input_a, const torch::Tensor& qweight
   if (input_a.dim() > 2) {
     outputshape.insert(outputshape.begin() + 1, input_a.size(1));
     mat_m *= input_a.size(1);
+  }
+  if (native) {
+    at::Tensor out = at::empty(outputshape, scales.options());
+    auto st = at::cuda::getCurrentCUDAStream().stream();
+    if (mat_m > 0) {
+      const size_t ws_bytes = xbit_gemv_workspace_bytes(2, in_features, (int)qweight.size(1), bits, groupsize);
+      at::Tensor ws = gemv_workspace(qweight.device(), st, ws_bytes);
+      raise_if(xbit_gemv_bf16(input_a.data_ptr(), qweight.data_ptr<int32_t>(), scales.data_ptr(), qzeros.data_ptr<int32_t>(),
+                              out.data_ptr(), (int)mat_m, in_features, (int)qweight.size(1), bits, groupsize, add_zero_bias,
+                              qweight.size(1), ws.data_ptr(), ws_bytes, g_static_weights.load() ? XBIT_GEMV_FLAG_STATIC_WEIGHTS : 0,
+                              reinterpret_cast<xbit_stream_t>(st)));
+    }
+    return out;
   }
   auto f16_scale = scales;
   const auto ori_dtype = scales.scalar_type();
@@ -161,4 +190,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         "promise that the weight tensors passed to gemv are never written by the kernel preceding the call in its "
         "stream (resident model weights): gemv then prefetches them while that kernel drains");
   m.def("get_static_weights", []() { return g_static_weights.load(); });
+  m.def("set_native_bf16", [](bool on) { g_native_bf16.store(on); },
+        "bf16 scales (dequant) / bf16 activations and scales (gemv) without the reference's fp16 round trip");
+  m.def("get_native_bf16", []() { return g_native_bf16.load(); });
 }

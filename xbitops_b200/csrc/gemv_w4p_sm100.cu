@@ -26,6 +26,7 @@
 //     partials waiting.  Sums are taken in warp / CTA order: deterministic, no atomics on data.
 //     Without a workspace CTA boundaries are tile-aligned instead and nothing crosses CTAs.
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stddef.h>
@@ -282,7 +283,8 @@ __device__ __forceinline__ void pimma_zero(int (&d)[4], uint32_t a0, uint32_t a1
 // row (16 * k-block), gt[b] = the group's table entry {2^(E-22) row 0, row 1, sum_k a_k row 0, row 1}.
 // tot[tt][h] accumulates sf * 2^(E-22) * (D0 + 256 D1 | D2 - 64 S) for weight column 4g + 2tt + h; zc[m] the zero-point
 // term of column 4g + t for activation row m.
-template <int NB>
+// BF: the scales are bf16 (bf16-native form of the kernel)
+template <int NB, bool BF = false>
 __device__ __forceinline__ void w4p_consume_i8(const unsigned char* const (&wp)[NB], const unsigned char* const (&sp)[NB],
                                                const unsigned char* const (&zp)[NB], const int (&wrow)[NB],
                                                const float* const (&gt)[NB], const W4PLaneI& L, float (&tot)[2][2], float (&zc)[2]) {
@@ -320,8 +322,8 @@ __device__ __forceinline__ void w4p_consume_i8(const unsigned char* const (&wp)[
   }
 #pragma unroll
   for (int b = 0; b < NB; ++b) {
-    const float2 s01 = __half22float2(u2h2(sraw[b].x));
-    const float2 s23 = __half22float2(u2h2(sraw[b].y));
+    const float2 s01 = BF ? make_float2(__uint_as_float(sraw[b].x << 16), __uint_as_float(sraw[b].x & 0xffff0000u)) : __half22float2(u2h2(sraw[b].x));
+    const float2 s23 = BF ? make_float2(__uint_as_float(sraw[b].y << 16), __uint_as_float(sraw[b].y & 0xffff0000u)) : __half22float2(u2h2(sraw[b].y));
     const float sfg[4] = {s01.x * gsv[b], s01.y * gsv[b], s23.x * gsv[b], s23.y * gsv[b]};
 #pragma unroll
     for (int tt = 0; tt < 2; ++tt)
@@ -331,7 +333,8 @@ __device__ __forceinline__ void w4p_consume_i8(const unsigned char* const (&wp)[
         tot[tt][h] = fmaf(sfg[2 * tt + h], (float)v, tot[tt][h]);
       }
     // zero point of column 4g + t: -(s * (z + bias)) * sum_k a_k per activation row
-    const float sz = __half2float(__ushort_as_half((unsigned short)prmt(sraw[b].x, sraw[b].y, L.ssel))) *
+    const uint32_t s16 = prmt(sraw[b].x, sraw[b].y, L.ssel) & 0xffffu;
+    const float sz = (BF ? __uint_as_float(s16 << 16) : __half2float(__ushort_as_half((unsigned short)s16))) *
                      ((float)((zraw[b] >> L.zsh) & 0xFu) + L.zbias);
     zc[0] = fmaf(sz, aq[b].x, zc[0]);
     zc[1] = fmaf(sz, aq[b].y, zc[1]);
@@ -373,7 +376,9 @@ __device__ __forceinline__ int p_slice_of(int w) { return (w & 3) * (NW / 4) + (
 // the loops over matrices fold away and the activation loads of the staging phase are issued back to back; measured
 // 3.37 against 3.96 us on 4096 x 4096 and 6.97 against 8.25 us on 11008 x 4096 for the general form, profiles/r02_ab.log);
 // 1 = several matrices (xbit_gemv_f16_multi); 2 = also the flag-in-data (LL) input / output forms.
-template <int UPG, int NW, int MODE, bool I8, int BPS, int MINB, int GEN>
+// BF: bf16-native form (activations, scales and output bf16; integer block math only): the activations' 24-bit fixed
+// point comes from the bf16 exponent, the scales widen by a shift, the result is rounded once, to bf16.
+template <int UPG, int NW, int MODE, bool I8, int BPS, int MINB, int GEN, bool BF = false>
 __global__ void __launch_bounds__((NW + 1) * 32, MINB)
 gemv_w4p_kernel(const __grid_constant__ W4PMapsN<(GEN ? kPMaxProblems : 1)> maps, const __grid_constant__ W4PArgsN<(GEN ? kPMaxProblems : 1)> a) {
   using Cfg = W4PCfg<UPG, BPS>;
@@ -383,6 +388,7 @@ gemv_w4p_kernel(const __grid_constant__ W4PMapsN<(GEN ? kPMaxProblems : 1)> maps
   constexpr bool DUAL = MODE == 1;
   static_assert(MODE == 0 || MODE == 1, "MODE: 0 = one block at a time, 1 = two blocks together");
   static_assert(!I8 || UPG == 4, "the integer block math covers groupsize 128");
+  static_assert(!BF || (I8 && GEN == 0), "the bf16-native form exists for the integer block math, one matrix per launch");
   constexpr int kPWarps = NW;                       // rings = slices of the CTA's range
   constexpr int kPConsumerThreads = NW * 32;
   constexpr int LPR = kPWarps <= 8 ? 4 : 2;         // producer lanes per ring
@@ -634,13 +640,24 @@ gemv_w4p_kernel(const __grid_constant__ W4PMapsN<(GEN ? kPMaxProblems : 1)> maps
           if (vw >= vecs) break;
           const int v = vw + lane;
           const bool ok = v < vecs;
-          const float2 f0 = __half22float2(u2h2(val[b].x)), f1 = __half22float2(u2h2(val[b].y));
-          const float2 f2 = __half22float2(u2h2(val[b].z)), f3 = __half22float2(u2h2(val[b].w));
-          // largest |a| of the group as fp16 bits (the bit patterns of non-negative halves order like integers): one
+          auto widen = [](uint32_t x) {
+            return BF ? make_float2(__uint_as_float(x << 16), __uint_as_float(x & 0xffff0000u)) : __half22float2(u2h2(x));
+          };
+          const float2 f0 = widen(val[b].x), f1 = widen(val[b].y), f2 = widen(val[b].z), f3 = widen(val[b].w);
+          // largest |a| of the group as fp16 (bf16) bits (the bit patterns of non-negative halves order like integers): one
           // REDUX over the half-warp instead of a shuffle tree -- this phase sits on the critical path of every call
-          const __half2 ax = __hmax2(__habs2(u2h2(val[b].x)), __habs2(u2h2(val[b].y)));
-          const __half2 az = __hmax2(__habs2(u2h2(val[b].z)), __habs2(u2h2(val[b].w)));
-          const uint32_t am2 = h22u(__hmax2(ax, az));
+          uint32_t am2;
+          if constexpr (BF) {
+            auto b2 = [](uint32_t x) { return *reinterpret_cast<const __nv_bfloat162*>(&x); };
+            const __nv_bfloat162 ax = __hmax2(__habs2(b2(val[b].x)), __habs2(b2(val[b].y)));
+            const __nv_bfloat162 az = __hmax2(__habs2(b2(val[b].z)), __habs2(b2(val[b].w)));
+            const __nv_bfloat162 am = __hmax2(ax, az);
+            am2 = *reinterpret_cast<const uint32_t*>(&am);
+          } else {
+            const __half2 ax = __hmax2(__habs2(u2h2(val[b].x)), __habs2(u2h2(val[b].y)));
+            const __half2 az = __hmax2(__habs2(u2h2(val[b].z)), __habs2(u2h2(val[b].w)));
+            am2 = h22u(__hmax2(ax, az));
+          }
           // (full-warp REDUX twice, one per half: a half-warp mask makes the compiler serialise the halves)
           const bool upper = (lane & 16) != 0;
           const uint32_t amax1 = max(am2 & 0xFFFFu, am2 >> 16);
@@ -655,9 +672,10 @@ gemv_w4p_kernel(const __grid_constant__ W4PMapsN<(GEN ? kPMaxProblems : 1)> maps
             for (int o = 1; o < 16; o <<= 1) amax = max(amax, __shfl_xor_sync(0xffffffffu, amax, o));
           }
           // |a| < 2^E with E = exponent field - 14; q = a * 2^(22-E) (odd k: 2^(18-E)); inf / nan activations poison the group
-          const uint32_t eb = amax >> 10;
-          const float se = __uint_as_float((163u - eb) << 23), so = __uint_as_float((159u - eb) << 23);
-          const float gs = eb >= 31u ? __uint_as_float(0x7fc00000u) : __uint_as_float((91u + eb) << 23);
+          // (bf16: |a| < 2^E with E = exponent field - 126; fields below 22 -- |a| < 2^-104 -- share the scale of 22)
+          const uint32_t eb = BF ? max(amax >> 7, 22u) : amax >> 10;
+          const float se = __uint_as_float(((BF ? 275u : 163u) - eb) << 23), so = __uint_as_float(((BF ? 271u : 159u) - eb) << 23);
+          const float gs = eb >= (BF ? 255u : 31u) ? __uint_as_float(0x7fc00000u) : __uint_as_float(BF ? (eb - 21u) << 23 : (91u + eb) << 23);
           const float kMagic = 12582912.f;         // 1.5 * 2^23: the bits of (q + kMagic) are 0x4B400000 + q
           const uint32_t u0 = __float_as_uint(fmaf(f0.x, se, kMagic)), u1 = __float_as_uint(fmaf(f0.y, so, kMagic));
           const uint32_t u2 = __float_as_uint(fmaf(f1.x, se, kMagic)), u3 = __float_as_uint(fmaf(f1.y, so, kMagic));
@@ -795,21 +813,21 @@ gemv_w4p_kernel(const __grid_constant__ W4PMapsN<(GEN ? kPMaxProblems : 1)> maps
             const unsigned char* const zp[2] = {z0, z1};
             const int wr[2] = {(kb + i) * 16, (kb + i + 1) * 16};
             const float* const gp[2] = {g0, g0 + 4};
-            w4p_consume_i8<2>(wp, sp, zp, wr, gp, LI, toti, zci);
+            w4p_consume_i8<2, BF>(wp, sp, zp, wr, gp, LI, toti, zci);
           } else {
             const unsigned char* const wp[1] = {w0};
             const unsigned char* const sp[1] = {sc0};
             const unsigned char* const zp[1] = {z0};
             const int wr[1] = {(kb + i) * 16};
             const float* const gp[1] = {g0};
-            w4p_consume_i8<1>(wp, sp, zp, wr, gp, LI, toti, zci);
+            w4p_consume_i8<1, BF>(wp, sp, zp, wr, gp, LI, toti, zci);
             if (!DUAL && i + 2 <= cnt) {
               const unsigned char* const wp1[1] = {w1};
               const unsigned char* const sp1[1] = {sc1};
               const unsigned char* const zp1[1] = {z1};
               const int wr1[1] = {(kb + i + 1) * 16};
               const float* const gp1[1] = {g0 + 4};
-              w4p_consume_i8<1>(wp1, sp1, zp1, wr1, gp1, LI, toti, zci);
+              w4p_consume_i8<1, BF>(wp1, sp1, zp1, wr1, gp1, LI, toti, zci);
             }
           }
         } else if (DUAL && i + 2 <= cnt) {
@@ -953,7 +971,7 @@ gemv_w4p_kernel(const __grid_constant__ W4PMapsN<(GEN ? kPMaxProblems : 1)> maps
           }
         }
         if (starts_tile) {
-          const __half h = __float2half_rn(v);
+          const __half h = BF ? __ushort_as_half(__bfloat16_as_ushort(__float2bfloat16_rn(v))) : __float2half_rn(v);   // (16 result bits)
           const size_t off = (size_t)m * P.ldo + P.col_offset + n;
           if (ll_out) {
             // flag-in-data all-gather: each pair of results goes to every rank as one {half2, call number} store
@@ -1043,6 +1061,7 @@ static bool plan_w4p_nw(const GemvArgs& a, bool have_ws, W4PPlan& p, bool allow1
   // integer block math: groupsize 128, M <= 2 (XBIT_W4P_I8=0: the fp16 exact-product math everywhere)
   const bool i8 = a.groupsize == 128 && a.M <= 2 && env_int("XBIT_W4P_I8", 1) != 0;
   p.i8 = i8 ? 1 : 0;
+  if (a.bf16 && (!i8 || count != 1 || a.ll_out || a.a_is_ll)) return false;   // the bf16-native form: integer block math, one matrix
   // CTA boundaries: block granular (perfect balance, tiles shared between CTAs meet in the workspace) or tile aligned
   // (nothing crosses CTAs).  Cost model in blocks per CTA; the cross-CTA fix-up is worth about 4 blocks of time.
   // Tile-aligned: always one CTA per SM, also when there are fewer tiles (CTAs without work hold their slot until the
@@ -1213,7 +1232,11 @@ cudaError_t launch_gemv_w4p_multi(const GemvArgs* gs, int count, void* workspace
 #define XBIT_W4P_GEN(GEN_)                                                                              \
   XBIT_W4P_CASE(1, false, GEN_) XBIT_W4P_CASE(2, false, GEN_) XBIT_W4P_CASE(4, false, GEN_) XBIT_W4P_CASE(4, true, GEN_)
   const int gen = (a.ll_out || a.a_is_ll) ? 2 : (count > 1 ? 1 : 0);
-  if (gen == 0) { XBIT_W4P_GEN(0) }
+  if (g0.bf16) {
+    if (p.nw == 16) kern = (const void*)gemv_w4p_kernel<4, 16, 1, true, 2, 1, 0, true>;
+    else if (p.minb == 2) kern = (const void*)gemv_w4p_kernel<4, 8, 1, true, 2, 2, 0, true>;
+    else kern = (const void*)gemv_w4p_kernel<4, 8, 1, true, 2, 1, 0, true>;
+  } else if (gen == 0) { XBIT_W4P_GEN(0) }
   else if (gen == 1) { XBIT_W4P_GEN(1) }
   else { XBIT_W4P_GEN(2) }
 #undef XBIT_W4P_GEN

@@ -59,16 +59,30 @@ int xbit_set_option(const char* name, int value) {
 
 const char* xbit_last_error(void) { return g_err; }
 
+static int dequant_any(const int32_t* qweight, const void* scales_f16, const int32_t* qzeros, void* out_f16, int K, int N,
+                       int bits, int groupsize, int add_zero_bias, xbit_stream_t stream, int bf16);
+
 int xbit_dequant_f16(const int32_t* qweight, const void* scales_f16, const int32_t* qzeros, void* out_f16, int K, int N,
                      int bits, int groupsize, int add_zero_bias, xbit_stream_t stream) {
+  return dequant_any(qweight, scales_f16, qzeros, out_f16, K, N, bits, groupsize, add_zero_bias, stream, 0);
+}
+
+int xbit_dequant_bf16(const int32_t* qweight, const void* scales_bf16, const int32_t* qzeros, void* out_bf16, int K, int N,
+                      int bits, int groupsize, int add_zero_bias, xbit_stream_t stream) {
+  return dequant_any(qweight, scales_bf16, qzeros, out_bf16, K, N, bits, groupsize, add_zero_bias, stream, 1);
+}
+
+static int dequant_any(const int32_t* qweight, const void* scales_f16, const int32_t* qzeros, void* out_f16, int K, int N,
+                       int bits, int groupsize, int add_zero_bias, xbit_stream_t stream, int bf16) {
   g_err[0] = 0;
   if (int rc = check_common(qweight, scales_f16, qzeros, K, N, bits, groupsize, add_zero_bias)) return rc;
   if (!out_f16) return fail(XBIT_EINVAL, "null output pointer");
   if ((reinterpret_cast<uintptr_t>(out_f16) | reinterpret_cast<uintptr_t>(scales_f16)) & 1u)
-    return fail(XBIT_EINVAL, "fp16 pointers must be 2-byte aligned");
+    return fail(XBIT_EINVAL, "16-bit float pointers must be 2-byte aligned");
   if ((reinterpret_cast<uintptr_t>(qweight) | reinterpret_cast<uintptr_t>(qzeros)) & 3u)
     return fail(XBIT_EINVAL, "int32 pointers must be 4-byte aligned");
   xbit::DqArgs a;
+  a.bf16 = bf16;
   a.qweight = reinterpret_cast<const uint32_t*>(qweight);
   a.scales = reinterpret_cast<const __half*>(scales_f16);
   a.qzeros = reinterpret_cast<const uint32_t*>(qzeros);
@@ -77,7 +91,7 @@ int xbit_dequant_f16(const int32_t* qweight, const void* scales_f16, const int32
   a.qrows = ceil_div((long long)K * bits, 32);
   a.zwords = ceil_div((long long)N * bits, 32);
   cudaError_t e = xbit::launch_dequant(a, reinterpret_cast<cudaStream_t>(stream), nullptr);
-  if (e != cudaSuccess) return cuda_fail(e, "xbit_dequant_f16 launch");
+  if (e != cudaSuccess) return cuda_fail(e, bf16 ? "xbit_dequant_bf16 launch" : "xbit_dequant_f16 launch");
   return XBIT_OK;
 }
 
@@ -268,6 +282,41 @@ int xbit_gemv_f16(const void* a_f16, const int32_t* qweight, const void* scales_
                   size_t workspace_bytes, xbit_stream_t stream) {
   return xbit_gemv_f16_ex(a_f16, qweight, scales_f16, qzeros, out_f16, M, K, N, bits, groupsize, add_zero_bias,
                           out_row_stride, workspace, workspace_bytes, XBIT_GEMV_AUTO, stream);
+}
+
+int xbit_gemv_bf16(const void* a_bf16, const int32_t* qweight, const void* scales_bf16, const int32_t* qzeros, void* out_bf16,
+                   int M, int K, int N, int bits, int groupsize, int add_zero_bias, int64_t out_row_stride, void* workspace,
+                   size_t workspace_bytes, int flags, xbit_stream_t stream) {
+  g_err[0] = 0;
+  if (int rc = check_common(qweight, scales_bf16, qzeros, K, N, bits, groupsize, add_zero_bias)) return rc;
+  if (!a_bf16 || !out_bf16 || M < 1 || out_row_stride < N) return fail(XBIT_EINVAL, "bad activation / output arguments");
+  if (bits != 4 || groupsize != 128)
+    return fail(XBIT_EINVAL, "the bf16-native GEMV covers bits=4, groupsize=128 (got %d, %d): convert to fp16 as the reference does", bits, groupsize);
+  const size_t off = persist_ws_offset(2);
+  const bool has = workspace && workspace_bytes > off;
+  for (int m0 = 0; m0 < M; m0 += 2) {                 // the integer block math takes two activation rows per launch
+    xbit::GemvArgs g;
+    memset(&g, 0, sizeof(g));
+    g.bf16 = 1;
+    g.a = reinterpret_cast<const __half*>(a_bf16) + (size_t)m0 * K;
+    g.out[0] = reinterpret_cast<__half*>(out_bf16) + (size_t)m0 * out_row_stride;
+    g.world = 1;
+    g.qweight = reinterpret_cast<const uint32_t*>(qweight);
+    g.scales = reinterpret_cast<const __half*>(scales_bf16);
+    g.qzeros = reinterpret_cast<const uint32_t*>(qzeros);
+    g.M = M - m0 < 2 ? M - m0 : 2; g.K = K; g.N = N; g.bits = bits; g.groupsize = groupsize; g.zero_bias = add_zero_bias;
+    g.ldo = out_row_stride; g.col_offset = 0;
+    g.qrows = ceil_div((long long)K * bits, 32);
+    g.zwords = ceil_div((long long)N * bits, 32);
+    g.groups = ceil_div(K, groupsize);
+    g.static_weights = (flags & XBIT_GEMV_FLAG_STATIC_WEIGHTS) ? 1 : 0;
+    if (!xbit::gemv_w4p_applicable(g))
+      return fail(XBIT_EINVAL, "the bf16-native GEMV needs K%%128=0, N%%32=0, 16-byte aligned pointers and K small enough to stage");
+    const cudaError_t e = xbit::launch_gemv_w4p(g, has ? static_cast<unsigned char*>(workspace) + off : nullptr, has ? workspace_bytes - off : 0,
+                                                reinterpret_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "xbit_gemv_bf16 launch");
+  }
+  return XBIT_OK;
 }
 
 int xbit_gemv_f16_multi(const void* a_f16, const xbit_gemv_problem* problems, int count, int M, int K, int bits, int groupsize,

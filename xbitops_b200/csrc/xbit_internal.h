@@ -17,6 +17,7 @@ struct DqArgs {
   int K, N, bits, groupsize, zero_bias;
   int qrows;   // ceil(K*bits/32)
   int zwords;  // ceil(N*bits/32)
+  int bf16;    // scales and out are bf16, arithmetic out = RN_bf16((w - z) * s) (dq_sm100.cu)
 };
 
 struct GemvArgs {
@@ -31,6 +32,7 @@ struct GemvArgs {
   long long col_offset;     // first output column of this shard
   int qrows, zwords, groups;
   int static_weights;       // XBIT_GEMV_FLAG_STATIC_WEIGHTS: weights may be read before griddepcontrol.wait
+  int bf16;                 // a, scales and out are bf16 (xbit_gemv_bf16: persistent kernel, integer block math only)
   // fused completion signal of the N-split epilogue (xbit_gemv_f16_peers_signal); null = none
   unsigned int* sig_flags[kMaxPeers];   // rank r's flag array [world] as mapped here; this rank writes slot sig_rank
   unsigned int* sig_state;              // local: [0] tiles stored so far, [1] calls published

@@ -71,6 +71,23 @@ def get_static_weights() -> bool:
     return _STATIC_WEIGHTS
 
 
+_NATIVE_BF16 = os.environ.get("XBIT_NATIVE_BF16", "0") not in ("", "0")
+
+
+def set_native_bf16(on: bool) -> None:
+    """bf16 without the fp16 round trip (default False = the reference's behaviour, which converts
+    bf16 scales to fp16, computes in fp16 and casts the result back, dq_torch_ops.cc:33-42, :65-76 -- and loses bf16's
+    range on the way).  When on, `dequant` with bf16 scales returns RN_bf16((w - z) * s) (xbit_dequant_bf16), and `gemv`
+    with bf16 activations AND bf16 scales runs the bf16-native kernel where it exists (bits 4, groupsize 128,
+    K % 128 = 0, N % 32 = 0: xbit_gemv_bf16); every other case keeps the reference's fp16 arithmetic."""
+    global _NATIVE_BF16
+    _NATIVE_BF16 = bool(on)
+
+
+def get_native_bf16() -> bool:
+    return _NATIVE_BF16
+
+
 def gemv_workspace(device: torch.device) -> torch.Tensor:
     """Zero-initialised scratch for the persistent stream-K GEMV schedule (include/xbitops_b200.h:
     xbit_gemv_workspace_bytes), one per (device, stream): calls on one stream are ordered, calls on
@@ -89,6 +106,12 @@ def dequant(qweight, scales, qzeros, groupsize, bits, in_features, add_zero_bias
     _check_quant_args(qweight, scales, qzeros, groupsize, bits, in_features)
     lib = capi.load()
     with torch.cuda.device(qweight.device):
+        if _NATIVE_BF16 and scales.dtype == torch.bfloat16:
+            out = torch.empty((in_features, qweight.size(1)), dtype=torch.bfloat16, device=qweight.device)
+            capi.check(lib.xbit_dequant_bf16(qweight.data_ptr(), scales.data_ptr(), qzeros.data_ptr(), out.data_ptr(),
+                                             in_features, qweight.size(1), bits, groupsize, int(add_zero_bias),
+                                             _stream_handle()))
+            return out
         f16_scale = scales.to(torch.float16) if scales.dtype == torch.bfloat16 else scales
         out = torch.empty((in_features, qweight.size(1)), dtype=torch.float16, device=qweight.device)
         capi.check(lib.xbit_dequant_f16(qweight.data_ptr(), f16_scale.data_ptr(), qzeros.data_ptr(), out.data_ptr(),
@@ -108,7 +131,10 @@ def gemv(input_a, qweight, scales, qzeros, groupsize, bits, in_features, add_zer
     _check_quant_args(qweight, scales, qzeros, groupsize, bits, in_features)
     if qweight.device.index != input_a.device.index:
         raise RuntimeError("input and weight must be on the same device")
-    if input_a.dtype != torch.float16:
+    native = (_NATIVE_BF16 and input_a.dtype == torch.bfloat16 and scales.dtype == torch.bfloat16 and bits == 4 and
+              groupsize == 128 and in_features % 128 == 0 and qweight.size(1) % 32 == 0 and family == capi.GEMV_AUTO and
+              in_features <= 16384)
+    if input_a.dtype != torch.float16 and not native:
         raise RuntimeError("input_a must be float16")
     if input_a.dim() < 2 or input_a.size(-1) != in_features:
         raise RuntimeError("input_a must be [..., in_features]")
@@ -119,6 +145,19 @@ def gemv(input_a, qweight, scales, qzeros, groupsize, bits, in_features, add_zer
     if input_a.dim() > 2:                      # dq_torch_ops.cc:60-64
         outshape.insert(1, input_a.size(1))
         m *= input_a.size(1)
+    if native:
+        with torch.cuda.device(qweight.device):
+            if out is None:
+                out = torch.empty(outshape, dtype=torch.bfloat16, device=qweight.device)
+            elif out.dtype != torch.bfloat16 or not out.is_contiguous() or list(out.shape) != outshape:
+                raise RuntimeError("out must be a contiguous bfloat16 tensor of the result shape")
+            if m > 0:
+                ws = gemv_workspace(qweight.device)
+                capi.check(lib.xbit_gemv_bf16(input_a.data_ptr(), qweight.data_ptr(), scales.data_ptr(), qzeros.data_ptr(),
+                                              out.data_ptr(), m, in_features, n, bits, groupsize, int(add_zero_bias), n,
+                                              ws.data_ptr(), ws.numel(),
+                                              capi.GEMV_FLAG_STATIC_WEIGHTS if _STATIC_WEIGHTS else 0, _stream_handle()))
+        return out
     with torch.cuda.device(qweight.device):
         f16_scale = scales.to(torch.float16) if scales.dtype == torch.bfloat16 else scales
         if out is None:
