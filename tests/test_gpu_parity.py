@@ -626,3 +626,34 @@ def test_gemv_bf16_native_vs_fp64_truth(M, dev):
                 assert err <= 4e-3, (K, N, M, boost, err)
     finally:
         X.set_native_bf16(False)
+
+
+# ------------------------------------------------------------------ A16W8 on the persistent kernel
+
+def test_gemv_w8_persistent_integer_math(dev, c_oracle):
+    """8-bit weights, groupsize 128 (the reference aborts on everything but bits 4, gemv_w4a16_pt.cu:152-155): AUTO routes
+    M <= 2 (and larger batches two rows at a time) to the persistent kernel, whose integer block math takes the packed
+    words as MMA operands unchanged.  Against the fp64 product over the oracle's dequantised weights; both CTA-boundary
+    modes; deterministic; the generic kernel agrees within the tolerance."""
+    lib = capi.load()
+    cases = ((512, 256, 1, 1), (4096, 4096, 1, 0), (4096, 4096, 2, 1), (4096, 11008, 1, 1), (11008, 4096, 2, 0), (1024, 96, 5, 1),
+             (4224, 4128, 3, 0))
+    for (K, N, M, bias) in cases:
+        qw, s, qz, a = synth.make_inputs(K, N, 8, 128, M=M, seed=K + N + M + 8)
+        w = c_oracle.dequant(qw, s, qz, 128, 8, K, bias)
+        y64 = a.astype(np.float64) @ w.astype(np.float64)
+        tq, ts, tz, ta = ti(qw, dev), t16(s, dev), ti(qz, dev), t16(a, dev)
+        assert lib.xbit_gemv_pick_family(min(M, 2), K, N, 8, 128) == capi.GEMV_PERSIST
+        y_auto = X.gemv(ta, tq, ts, tz, 128, 8, K, bias)
+        assert_gemv_close(y_auto.cpu().numpy(), y64, f"W8 AUTO {K}x{N} M={M}")
+        for fine in (1, 0):
+            capi.set_option("XBIT_W4P_FINE", fine)
+            try:
+                y1 = X.gemv(ta, tq, ts, tz, 128, 8, K, bias, family=capi.GEMV_PERSIST)
+                y2 = X.gemv(ta, tq, ts, tz, 128, 8, K, bias, family=capi.GEMV_PERSIST)
+            finally:
+                capi.set_option("XBIT_W4P_FINE")
+            assert torch.equal(y1, y2)
+            assert_gemv_close(y1.cpu().numpy(), y64, f"W8 persist fine={fine} {K}x{N} M={M}")
+        yg = X.gemv(ta, tq, ts, tz, 128, 8, K, bias, family=capi.GEMV_GENERIC)
+        assert float((yg.double() - y_auto.double()).abs().max()) <= 2e-3 * float(np.abs(y64).max())

@@ -1,2 +1,1 @@
-export PTIME_VARIANTS="1 0 0;0 0 0"
-for m in 2 4 8; do python tools/ptime.py --m $m 4096 4096 4096 11008 8192 8192 | grep "persist fine\|==\|cluster\|AUTO"; done
+python -m pytest tests/test_gpu_parity.py -q -m gpu -x -k "w8" 2>&1 | tail -12

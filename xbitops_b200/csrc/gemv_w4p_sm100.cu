@@ -99,13 +99,15 @@ struct W4PMapsN {
 };
 using W4PMaps = W4PMapsN<kPMaxProblems>;
 
-template <int UPG, int BPS>
+template <int UPG, int BPS, int BITS = 4>
 struct W4PCfg {
   static constexpr int GPB = 4 / UPG;                                   // scale groups per 128-k block
-  static constexpr int kBlockBytes = 2048;                              // 16 word-rows x 32 columns
+  static constexpr int kRowsPerBlock = 4 * BITS;                        // word-rows of a 128-k block
+  static constexpr int kBlockBytes = kRowsPerBlock * 128;               // x 32 columns (4 bits: 2 KiB, 8 bits: 4 KiB)
+  static constexpr int kZRow = BITS == 8 ? 32 : 16;                     // bytes of a tile's zero points per group row
   static constexpr int kWSlot = BPS * kBlockBytes;                      // a ring slot holds BPS (1 or 2) consecutive blocks
   static constexpr int kSSlot = BPS * GPB * 64;                         // their scale rows (32 columns x fp16)
-  static constexpr int kZSlot = BPS * GPB * 16;                         // their zero rows (4 words)
+  static constexpr int kZSlot = BPS * GPB * kZRow;                      // their zero rows
 };
 
 __device__ __forceinline__ void cp_async_16(void* dst_smem, const void* src) {
@@ -341,6 +343,75 @@ __device__ __forceinline__ void w4p_consume_i8(const unsigned char* const (&wp)[
   }
 }
 
+// The same for 8-bit weights (A16W8, groupsize 128, M <= 2): a packed word IS an A register -- four consecutive k of one
+// column as four u8 -- so there is no unpack instruction at all; the activations' digit planes are in natural k order and
+// all carry the scale 2^(22-E).  A block is 32 word-rows: per step u a lane takes rows 2(t + 4u), 2(t + 4u) + 1 (eight
+// consecutive k) of its four columns with two 16-byte loads, and the eight digit bytes of those k with one 8-byte load.
+// Largest sum: 255 * 128 * 65535 < 2^31.
+template <int NB, bool BF = false>
+__device__ __forceinline__ void w8p_consume_i8(const unsigned char* const (&wp)[NB], const unsigned char* const (&sp)[NB],
+                                               const unsigned char* const (&zp)[NB], const int (&wrow)[NB],
+                                               const float* const (&gt)[NB], const W4PLaneI& L, float (&tot)[2][2], float (&zc)[2]) {
+  uint2 sraw[NB];
+  uint32_t zraw[NB];
+  float gsv[NB];
+  float2 aq[NB];
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    sraw[b] = *reinterpret_cast<const uint2*>(sp[b] + L.s_off);
+    zraw[b] = *reinterpret_cast<const uint32_t*>(zp[b] + 2 * L.z_off);        // four 8-bit zero points of this lane's columns
+    gsv[b] = *reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(gt[b]) + L.crow4);
+    aq[b] = *reinterpret_cast<const float2*>(gt[b] + 2);
+  }
+  int acc[NB][2][4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    uint4 w1[NB], w2[NB];
+    uint2 bf[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      w1[b] = *reinterpret_cast<const uint4*>(wp[b] + L.w_x0 + u * 1024);
+      w2[b] = *reinterpret_cast<const uint4*>(wp[b] + (L.w_x0 ^ 16u) + 128 + u * 1024);
+      bf[b] = *reinterpret_cast<const uint2*>(L.bptr + (wrow[b] + (L.lane_row >> 1) + 4 * u) * L.bstride);
+    }
+#pragma unroll
+    for (int tt = 0; tt < 2; ++tt)
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        const uint32_t a0 = tt == 0 ? w1[b].x : w1[b].z, a1 = tt == 0 ? w1[b].y : w1[b].w;
+        const uint32_t a2 = tt == 0 ? w2[b].x : w2[b].z, a3 = tt == 0 ? w2[b].y : w2[b].w;
+        if (u == 0) pimma_zero(acc[b][tt], a0, a1, a2, a3, bf[b].x, bf[b].y);
+        else        pimma(acc[b][tt], a0, a1, a2, a3, bf[b].x, bf[b].y);
+      }
+  }
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    const float2 s01 = BF ? make_float2(__uint_as_float(sraw[b].x << 16), __uint_as_float(sraw[b].x & 0xffff0000u)) : __half22float2(u2h2(sraw[b].x));
+    const float2 s23 = BF ? make_float2(__uint_as_float(sraw[b].y << 16), __uint_as_float(sraw[b].y & 0xffff0000u)) : __half22float2(u2h2(sraw[b].y));
+    const float sfg[4] = {s01.x * gsv[b], s01.y * gsv[b], s23.x * gsv[b], s23.y * gsv[b]};
+#pragma unroll
+    for (int tt = 0; tt < 2; ++tt)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int v = acc[b][tt][2 * h] + L.cmul * acc[b][tt][2 * h + 1];
+        tot[tt][h] = fmaf(sfg[2 * tt + h], (float)v, tot[tt][h]);
+      }
+    const uint32_t s16 = prmt(sraw[b].x, sraw[b].y, L.ssel) & 0xffffu;
+    const float sz = (BF ? __uint_as_float(s16 << 16) : __half2float(__ushort_as_half((unsigned short)s16))) *
+                     ((float)((zraw[b] >> (2 * L.zsh)) & 0xFFu) + L.zbias);
+    zc[0] = fmaf(sz, aq[b].x, zc[0]);
+    zc[1] = fmaf(sz, aq[b].y, zc[1]);
+  }
+}
+
+template <int BITS, int NB, bool BF>
+__device__ __forceinline__ void wxp_consume_i8(const unsigned char* const (&wp)[NB], const unsigned char* const (&sp)[NB],
+                                               const unsigned char* const (&zp)[NB], const int (&wrow)[NB],
+                                               const float* const (&gt)[NB], const W4PLaneI& L, float (&tot)[2][2], float (&zc)[2]) {
+  if constexpr (BITS == 8) w8p_consume_i8<NB, BF>(wp, sp, zp, wrow, gt, L, tot, zc);
+  else w4p_consume_i8<NB, BF>(wp, sp, zp, wrow, gt, L, tot, zc);
+}
+
 __device__ __forceinline__ void p_ll_store(unsigned long long* slot, uint32_t data, uint32_t epoch) {
   asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(slot), "r"(data), "r"(epoch) : "memory");
 }
@@ -378,10 +449,12 @@ __device__ __forceinline__ int p_slice_of(int w) { return (w & 3) * (NW / 4) + (
 // 1 = several matrices (xbit_gemv_f16_multi); 2 = also the flag-in-data (LL) input / output forms.
 // BF: bf16-native form (activations, scales and output bf16; integer block math only): the activations' 24-bit fixed
 // point comes from the bf16 exponent, the scales widen by a shift, the result is rounded once, to bf16.
-template <int UPG, int NW, int MODE, bool I8, int BPS, int MINB, int GEN, bool BF = false>
+// BITS: 4, or 8 (A16W8: integer block math only; the packed words are the MMA operands as they are, w8p_consume_i8).
+template <int UPG, int NW, int MODE, bool I8, int BPS, int MINB, int GEN, bool BF = false, int BITS = 4>
 __global__ void __launch_bounds__((NW + 1) * 32, MINB)
 gemv_w4p_kernel(const __grid_constant__ W4PMapsN<(GEN ? kPMaxProblems : 1)> maps, const __grid_constant__ W4PArgsN<(GEN ? kPMaxProblems : 1)> a) {
-  using Cfg = W4PCfg<UPG, BPS>;
+  using Cfg = W4PCfg<UPG, BPS, BITS>;
+  static_assert(BITS == 4 || (BITS == 8 && I8 && GEN == 0), "8-bit weights: integer block math, one matrix per launch");
   const int count = GEN >= 1 ? a.count : 1;
   const bool ll_out = GEN == 2 && a.ll_out, a_is_ll = GEN == 2 && a.a_is_ll;
   constexpr int GPB = Cfg::GPB;
@@ -514,7 +587,7 @@ gemv_w4p_kernel(const __grid_constant__ W4PMapsN<(GEN ? kPMaxProblems : 1)> maps
           if (n >= R) mbar_wait(&empty_bar[w * kPMaxRing + s], ph ^ 1);
           if (sub == 0) {
             mbar_arrive_expect_tx(fb, (uint32_t)(nblk * Cfg::kBlockBytes));
-            tma_load_2d(wring + (w * R + s) * Cfg::kWSlot, &maps.m[2 * pi + (nblk == 2 ? 0 : 1)], tile * 32, kb * 16, fb, policy);
+            tma_load_2d(wring + (w * R + s) * Cfg::kWSlot, &maps.m[2 * pi + (nblk == 2 ? 0 : 1)], tile * 32, kb * Cfg::kRowsPerBlock, fb, policy);
           }
           unsigned char* sdst = sring + (w * R + s) * Cfg::kSSlot + sub * 16;
           unsigned char* zdst = zring + (w * R + s) * Cfg::kZSlot;
@@ -528,7 +601,11 @@ gemv_w4p_kernel(const __grid_constant__ W4PMapsN<(GEN ? kPMaxProblems : 1)> maps
             }
 #pragma unroll
           for (int rr = 0; rr < BPS * GPB; ++rr)
-            if (rr < rows && (rr % LPR) == sub) cp_async_16(zdst + rr * 16, zbase + ((size_t)(row0 + rr) * P.zwords + tile * 4) * 4);
+            if (rr < rows && (rr % LPR) == sub) {
+              // (a tile's zero points of one group: 32 * BITS / 8 bytes)
+              cp_async_16(zdst + rr * Cfg::kZRow, zbase + ((size_t)(row0 + rr) * P.zwords + tile * BITS) * 4);
+              if (BITS == 8) cp_async_16(zdst + rr * Cfg::kZRow + 16, zbase + ((size_t)(row0 + rr) * P.zwords + tile * BITS) * 4 + 16);
+            }
           cp_async_mbar_arrive_noinc(fb);
           j += nblk;
           kb += nblk;
@@ -677,12 +754,18 @@ gemv_w4p_kernel(const __grid_constant__ W4PMapsN<(GEN ? kPMaxProblems : 1)> maps
           const float se = __uint_as_float(((BF ? 275u : 163u) - eb) << 23), so = __uint_as_float(((BF ? 271u : 159u) - eb) << 23);
           const float gs = eb >= (BF ? 255u : 31u) ? __uint_as_float(0x7fc00000u) : __uint_as_float(BF ? (eb - 21u) << 23 : (91u + eb) << 23);
           const float kMagic = 12582912.f;         // 1.5 * 2^23: the bits of (q + kMagic) are 0x4B400000 + q
-          const uint32_t u0 = __float_as_uint(fmaf(f0.x, se, kMagic)), u1 = __float_as_uint(fmaf(f0.y, so, kMagic));
-          const uint32_t u2 = __float_as_uint(fmaf(f1.x, se, kMagic)), u3 = __float_as_uint(fmaf(f1.y, so, kMagic));
-          const uint32_t u4 = __float_as_uint(fmaf(f2.x, se, kMagic)), u5 = __float_as_uint(fmaf(f2.y, so, kMagic));
-          const uint32_t u6 = __float_as_uint(fmaf(f3.x, se, kMagic)), u7 = __float_as_uint(fmaf(f3.y, so, kMagic));
+          // 4-bit weights: (u0, u2, u4, u6) = even k, (u1, u3, u5, u7) = odd k at 1/16 of the scale (the odd nibbles reach the
+          // MMA times 16).  8-bit weights: natural order, one scale: (u0, u2, u4, u6) = k 0..3, (u1, u3, u5, u7) = k 4..7.
+          const float so_ = BITS == 8 ? se : so;
+          const float x1 = BITS == 8 ? f2.x : f0.y, x2 = BITS == 8 ? f0.y : f1.x, x3 = BITS == 8 ? f2.y : f1.y;
+          const float x4 = BITS == 8 ? f1.x : f2.x, x5 = BITS == 8 ? f3.x : f2.y, x6 = BITS == 8 ? f1.y : f3.x;
+          const uint32_t u0 = __float_as_uint(fmaf(f0.x, se, kMagic)), u1 = __float_as_uint(fmaf(x1, so_, kMagic));
+          const uint32_t u2 = __float_as_uint(fmaf(x2, se, kMagic)), u3 = __float_as_uint(fmaf(x3, so_, kMagic));
+          const uint32_t u4 = __float_as_uint(fmaf(x4, se, kMagic)), u5 = __float_as_uint(fmaf(x5, so_, kMagic));
+          const uint32_t u6 = __float_as_uint(fmaf(x6, se, kMagic)), u7 = __float_as_uint(fmaf(f3.y, so_, kMagic));
           // sum_k q_k in units of 2^(E-22), exactly, in integers (|.| <= 2^29): even k + 16 * odd k - 68 * 0x4B400000
-          const int q1 = (int)(((u0 + u2) + (u4 + u6)) + 16u * ((u1 + u3) + (u5 + u7)) - 68u * 0x4B400000u);
+          const int q1 = BITS == 8 ? (int)(((u0 + u2) + (u4 + u6)) + ((u1 + u3) + (u5 + u7)) - 8u * 0x4B400000u)
+                                   : (int)(((u0 + u2) + (u4 + u6)) + 16u * ((u1 + u3) + (u5 + u7)) - 68u * 0x4B400000u);
           int qsum;
           if (a.stage_redux) {
             const int slo = __reduce_add_sync(0xffffffffu, upper ? 0 : q1);
@@ -802,7 +885,7 @@ gemv_w4p_kernel(const __grid_constant__ W4PMapsN<(GEN ? kPMaxProblems : 1)> maps
         const unsigned char* const z0 = my_z + s0 * Cfg::kZSlot;
         const unsigned char* const w1 = BPS == 2 ? w0 + Cfg::kBlockBytes : my_w + s1 * Cfg::kWSlot;      // the step's second block
         const unsigned char* const sc1 = BPS == 2 ? sc0 + GPB * 64 : my_s + s1 * Cfg::kSSlot;
-        const unsigned char* const z1 = BPS == 2 ? z0 + GPB * 16 : my_z + s1 * Cfg::kZSlot;
+        const unsigned char* const z1 = BPS == 2 ? z0 + GPB * Cfg::kZRow : my_z + s1 * Cfg::kZSlot;
         const __half* const a0 = act_sm + (kb + i) * 128;
         const unsigned char* const zt0 = zt_bytes + (size_t)(kb + i) * GPB * zt_group_bytes;
         if constexpr (I8) {
@@ -813,21 +896,21 @@ gemv_w4p_kernel(const __grid_constant__ W4PMapsN<(GEN ? kPMaxProblems : 1)> maps
             const unsigned char* const zp[2] = {z0, z1};
             const int wr[2] = {(kb + i) * 16, (kb + i + 1) * 16};
             const float* const gp[2] = {g0, g0 + 4};
-            w4p_consume_i8<2, BF>(wp, sp, zp, wr, gp, LI, toti, zci);
+            wxp_consume_i8<BITS, 2, BF>(wp, sp, zp, wr, gp, LI, toti, zci);
           } else {
             const unsigned char* const wp[1] = {w0};
             const unsigned char* const sp[1] = {sc0};
             const unsigned char* const zp[1] = {z0};
             const int wr[1] = {(kb + i) * 16};
             const float* const gp[1] = {g0};
-            w4p_consume_i8<1, BF>(wp, sp, zp, wr, gp, LI, toti, zci);
+            wxp_consume_i8<BITS, 1, BF>(wp, sp, zp, wr, gp, LI, toti, zci);
             if (!DUAL && i + 2 <= cnt) {
               const unsigned char* const wp1[1] = {w1};
               const unsigned char* const sp1[1] = {sc1};
               const unsigned char* const zp1[1] = {z1};
               const int wr1[1] = {(kb + i + 1) * 16};
               const float* const gp1[1] = {g0 + 4};
-              w4p_consume_i8<1, BF>(wp1, sp1, zp1, wr1, gp1, LI, toti, zci);
+              wxp_consume_i8<BITS, 1, BF>(wp1, sp1, zp1, wr1, gp1, LI, toti, zci);
             }
           }
         } else if (DUAL && i + 2 <= cnt) {
@@ -1020,12 +1103,12 @@ struct W4PPlan {
   size_t smem;
 };
 
-static size_t w4p_smem_bytes(int upg, int nr, int m, int k, int ring, bool i8, int bps, int count = 1) {
+static size_t w4p_smem_bytes(int upg, int nr, int m, int k, int ring, bool i8, int bps, int count = 1, int bits = 4) {
   const int gpb = 4 / upg;
   const size_t acts = i8 ? (size_t)(k / 128) * 16 + 16 + (size_t)3 * m * (k + 128) + 128      // group table, constants, digit planes
                          : (size_t)(k / 128) * gpb * m * 16 + (size_t)m * (k + 8) * sizeof(__half);   // zt_sm, act_sm
   return 1024                                                        // alignment slack
-         + (size_t)nr * ring * bps * (2048 + 80 * gpb)                // rings of bps-block slots
+         + (size_t)nr * ring * bps * (512 * bits + (64 + (bits == 8 ? 32 : 16)) * gpb)   // rings of bps-block slots
          + (size_t)2 * nr * kPMaxRing * 8 + kPMaxProblems * 48 * 4   // mbarriers, counters, slice boundaries
          + (size_t)count * nr * 2 * m * 32 * sizeof(float)            // part_sm
          + acts;
@@ -1035,8 +1118,17 @@ size_t gemv_w4p_workspace_bytes(int M) {
   return (size_t)device_sm_count() * (size_t)(M < 1 ? 1 : (M > 8 ? 8 : M)) * 32 * sizeof(unsigned long long);
 }
 
+// 8-bit weights on this kernel (A16W8): groupsize 128, M <= 2 (integer block math only), one matrix per launch
+static bool w8p_supported(const GemvArgs& a) {
+  const uintptr_t al = reinterpret_cast<uintptr_t>(a.a) | reinterpret_cast<uintptr_t>(a.qweight) |
+                       reinterpret_cast<uintptr_t>(a.scales) | reinterpret_cast<uintptr_t>(a.qzeros);
+  return a.bits == 8 && a.groupsize == 128 && a.K % 128 == 0 && a.N % 32 == 0 && (al & 15u) == 0 && a.M >= 1 && a.M <= 2 &&
+         !a.bf16 && !a.ll_out && !a.a_is_ll && a.world <= 1;
+}
+
 static bool plan_w4p_nw(const GemvArgs& a, bool have_ws, W4PPlan& p, bool allow16, int count, long long share_all) {
-  if (!gemv_w4_supported(a) || a.M > 8) return false;
+  const bool w8 = w8p_supported(a) && count == 1 && env_int("XBIT_W4P_I8", 1) != 0;
+  if ((!gemv_w4_supported(a) && !w8) || a.M > 8) return false;
   const int sms = device_sm_count();
   const int upg = p_upg_of(a.groupsize);
   const long long tiles = a.N / 32, nb = a.K / 128;
@@ -1056,10 +1148,10 @@ static bool plan_w4p_nw(const GemvArgs& a, bool have_ws, W4PPlan& p, bool allow1
   const bool small = (share_all > 0 ? share_all : share) <= 8 * 2 * 3;   // fits 8 rings of 3 two-block slots
   const bool large = share >= 100 && a.K <= 8192;                   // 16 warps pay off from about 35 MB (8192 x 8192: 8.6 vs 8.7 us, 8192 x 28672: 22.3 vs 23.0)
   const int env_nw = env_int("XBIT_W4P_WARPS", 0);                  // 8 / 16: override (tools/ptime.py)
-  p.nw = env_nw == 16 ? 16 : (env_nw == 8 ? 8 : (large && allow16 ? 16 : 8));
+  p.nw = w8 ? 8 : (env_nw == 16 ? 16 : (env_nw == 8 ? 8 : (large && allow16 ? 16 : 8)));
   const int nr = p.nw;                               // rings
   // integer block math: groupsize 128, M <= 2 (XBIT_W4P_I8=0: the fp16 exact-product math everywhere)
-  const bool i8 = a.groupsize == 128 && a.M <= 2 && env_int("XBIT_W4P_I8", 1) != 0;
+  const bool i8 = w8 || (a.groupsize == 128 && a.M <= 2 && env_int("XBIT_W4P_I8", 1) != 0);
   p.i8 = i8 ? 1 : 0;
   if (a.bf16 && (!i8 || count != 1 || a.ll_out || a.a_is_ll)) return false;   // the bf16-native form: integer block math, one matrix
   // CTA boundaries: block granular (perfect balance, tiles shared between CTAs meet in the workspace) or tile aligned
@@ -1093,17 +1185,17 @@ static bool plan_w4p_nw(const GemvArgs& a, bool have_ws, W4PPlan& p, bool allow1
   // everything else one CTA per SM with the deepest rings that fit (XBIT_W4P_RING overrides, tools/ptime.py)
   const size_t half = 113 * 1024;
   int ring = 0;
-  if (small && nr == 8)
+  if (small && nr == 8 && !w8)
     for (int r = 3; r >= 2 && !ring; --r)
-      if (w4p_smem_bytes(upg, nr, a.M, a.K, r, i8, 2, count) <= half) ring = r;
+      if (w4p_smem_bytes(upg, nr, a.M, a.K, r, i8, 2, count, a.bits) <= half) ring = r;
   for (int r = (nr == 16 ? 2 : 4); r >= 2 && !ring; --r)      // (16 rings: 3 slots measured no better than 2)
-    if (w4p_smem_bytes(upg, nr, a.M, a.K, r, i8, 2, count) <= kMaxDynSmem) ring = r;
+    if (w4p_smem_bytes(upg, nr, a.M, a.K, r, i8, 2, count, a.bits) <= kMaxDynSmem) ring = r;
   if (!ring) return false;
   const int env_ring = env_int("XBIT_W4P_RING", 0);
   if (env_ring >= 2 && env_ring <= kPMaxRing) ring = env_ring;
-  if (w4p_smem_bytes(upg, nr, a.M, a.K, ring, i8, 2, count) > kMaxDynSmem) return false;
+  if (w4p_smem_bytes(upg, nr, a.M, a.K, ring, i8, 2, count, a.bits) > kMaxDynSmem) return false;
   p.ring = ring;
-  p.smem = w4p_smem_bytes(upg, nr, a.M, a.K, ring, i8, 2, count);
+  p.smem = w4p_smem_bytes(upg, nr, a.M, a.K, ring, i8, 2, count, a.bits);
   p.minb = (p.smem <= half && p.nw != 16) ? 2 : 1;
   // AUTO prefers this kernel where it was measured ahead of the cluster split-K kernel: shares that fit the rings (any
   // block math), and with the integer block math every matrix that gets the 4-slot rings
@@ -1116,6 +1208,7 @@ static bool plan_w4p_nw(const GemvArgs& a, bool have_ws, W4PPlan& p, bool allow1
   // (4096 x 11008: M = 4 8.9 against 10.0 us, M = 8 11.8 against 18.0 us; 4096 x 4096 and 8192 x 8192: behind or level)
   if (a.M > 2) p.preferred = !fine && nb <= 32 && tiles >= 2 * sms;
   if (a.K > 16384) p.preferred = false;
+  if (w8) p.preferred = true;                        // (the alternative for 8-bit weights is the generic kernel)
   return true;
 }
 
@@ -1206,10 +1299,10 @@ cudaError_t launch_gemv_w4p_multi(const GemvArgs* gs, int count, void* workspace
     P.ur = (P.total / pi.unit) % p.grid;
     P.ws = pi.unit == 1 ? reinterpret_cast<unsigned long long*>(static_cast<unsigned char*>(workspace) + (size_t)i * region) : nullptr;
     // qweight [qrows, N] u32: box = two blocks (32 word-rows) x 32 columns (128 B), 128-byte swizzle; one block for odd tails
-    cudaError_t e = encode_2d(&maps.m[2 * i], CU_TENSOR_MAP_DATA_TYPE_UINT32, g.qweight, (uint64_t)g.N, (uint64_t)g.qrows, (uint64_t)g.N * 4, 32, 32,
+    cudaError_t e = encode_2d(&maps.m[2 * i], CU_TENSOR_MAP_DATA_TYPE_UINT32, g.qweight, (uint64_t)g.N, (uint64_t)g.qrows, (uint64_t)g.N * 4, 32, (uint32_t)(8 * g.bits),
                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
     if (e != cudaSuccess) return e;
-    e = encode_2d(&maps.m[2 * i + 1], CU_TENSOR_MAP_DATA_TYPE_UINT32, g.qweight, (uint64_t)g.N, (uint64_t)g.qrows, (uint64_t)g.N * 4, 32, 16,
+    e = encode_2d(&maps.m[2 * i + 1], CU_TENSOR_MAP_DATA_TYPE_UINT32, g.qweight, (uint64_t)g.N, (uint64_t)g.qrows, (uint64_t)g.N * 4, 32, (uint32_t)(4 * g.bits),
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
     if (e != cudaSuccess) return e;
   }
@@ -1232,7 +1325,9 @@ cudaError_t launch_gemv_w4p_multi(const GemvArgs* gs, int count, void* workspace
 #define XBIT_W4P_GEN(GEN_)                                                                              \
   XBIT_W4P_CASE(1, false, GEN_) XBIT_W4P_CASE(2, false, GEN_) XBIT_W4P_CASE(4, false, GEN_) XBIT_W4P_CASE(4, true, GEN_)
   const int gen = (a.ll_out || a.a_is_ll) ? 2 : (count > 1 ? 1 : 0);
-  if (g0.bf16) {
+  if (g0.bits == 8) {
+    kern = (const void*)gemv_w4p_kernel<4, 8, 1, true, 2, 1, 0, false, 8>;
+  } else if (g0.bf16) {
     if (p.nw == 16) kern = (const void*)gemv_w4p_kernel<4, 16, 1, true, 2, 1, 0, true>;
     else if (p.minb == 2) kern = (const void*)gemv_w4p_kernel<4, 8, 1, true, 2, 2, 0, true>;
     else kern = (const void*)gemv_w4p_kernel<4, 8, 1, true, 2, 1, 0, true>;

@@ -101,7 +101,7 @@ size_t xbit_gemv_workspace_bytes(int M, int, int, int bits, int) {
   // Optional: with this much zero-initialised scratch the W4 path runs the persistent, perfectly
   // balanced stream-K schedule (partial tiles + ready flags; left zeroed after every call).
   // Without it (NULL / too small) split-K is reduced through cluster shared memory instead.
-  if (bits != 4) return 0;
+  if (bits != 4 && bits != 8) return 0;
   const int m = M > 16 ? 16 : (M < 1 ? 1 : M);
   // two disjoint regions: [0, sk) the stream-K kernel's flags + partial tiles, [sk, sk + pp) the persistent kernel's
   // {partial, flag} slots (the former leaves its partial tiles behind, which must never be read as slots)
@@ -111,6 +111,10 @@ size_t xbit_gemv_workspace_bytes(int M, int, int, int bits, int) {
 static size_t persist_ws_offset(int m) { return (xbit::gemv_w4_streamk_workspace_bytes(m) + 255) / 256 * 256; }
 
 static int pick_family(const xbit::GemvArgs& a) {
+  // 8-bit weights, groupsize 128, M <= 2: the persistent kernel's integer block math (the packed words are the MMA
+  // operands as they are); every other width / group size outside the W4 kernels: the generic kernel
+  if (a.bits == 8 && a.M <= 2 && xbit::env_int("XBIT_GEMV_FAMILY", 0) != XBIT_GEMV_GENERIC && xbit::gemv_w4p_preferred(a))
+    return XBIT_GEMV_PERSIST;
   if (!xbit::gemv_w4_supported(a)) return XBIT_GEMV_GENERIC;
   // Crossover measured on B200 (BASELINE.json configs[4]; profiles/): with the nibble
   // bits fed to the tensor core as fp16 subnormals the mma.sync kernel needs one ALU op per weight
@@ -217,7 +221,10 @@ static int gemv_impl(const void* a_f16, const int32_t* qweight, const void* scal
       for (int slab_try = g.M > 16 ? 16 : g.M; slab_try >= 1; slab_try = slab_try > 1 ? (slab_try + 1) / 2 : 0) {
         probe.M = slab_try;
         const int f = pick_family(probe);
-        if (f == XBIT_GEMV_GENERIC) break;
+        if (f == XBIT_GEMV_GENERIC) {
+          if (g.bits == 8 && slab_try > 2) continue;   // 8-bit weights: the persistent kernel takes two rows per launch
+          break;
+        }
         if (f != XBIT_GEMV_MMA || xbit::gemv_w4_mma_has_plan(probe) || use_streamk(probe, XBIT_GEMV_MMA, workspace, workspace_bytes)) {
           family = f;
           auto_slab = slab_try;
@@ -241,8 +248,10 @@ static int gemv_impl(const void* a_f16, const int32_t* qweight, const void* scal
         else e = xbit::launch_gemv_w4_mma(g, st);
         break;
       case XBIT_GEMV_PERSIST:
-        slab = auto_slab ? auto_slab : (g.M > 8 ? 8 : g.M); g.M = slab;
-        if (!xbit::gemv_w4p_applicable(g)) return fail(XBIT_EINVAL, "PERSIST family needs bits=4, groupsize in {32, 64, 128}, K%%128=0, N%%32=0, 16-byte aligned pointers and M*K small enough to stage");
+        slab = auto_slab ? auto_slab : (g.M > 8 ? 8 : g.M);
+        if (g.bits == 8 && slab > 2) slab = 2;
+        g.M = slab;
+        if (!xbit::gemv_w4p_applicable(g)) return fail(XBIT_EINVAL, "PERSIST family needs bits=4 (groupsize in {32, 64, 128}) or bits=8 (groupsize 128), K%%128=0, N%%32=0, 16-byte aligned pointers and M*K small enough to stage");
         {
           // the persistent kernel's region of the workspace lies behind the stream-K kernel's (xbit_gemv_workspace_bytes)
           const size_t off = persist_ws_offset(g.M);
