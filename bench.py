@@ -615,6 +615,49 @@ def run_gpu_arm(args):
         line["skinny"] = {"shape": "8192x8192", "by_M": skinny}
         del sk, o16
 
+        # (3b) A16W8 (8-bit weights, groupsize 128) on the same shapes: the persistent kernel's integer block math takes
+        #      the packed words as MMA operands unchanged (the reference aborts on bits != 4, gemv_w4a16_pt.cu:152-155)
+        w8 = {}
+        for (K8, N8) in shapes:
+            nb8 = synth.gemv_bytes(K8, N8, 8, GROUP, 1)
+            R8 = max(2, (1 << 30) // nb8 + 1)
+            qw8 = torch.randint(-2**31, 2**31 - 1, (R8, K8 // 4, N8), dtype=torch.int32, device=dev, generator=gen)
+            qz8 = torch.randint(-2**31, 2**31 - 1, (R8, K8 // GROUP, N8 // 4), dtype=torch.int32, device=dev, generator=gen)
+            sc8 = (torch.rand((R8, K8 // GROUP, N8), device=dev, generator=gen) * 0.018 + 0.002).to(torch.float16)
+            a8 = torch.randn((1, K8), device=dev, generator=gen).to(torch.float16)
+            o8 = torch.empty((R8, 1, N8), device=dev, dtype=torch.float16)
+
+            def fn(i, K8=K8, N8=N8, R8=R8, qw8=qw8, qz8=qz8, sc8=sc8, a8=a8, o8=o8):
+                j = i % R8
+                rc = lib.xbit_gemv_f16_ex(a8.data_ptr(), qw8[j].data_ptr(), sc8[j].data_ptr(), qz8[j].data_ptr(), o8[j].data_ptr(),
+                                          1, K8, N8, 8, GROUP, 0, N8, ws_ptr, ws_len, capi.GEMV_AUTO | flags, torch.cuda.current_stream().cuda_stream)
+                if rc != 0:
+                    raise RuntimeError(capi.last_error())
+            us = graph_us(fn, R8)
+            w8[f"{K8}x{N8}"] = {"us_per_call": round(us, 3), "GBps": round(nb8 / us / 1e3, 1), "frac_of_measured_peak": round(nb8 / us / 1e3 / peak, 4),
+                                "family": lib.xbit_gemv_pick_family(1, K8, N8, 8, GROUP)}
+            del qw8, qz8, sc8, o8
+        line["w8"] = {"bits": 8, "groupsize": GROUP, "per_shape": w8}
+
+        # (3c) bf16-native GEMV (bf16 activations, scales and output, no fp16 round trip) on the headline sets
+        bfn = {}
+        for ss in sets:
+            ab = ss.a.to(torch.bfloat16)
+            scb = ss.sc.to(torch.bfloat16)
+            ob = torch.empty((ss.R, 1, ss.N_total), device=dev, dtype=torch.bfloat16)
+
+            def fn(i, ss=ss, ab=ab, scb=scb, ob=ob):
+                j = i % ss.R
+                rc = lib.xbit_gemv_bf16(ab.data_ptr(), ss.qw[j].data_ptr(), scb[j].data_ptr(), ss.qz[j].data_ptr(), ob[j].data_ptr(),
+                                        1, ss.K, ss.N, BITS, GROUP, 0, ss.N_total, ws_ptr, ws_len, flags, torch.cuda.current_stream().cuda_stream)
+                if rc != 0:
+                    raise RuntimeError(capi.last_error())
+            us = graph_us(fn, ss.R)
+            bfn[f"{ss.K}x{ss.N_total}"] = {"us_per_call": round(us, 3), "GBps": round(ss.bytes_call / us / 1e3, 1),
+                                           "frac_of_measured_peak": round(ss.bytes_call / us / 1e3 / peak, 4)}
+            del ab, scb, ob
+        line["bf16_native"] = {"per_shape": bfn, "how": "xbit_gemv_bf16 on the headline weight sets (scales cast to bf16)"}
+
         # (4) configs[2]: dequant to fp16, bits 2..8 x group size 32 / 64 / 128 on 4096 x 11008
         Kd, Nd, Rd = 4096, 11008, 3
         outd = torch.empty((Rd, Kd, Nd), device=dev, dtype=torch.float16)
