@@ -155,7 +155,7 @@ typedef struct xbit_gemv_problem {
 /* bf16-native GEMV (no reference counterpart: the reference computes in fp16 whatever the scales'
  * type, /root/reference/src/dq_torch_ops.cc:65-76): activations, scales and output bf16, fp32 accumulation, ONE rounding
  * of the result to bf16 -- nothing passes through fp16, so scales and activations keep bf16's range.
- * Covers bits = 4, groupsize = 128, K % 128 = 0, N % 32 = 0 (the persistent kernel's integer block math; rows are taken
+ * Covers bits = 4 and 8, groupsize = 128, K % 128 = 0, N % 32 = 0 (the persistent kernel's integer block math; rows are taken
  * two per launch); XBIT_EINVAL otherwise -- the caller then converts to fp16 as the reference does.
  * `flags`: XBIT_GEMV_FLAG_STATIC_WEIGHTS or 0.  Workspace as for xbit_gemv_f16. */
 XBIT_API int xbit_gemv_bf16(const void* a_bf16, const int32_t* qweight, const void* scales_bf16,

@@ -608,29 +608,30 @@ def test_gemv_bf16_native_vs_fp64_truth(M, dev):
     from oracle import oracle as orc
     X.set_native_bf16(True)
     try:
-        for (K, N) in ((512, 256), (4096, 4096), (4096, 11008), (11008, 4096)):
+        for (K, N, bits) in ((512, 256, 4), (4096, 4096, 4), (4096, 11008, 4), (11008, 4096, 4), (512, 256, 8), (4096, 4096, 8), (4224, 4128, 8), (512, 256, 2), (4096, 11008, 2)):
             for boost in (1.0, 2.0 ** 18):
-                qw, s, qz, _ = synth.make_inputs(K, N, 4, 128, seed=K + N + M)
+                qw, s, qz, _ = synth.make_inputs(K, N, bits, 128, seed=K + N + M)
                 sb = (torch.from_numpy(s.astype(np.float32)) * boost).to(torch.bfloat16)
                 gen = torch.Generator().manual_seed(K)
                 a = torch.randn((M, K), generator=gen).to(torch.bfloat16)
-                y = X.gemv(a.to(dev), ti(qw, dev), sb.to(dev), ti(qz, dev), 128, 4, K, 1)
+                y = X.gemv(a.to(dev), ti(qw, dev), sb.to(dev), ti(qz, dev), 128, bits, K, 1)
                 assert y.dtype == torch.bfloat16 and tuple(y.shape) == (M, N)
-                w = orc.np_unpack_qweight(qw, K, 4).astype(np.float64)
-                z = orc.np_unpack_qzeros(qz, N, 4).astype(np.float64) + 1
+                w = orc.np_unpack_qweight(qw, K, bits).astype(np.float64)
+                z = orc.np_unpack_qzeros(qz, N, bits).astype(np.float64) + 1
                 grp = np.arange(K) // 128
                 truth = a.double().numpy() @ ((w - z[grp]) * sb.double().numpy()[grp])
                 got = y.double().cpu().numpy()
                 assert np.isfinite(got).all()
                 err = np.abs(got - truth).max() / np.abs(truth).max()
-                assert err <= 4e-3, (K, N, M, boost, err)
+                assert err <= 4e-3, (K, N, bits, M, boost, err)
     finally:
         X.set_native_bf16(False)
 
 
 # ------------------------------------------------------------------ A16W8 on the persistent kernel
 
-def test_gemv_w8_persistent_integer_math(dev, c_oracle):
+@pytest.mark.parametrize("wbits", (8, 2))
+def test_gemv_w8_persistent_integer_math(wbits, dev, c_oracle):
     """8-bit weights, groupsize 128 (the reference aborts on everything but bits 4, gemv_w4a16_pt.cu:152-155): AUTO routes
     M <= 2 (and larger batches two rows at a time) to the persistent kernel, whose integer block math takes the packed
     words as MMA operands unchanged.  Against the fp64 product over the oracle's dequantised weights; both CTA-boundary
@@ -639,21 +640,21 @@ def test_gemv_w8_persistent_integer_math(dev, c_oracle):
     cases = ((512, 256, 1, 1), (4096, 4096, 1, 0), (4096, 4096, 2, 1), (4096, 11008, 1, 1), (11008, 4096, 2, 0), (1024, 96, 5, 1),
              (4224, 4128, 3, 0))
     for (K, N, M, bias) in cases:
-        qw, s, qz, a = synth.make_inputs(K, N, 8, 128, M=M, seed=K + N + M + 8)
-        w = c_oracle.dequant(qw, s, qz, 128, 8, K, bias)
+        qw, s, qz, a = synth.make_inputs(K, N, wbits, 128, M=M, seed=K + N + M + wbits)
+        w = c_oracle.dequant(qw, s, qz, 128, wbits, K, bias)
         y64 = a.astype(np.float64) @ w.astype(np.float64)
         tq, ts, tz, ta = ti(qw, dev), t16(s, dev), ti(qz, dev), t16(a, dev)
-        assert lib.xbit_gemv_pick_family(min(M, 2), K, N, 8, 128) == capi.GEMV_PERSIST
-        y_auto = X.gemv(ta, tq, ts, tz, 128, 8, K, bias)
-        assert_gemv_close(y_auto.cpu().numpy(), y64, f"W8 AUTO {K}x{N} M={M}")
+        assert lib.xbit_gemv_pick_family(min(M, 2), K, N, wbits, 128) == capi.GEMV_PERSIST
+        y_auto = X.gemv(ta, tq, ts, tz, 128, wbits, K, bias)
+        assert_gemv_close(y_auto.cpu().numpy(), y64, f"W{wbits} AUTO {K}x{N} M={M}")
         for fine in (1, 0):
             capi.set_option("XBIT_W4P_FINE", fine)
             try:
-                y1 = X.gemv(ta, tq, ts, tz, 128, 8, K, bias, family=capi.GEMV_PERSIST)
-                y2 = X.gemv(ta, tq, ts, tz, 128, 8, K, bias, family=capi.GEMV_PERSIST)
+                y1 = X.gemv(ta, tq, ts, tz, 128, wbits, K, bias, family=capi.GEMV_PERSIST)
+                y2 = X.gemv(ta, tq, ts, tz, 128, wbits, K, bias, family=capi.GEMV_PERSIST)
             finally:
                 capi.set_option("XBIT_W4P_FINE")
             assert torch.equal(y1, y2)
-            assert_gemv_close(y1.cpu().numpy(), y64, f"W8 persist fine={fine} {K}x{N} M={M}")
-        yg = X.gemv(ta, tq, ts, tz, 128, 8, K, bias, family=capi.GEMV_GENERIC)
+            assert_gemv_close(y1.cpu().numpy(), y64, f"W{wbits} persist fine={fine} {K}x{N} M={M}")
+        yg = X.gemv(ta, tq, ts, tz, 128, wbits, K, bias, family=capi.GEMV_GENERIC)
         assert float((yg.double() - y_auto.double()).abs().max()) <= 2e-3 * float(np.abs(y64).max())

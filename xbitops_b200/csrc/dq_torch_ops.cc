@@ -129,7 +129,7 @@ torch::Tensor op_gemv(const torch::Tensor& input_a, const torch::Tensor& qweight
   check_quant_args(qweight, scales, qzeros, groupsize, bits, in_features);
   TORCH_CHECK(qweight.device().index() == input_a.device().index(), "input and weight must be on the same device");
   const bool native = g_native_bf16.load() && input_a.scalar_type() == torch::kBFloat16 && scales.scalar_type() == torch::kBFloat16 &&
-                      bits == 4 && groupsize == 128 && in_features % 128 == 0 && qweight.size(1) % 32 == 0 && in_features <= 16384;
+                      (bits == 2 || bits == 4 || bits == 8) && groupsize == 128 && in_features % 128 == 0 && qweight.size(1) % 32 == 0 && in_features <= 16384;
   TORCH_CHECK(native || input_a.scalar_type() == torch::kFloat16, "input_a must be float16");
   TORCH_CHECK(input_a.dim() >= 2 && input_a.size(-1) == in_features, "input_a must be [..., in_features]");
   const c10::cuda::CUDAGuard guard(qweight.device());

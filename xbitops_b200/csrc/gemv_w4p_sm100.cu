@@ -113,6 +113,9 @@ struct W4PCfg {
 __device__ __forceinline__ void cp_async_16(void* dst_smem, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cp_async_8(void* dst_smem, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
 // the mbarrier receives one (pre-counted) arrival when all cp.async issued so far by this thread have landed
 __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -404,11 +407,76 @@ __device__ __forceinline__ void w8p_consume_i8(const unsigned char* const (&wp)[
   }
 }
 
+// ... and for 2-bit weights (A16W2): a packed word is 16 consecutive k; the masks 0x03 << 2c of its bytes are the k with
+// k mod 4 = c as four u8 times 4^c, so one word yields four A registers with no shift (the activations' digit planes carry
+// 4^-c of the scale for those k, see the staging).  A block is 8 word-rows: a lane takes rows t and t + 4 of its four columns.
+template <int NB, bool BF = false>
+__device__ __forceinline__ void w2p_consume_i8(const unsigned char* const (&wp)[NB], const unsigned char* const (&sp)[NB],
+                                               const unsigned char* const (&zp)[NB], const int (&wrow)[NB],
+                                               const float* const (&gt)[NB], const W4PLaneI& L, float (&tot)[2][2], float (&zc)[2]) {
+  uint2 sraw[NB];
+  uint32_t zraw[NB];
+  float gsv[NB];
+  float2 aq[NB];
+  const int t = L.lane_row >> 1;
+  const uint32_t x0 = (uint32_t)(t * 128) + (((L.s_off >> 3) ^ (uint32_t)t) << 4);      // row t, chunk (lane / 4) ^ t
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    sraw[b] = *reinterpret_cast<const uint2*>(sp[b] + L.s_off);
+    zraw[b] = *reinterpret_cast<const unsigned char*>(zp[b] + (L.z_off >> 1));           // four 2-bit zero points of this lane's columns
+    gsv[b] = *reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(gt[b]) + L.crow4);
+    aq[b] = *reinterpret_cast<const float2*>(gt[b] + 2);
+  }
+  int acc[NB][2][4];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    uint4 wv[NB];
+    uint2 bf[NB][2];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      wv[b] = *reinterpret_cast<const uint4*>(wp[b] + (u ? (x0 ^ 64u) + 512u : x0));
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc)
+        bf[b][cc] = *reinterpret_cast<const uint2*>(L.bptr + (wrow[b] + 2 * (t + 4 * u) + cc) * L.bstride);
+    }
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc)
+#pragma unroll
+      for (int tt = 0; tt < 2; ++tt)
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+          const uint32_t ca = tt == 0 ? wv[b].x : wv[b].z, cb = tt == 0 ? wv[b].y : wv[b].w;
+          const uint32_t m0 = 0x03030303u << (4 * cc), m1 = 0x0C0C0C0Cu << (4 * cc);
+          if (u == 0 && cc == 0) pimma_zero(acc[b][tt], ca & m0, cb & m0, ca & m1, cb & m1, bf[b][cc].x, bf[b][cc].y);
+          else                   pimma(acc[b][tt], ca & m0, cb & m0, ca & m1, cb & m1, bf[b][cc].x, bf[b][cc].y);
+        }
+  }
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    const float2 s01 = BF ? make_float2(__uint_as_float(sraw[b].x << 16), __uint_as_float(sraw[b].x & 0xffff0000u)) : __half22float2(u2h2(sraw[b].x));
+    const float2 s23 = BF ? make_float2(__uint_as_float(sraw[b].y << 16), __uint_as_float(sraw[b].y & 0xffff0000u)) : __half22float2(u2h2(sraw[b].y));
+    const float sfg[4] = {s01.x * gsv[b], s01.y * gsv[b], s23.x * gsv[b], s23.y * gsv[b]};
+#pragma unroll
+    for (int tt = 0; tt < 2; ++tt)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int v = acc[b][tt][2 * h] + L.cmul * acc[b][tt][2 * h + 1];
+        tot[tt][h] = fmaf(sfg[2 * tt + h], (float)v, tot[tt][h]);
+      }
+    const uint32_t s16 = prmt(sraw[b].x, sraw[b].y, L.ssel) & 0xffffu;
+    const float sz = (BF ? __uint_as_float(s16 << 16) : __half2float(__ushort_as_half((unsigned short)s16))) *
+                     ((float)((zraw[b] >> (L.zsh >> 1)) & 0x3u) + L.zbias);
+    zc[0] = fmaf(sz, aq[b].x, zc[0]);
+    zc[1] = fmaf(sz, aq[b].y, zc[1]);
+  }
+}
+
 template <int BITS, int NB, bool BF>
 __device__ __forceinline__ void wxp_consume_i8(const unsigned char* const (&wp)[NB], const unsigned char* const (&sp)[NB],
                                                const unsigned char* const (&zp)[NB], const int (&wrow)[NB],
                                                const float* const (&gt)[NB], const W4PLaneI& L, float (&tot)[2][2], float (&zc)[2]) {
   if constexpr (BITS == 8) w8p_consume_i8<NB, BF>(wp, sp, zp, wrow, gt, L, tot, zc);
+  else if constexpr (BITS == 2) w2p_consume_i8<NB, BF>(wp, sp, zp, wrow, gt, L, tot, zc);
   else w4p_consume_i8<NB, BF>(wp, sp, zp, wrow, gt, L, tot, zc);
 }
 
@@ -454,7 +522,7 @@ template <int UPG, int NW, int MODE, bool I8, int BPS, int MINB, int GEN, bool B
 __global__ void __launch_bounds__((NW + 1) * 32, MINB)
 gemv_w4p_kernel(const __grid_constant__ W4PMapsN<(GEN ? kPMaxProblems : 1)> maps, const __grid_constant__ W4PArgsN<(GEN ? kPMaxProblems : 1)> a) {
   using Cfg = W4PCfg<UPG, BPS, BITS>;
-  static_assert(BITS == 4 || (BITS == 8 && I8 && GEN == 0), "8-bit weights: integer block math, one matrix per launch");
+  static_assert(BITS == 4 || ((BITS == 8 || BITS == 2) && I8 && GEN == 0), "2- / 8-bit weights: integer block math, one matrix per launch");
   const int count = GEN >= 1 ? a.count : 1;
   const bool ll_out = GEN == 2 && a.ll_out, a_is_ll = GEN == 2 && a.a_is_ll;
   constexpr int GPB = Cfg::GPB;
@@ -603,8 +671,10 @@ gemv_w4p_kernel(const __grid_constant__ W4PMapsN<(GEN ? kPMaxProblems : 1)> maps
           for (int rr = 0; rr < BPS * GPB; ++rr)
             if (rr < rows && (rr % LPR) == sub) {
               // (a tile's zero points of one group: 32 * BITS / 8 bytes)
-              cp_async_16(zdst + rr * Cfg::kZRow, zbase + ((size_t)(row0 + rr) * P.zwords + tile * BITS) * 4);
-              if (BITS == 8) cp_async_16(zdst + rr * Cfg::kZRow + 16, zbase + ((size_t)(row0 + rr) * P.zwords + tile * BITS) * 4 + 16);
+              const unsigned char* zsrc = zbase + ((size_t)(row0 + rr) * P.zwords + tile * BITS) * 4;
+              if (BITS == 2) cp_async_8(zdst + rr * Cfg::kZRow, zsrc);
+              else cp_async_16(zdst + rr * Cfg::kZRow, zsrc);
+              if (BITS == 8) cp_async_16(zdst + rr * Cfg::kZRow + 16, zsrc + 16);
             }
           cp_async_mbar_arrive_noinc(fb);
           j += nblk;
@@ -756,16 +826,28 @@ gemv_w4p_kernel(const __grid_constant__ W4PMapsN<(GEN ? kPMaxProblems : 1)> maps
           const float kMagic = 12582912.f;         // 1.5 * 2^23: the bits of (q + kMagic) are 0x4B400000 + q
           // 4-bit weights: (u0, u2, u4, u6) = even k, (u1, u3, u5, u7) = odd k at 1/16 of the scale (the odd nibbles reach the
           // MMA times 16).  8-bit weights: natural order, one scale: (u0, u2, u4, u6) = k 0..3, (u1, u3, u5, u7) = k 4..7.
+          // 2-bit weights: k mod 4 = c reaches the MMA times 4^c (the masks 0x03 << 2c of a byte): u_k carries 4^-c of the scale
           const float so_ = BITS == 8 ? se : so;
           const float x1 = BITS == 8 ? f2.x : f0.y, x2 = BITS == 8 ? f0.y : f1.x, x3 = BITS == 8 ? f2.y : f1.y;
           const float x4 = BITS == 8 ? f1.x : f2.x, x5 = BITS == 8 ? f3.x : f2.y, x6 = BITS == 8 ? f1.y : f3.x;
-          const uint32_t u0 = __float_as_uint(fmaf(f0.x, se, kMagic)), u1 = __float_as_uint(fmaf(x1, so_, kMagic));
-          const uint32_t u2 = __float_as_uint(fmaf(x2, se, kMagic)), u3 = __float_as_uint(fmaf(x3, so_, kMagic));
-          const uint32_t u4 = __float_as_uint(fmaf(x4, se, kMagic)), u5 = __float_as_uint(fmaf(x5, so_, kMagic));
-          const uint32_t u6 = __float_as_uint(fmaf(x6, se, kMagic)), u7 = __float_as_uint(fmaf(f3.y, so_, kMagic));
-          // sum_k q_k in units of 2^(E-22), exactly, in integers (|.| <= 2^29): even k + 16 * odd k - 68 * 0x4B400000
-          const int q1 = BITS == 8 ? (int)(((u0 + u2) + (u4 + u6)) + ((u1 + u3) + (u5 + u7)) - 8u * 0x4B400000u)
-                                   : (int)(((u0 + u2) + (u4 + u6)) + 16u * ((u1 + u3) + (u5 + u7)) - 68u * 0x4B400000u);
+          uint32_t u0, u1, u2, u3, u4, u5, u6, u7;
+          int q1;
+          if constexpr (BITS == 2) {
+            const float s1 = se * 0.25f, s2 = so, s3 = so * 0.25f;       // 2^(22-E) / 4, / 16, / 64
+            u0 = __float_as_uint(fmaf(f0.x, se, kMagic)); u1 = __float_as_uint(fmaf(f0.y, s1, kMagic));
+            u2 = __float_as_uint(fmaf(f1.x, s2, kMagic)); u3 = __float_as_uint(fmaf(f1.y, s3, kMagic));
+            u4 = __float_as_uint(fmaf(f2.x, se, kMagic)); u5 = __float_as_uint(fmaf(f2.y, s1, kMagic));
+            u6 = __float_as_uint(fmaf(f3.x, s2, kMagic)); u7 = __float_as_uint(fmaf(f3.y, s3, kMagic));
+            q1 = (int)((u0 + u4) + 4u * (u1 + u5) + 16u * (u2 + u6) + 64u * (u3 + u7) - 170u * 0x4B400000u);
+          } else {
+            u0 = __float_as_uint(fmaf(f0.x, se, kMagic)); u1 = __float_as_uint(fmaf(x1, so_, kMagic));
+            u2 = __float_as_uint(fmaf(x2, se, kMagic)); u3 = __float_as_uint(fmaf(x3, so_, kMagic));
+            u4 = __float_as_uint(fmaf(x4, se, kMagic)); u5 = __float_as_uint(fmaf(x5, so_, kMagic));
+            u6 = __float_as_uint(fmaf(x6, se, kMagic)); u7 = __float_as_uint(fmaf(f3.y, so_, kMagic));
+            // sum_k q_k in units of 2^(E-22), exactly, in integers (|.| <= 2^29): even k + 16 * odd k - 68 * 0x4B400000
+            q1 = BITS == 8 ? (int)(((u0 + u2) + (u4 + u6)) + ((u1 + u3) + (u5 + u7)) - 8u * 0x4B400000u)
+                           : (int)(((u0 + u2) + (u4 + u6)) + 16u * ((u1 + u3) + (u5 + u7)) - 68u * 0x4B400000u);
+          }
           int qsum;
           if (a.stage_redux) {
             const int slo = __reduce_add_sync(0xffffffffu, upper ? 0 : q1);
@@ -777,15 +859,36 @@ gemv_w4p_kernel(const __grid_constant__ W4PMapsN<(GEN ? kPMaxProblems : 1)> maps
             for (int o = 1; o < 16; o <<= 1) qsum += __shfl_xor_sync(0xffffffffu, qsum, o);
           }
           const float sum = (float)qsum * gs;
-          // byte j of (u0, u2, u4, u6) -> even word of plane j, of (u1, u3, u5, u7) -> odd word
-          const uint32_t e02 = prmt(u0, u2, 0x5140), e46 = prmt(u4, u6, 0x5140);
-          const uint32_t o13 = prmt(u1, u3, 0x5140), o57 = prmt(u5, u7, 0x5140);
-          const uint32_t e02h = prmt(u0, u2, 0x0062), e46h = prmt(u4, u6, 0x0062);
-          const uint32_t o13h = prmt(u1, u3, 0x0062), o57h = prmt(u5, u7, 0x0062);
+          uint2 st0, st1, st2;
+          if constexpr (BITS == 2) {
+            // a word-row of 2-bit weights is 16 k = two vectors = a lane pair.  Per plane its record is 16 bytes,
+            // [k mod 4 = 0: k 0 4 8 12][= 1][= 2][= 3]: the even lane (k 0..7) stores the first eight, the odd lane (k 8..15)
+            // the last eight, after one exchange of the two classes the other lane stores
+            const bool odd = (lane & 1) != 0;
+            auto mix = [&](uint32_t own01, uint32_t own23) {
+              const uint32_t recv = __shfl_xor_sync(0xffffffffu, odd ? own01 : own23, 1);
+              const uint32_t x = odd ? recv : own01, y = odd ? own23 : recv;
+              return make_uint2(prmt(x, y, 0x5410), prmt(x, y, 0x7632));
+            };
+            const uint32_t t04 = prmt(u0, u4, 0x5140), t15 = prmt(u1, u5, 0x5140), t26 = prmt(u2, u6, 0x5140), t37 = prmt(u3, u7, 0x5140);
+            const uint32_t h04 = prmt(u0, u4, 0x0062), h15 = prmt(u1, u5, 0x0062), h26 = prmt(u2, u6, 0x0062), h37 = prmt(u3, u7, 0x0062);
+            st0 = mix(prmt(t04, t15, 0x5410), prmt(t26, t37, 0x5410));
+            st1 = mix(prmt(t04, t15, 0x7632), prmt(t26, t37, 0x7632));
+            st2 = mix(prmt(h04, h15, 0x5410), prmt(h26, h37, 0x5410));
+          } else {
+            // byte j of (u0, u2, u4, u6) -> even word of plane j, of (u1, u3, u5, u7) -> odd word
+            const uint32_t e02 = prmt(u0, u2, 0x5140), e46 = prmt(u4, u6, 0x5140);
+            const uint32_t o13 = prmt(u1, u3, 0x5140), o57 = prmt(u5, u7, 0x5140);
+            const uint32_t e02h = prmt(u0, u2, 0x0062), e46h = prmt(u4, u6, 0x0062);
+            const uint32_t o13h = prmt(u1, u3, 0x0062), o57h = prmt(u5, u7, 0x0062);
+            st0 = make_uint2(prmt(e02, e46, 0x5410), prmt(o13, o57, 0x5410));
+            st1 = make_uint2(prmt(e02, e46, 0x7632), prmt(o13, o57, 0x7632));
+            st2 = make_uint2(prmt(e02h, e46h, 0x5410), prmt(o13h, o57h, 0x5410));
+          }
           if (ok) {
-            *reinterpret_cast<uint2*>(pl0 + (size_t)v * 8) = make_uint2(prmt(e02, e46, 0x5410), prmt(o13, o57, 0x5410));
-            *reinterpret_cast<uint2*>(pl1 + (size_t)v * 8) = make_uint2(prmt(e02, e46, 0x7632), prmt(o13, o57, 0x7632));
-            *reinterpret_cast<uint2*>(pl2 + (size_t)v * 8) = make_uint2(prmt(e02h, e46h, 0x5410), prmt(o13h, o57h, 0x5410));
+            *reinterpret_cast<uint2*>(pl0 + (size_t)v * 8) = st0;
+            *reinterpret_cast<uint2*>(pl1 + (size_t)v * 8) = st1;
+            *reinterpret_cast<uint2*>(pl2 + (size_t)v * 8) = st2;
             if ((lane & 15) == 0) {
               gt_sm[(v >> 4) * 4 + m] = gs;
               gt_sm[(v >> 4) * 4 + 2 + m] = sum;
@@ -1118,12 +1221,12 @@ size_t gemv_w4p_workspace_bytes(int M) {
   return (size_t)device_sm_count() * (size_t)(M < 1 ? 1 : (M > 8 ? 8 : M)) * 32 * sizeof(unsigned long long);
 }
 
-// 8-bit weights on this kernel (A16W8): groupsize 128, M <= 2 (integer block math only), one matrix per launch
+// 2- and 8-bit weights on this kernel (A16W2 / A16W8): groupsize 128, M <= 2 (integer block math only), one matrix per launch
 static bool w8p_supported(const GemvArgs& a) {
   const uintptr_t al = reinterpret_cast<uintptr_t>(a.a) | reinterpret_cast<uintptr_t>(a.qweight) |
                        reinterpret_cast<uintptr_t>(a.scales) | reinterpret_cast<uintptr_t>(a.qzeros);
-  return a.bits == 8 && a.groupsize == 128 && a.K % 128 == 0 && a.N % 32 == 0 && (al & 15u) == 0 && a.M >= 1 && a.M <= 2 &&
-         !a.bf16 && !a.ll_out && !a.a_is_ll && a.world <= 1;
+  return (a.bits == 8 || a.bits == 2) && a.groupsize == 128 && a.K % 128 == 0 && a.N % 32 == 0 && (al & 15u) == 0 && a.M >= 1 && a.M <= 2 &&
+         !a.ll_out && !a.a_is_ll && a.world <= 1;
 }
 
 static bool plan_w4p_nw(const GemvArgs& a, bool have_ws, W4PPlan& p, bool allow16, int count, long long share_all) {
@@ -1185,7 +1288,7 @@ static bool plan_w4p_nw(const GemvArgs& a, bool have_ws, W4PPlan& p, bool allow1
   // everything else one CTA per SM with the deepest rings that fit (XBIT_W4P_RING overrides, tools/ptime.py)
   const size_t half = 113 * 1024;
   int ring = 0;
-  if (small && nr == 8 && !w8)
+  if (small && nr == 8 && a.bits != 8)
     for (int r = 3; r >= 2 && !ring; --r)
       if (w4p_smem_bytes(upg, nr, a.M, a.K, r, i8, 2, count, a.bits) <= half) ring = r;
   for (int r = (nr == 16 ? 2 : 4); r >= 2 && !ring; --r)      // (16 rings: 3 slots measured no better than 2)
@@ -1326,7 +1429,10 @@ cudaError_t launch_gemv_w4p_multi(const GemvArgs* gs, int count, void* workspace
   XBIT_W4P_CASE(1, false, GEN_) XBIT_W4P_CASE(2, false, GEN_) XBIT_W4P_CASE(4, false, GEN_) XBIT_W4P_CASE(4, true, GEN_)
   const int gen = (a.ll_out || a.a_is_ll) ? 2 : (count > 1 ? 1 : 0);
   if (g0.bits == 8) {
-    kern = (const void*)gemv_w4p_kernel<4, 8, 1, true, 2, 1, 0, false, 8>;
+    kern = g0.bf16 ? (const void*)gemv_w4p_kernel<4, 8, 1, true, 2, 1, 0, true, 8> : (const void*)gemv_w4p_kernel<4, 8, 1, true, 2, 1, 0, false, 8>;
+  } else if (g0.bits == 2) {
+    if (p.minb == 2) kern = g0.bf16 ? (const void*)gemv_w4p_kernel<4, 8, 1, true, 2, 2, 0, true, 2> : (const void*)gemv_w4p_kernel<4, 8, 1, true, 2, 2, 0, false, 2>;
+    else kern = g0.bf16 ? (const void*)gemv_w4p_kernel<4, 8, 1, true, 2, 1, 0, true, 2> : (const void*)gemv_w4p_kernel<4, 8, 1, true, 2, 1, 0, false, 2>;
   } else if (g0.bf16) {
     if (p.nw == 16) kern = (const void*)gemv_w4p_kernel<4, 16, 1, true, 2, 1, 0, true>;
     else if (p.minb == 2) kern = (const void*)gemv_w4p_kernel<4, 8, 1, true, 2, 2, 0, true>;

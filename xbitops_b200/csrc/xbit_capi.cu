@@ -101,7 +101,7 @@ size_t xbit_gemv_workspace_bytes(int M, int, int, int bits, int) {
   // Optional: with this much zero-initialised scratch the W4 path runs the persistent, perfectly
   // balanced stream-K schedule (partial tiles + ready flags; left zeroed after every call).
   // Without it (NULL / too small) split-K is reduced through cluster shared memory instead.
-  if (bits != 4 && bits != 8) return 0;
+  if (bits != 4 && bits != 8 && bits != 2) return 0;
   const int m = M > 16 ? 16 : (M < 1 ? 1 : M);
   // two disjoint regions: [0, sk) the stream-K kernel's flags + partial tiles, [sk, sk + pp) the persistent kernel's
   // {partial, flag} slots (the former leaves its partial tiles behind, which must never be read as slots)
@@ -113,7 +113,7 @@ static size_t persist_ws_offset(int m) { return (xbit::gemv_w4_streamk_workspace
 static int pick_family(const xbit::GemvArgs& a) {
   // 8-bit weights, groupsize 128, M <= 2: the persistent kernel's integer block math (the packed words are the MMA
   // operands as they are); every other width / group size outside the W4 kernels: the generic kernel
-  if (a.bits == 8 && a.M <= 2 && xbit::env_int("XBIT_GEMV_FAMILY", 0) != XBIT_GEMV_GENERIC && xbit::gemv_w4p_preferred(a))
+  if ((a.bits == 8 || a.bits == 2) && a.M <= 2 && xbit::env_int("XBIT_GEMV_FAMILY", 0) != XBIT_GEMV_GENERIC && xbit::gemv_w4p_preferred(a))
     return XBIT_GEMV_PERSIST;
   if (!xbit::gemv_w4_supported(a)) return XBIT_GEMV_GENERIC;
   // Crossover measured on B200 (BASELINE.json configs[4]; profiles/): with the nibble
@@ -222,7 +222,7 @@ static int gemv_impl(const void* a_f16, const int32_t* qweight, const void* scal
         probe.M = slab_try;
         const int f = pick_family(probe);
         if (f == XBIT_GEMV_GENERIC) {
-          if (g.bits == 8 && slab_try > 2) continue;   // 8-bit weights: the persistent kernel takes two rows per launch
+          if ((g.bits == 8 || g.bits == 2) && slab_try > 2) continue;   // 2- / 8-bit weights: the persistent kernel takes two rows per launch
           break;
         }
         if (f != XBIT_GEMV_MMA || xbit::gemv_w4_mma_has_plan(probe) || use_streamk(probe, XBIT_GEMV_MMA, workspace, workspace_bytes)) {
@@ -249,7 +249,7 @@ static int gemv_impl(const void* a_f16, const int32_t* qweight, const void* scal
         break;
       case XBIT_GEMV_PERSIST:
         slab = auto_slab ? auto_slab : (g.M > 8 ? 8 : g.M);
-        if (g.bits == 8 && slab > 2) slab = 2;
+        if ((g.bits == 8 || g.bits == 2) && slab > 2) slab = 2;
         g.M = slab;
         if (!xbit::gemv_w4p_applicable(g)) return fail(XBIT_EINVAL, "PERSIST family needs bits=4 (groupsize in {32, 64, 128}) or bits=8 (groupsize 128), K%%128=0, N%%32=0, 16-byte aligned pointers and M*K small enough to stage");
         {
@@ -299,8 +299,8 @@ int xbit_gemv_bf16(const void* a_bf16, const int32_t* qweight, const void* scale
   g_err[0] = 0;
   if (int rc = check_common(qweight, scales_bf16, qzeros, K, N, bits, groupsize, add_zero_bias)) return rc;
   if (!a_bf16 || !out_bf16 || M < 1 || out_row_stride < N) return fail(XBIT_EINVAL, "bad activation / output arguments");
-  if (bits != 4 || groupsize != 128)
-    return fail(XBIT_EINVAL, "the bf16-native GEMV covers bits=4, groupsize=128 (got %d, %d): convert to fp16 as the reference does", bits, groupsize);
+  if ((bits != 4 && bits != 8 && bits != 2) || groupsize != 128)
+    return fail(XBIT_EINVAL, "the bf16-native GEMV covers bits 2, 4 and 8, groupsize=128 (got %d, %d): convert to fp16 as the reference does", bits, groupsize);
   const size_t off = persist_ws_offset(2);
   const bool has = workspace && workspace_bytes > off;
   for (int m0 = 0; m0 < M; m0 += 2) {                 // the integer block math takes two activation rows per launch

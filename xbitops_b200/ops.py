@@ -131,7 +131,7 @@ def gemv(input_a, qweight, scales, qzeros, groupsize, bits, in_features, add_zer
     _check_quant_args(qweight, scales, qzeros, groupsize, bits, in_features)
     if qweight.device.index != input_a.device.index:
         raise RuntimeError("input and weight must be on the same device")
-    native = (_NATIVE_BF16 and input_a.dtype == torch.bfloat16 and scales.dtype == torch.bfloat16 and bits == 4 and
+    native = (_NATIVE_BF16 and input_a.dtype == torch.bfloat16 and scales.dtype == torch.bfloat16 and bits in (2, 4, 8) and
               groupsize == 128 and in_features % 128 == 0 and qweight.size(1) % 32 == 0 and family == capi.GEMV_AUTO and
               in_features <= 16384)
     if input_a.dtype != torch.float16 and not native:

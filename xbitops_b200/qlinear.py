@@ -149,7 +149,7 @@ class QLinear(torch.nn.Module):
         if rows <= self.gemv_max_rows:
             # (bf16 layers keep bf16 activations when the bf16-native kernels are switched on, ops.set_native_bf16; the
             # op falls back to the reference's fp16 arithmetic where no native kernel exists)
-            native = (ops.get_native_bf16() and self.scales.dtype == torch.bfloat16 and self.bits == 4 and self.groupsize == 128
+            native = (ops.get_native_bf16() and self.scales.dtype == torch.bfloat16 and self.bits in (2, 4, 8) and self.groupsize == 128
                       and self.in_features % 128 == 0 and self.out_features % 32 == 0 and self.in_features <= 16384)
             xin = x2.to(torch.bfloat16 if native else torch.float16).contiguous()
             y = ops.gemv(xin, self.qweight, self.scales, self.qzeros, self.groupsize, self.bits,
