@@ -1352,77 +1352,124 @@ gemv_w4_tc5_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_consta
 
 // ------------------------------------------------------------------------------------------------
 // generic: any bits / groupsize / M / N.  One column per thread, 32 columns x 8 K-slices per CTA.
-__global__ void __launch_bounds__(kThreads)
+// A 32-k unit of a column is exactly BITS packed words: they are loaded together (and the next unit's before this one
+// is unpacked -- the loop was bound by one dependent global load per word), every field position is a compile-time
+// constant (shift + mask, a funnel shift where a field straddles two words), the activations come eight k at a time as
+// one 16-byte load per batch row (every lane the same address), and the group boundary is tracked as a k value: no
+// division and no run-time indexed word array in the loop.  8-bit 4096 x 11008: 238 -> 128 (vector activations) -> see
+// profiles/r02_pw8_generic_kernel.log.
+// (scale and effective zero point of (group g, column n); kept out of line: it is reached once per group from 32
+// unrolled call sites)
+template <int BITS>
+__device__ __noinline__ float2 generic_group_params(const __half* scales, const uint32_t* qzeros, int g, int n, int N, int zwords, int zero_bias) {
+  constexpr uint32_t mask = (1u << BITS) - 1u;
+  const float s = __half2float(scales[(size_t)g * N + n]);
+  const int zpos = n * BITS, zi = zpos >> 5, zsh = zpos & 31;
+  const uint32_t zlo = __ldg(qzeros + (size_t)g * zwords + zi);
+  const uint32_t zhi = (zsh + BITS > 32 && zi + 1 < zwords) ? __ldg(qzeros + (size_t)g * zwords + zi + 1) : 0u;
+  return make_float2(s, (float)((__funnelshift_r(zlo, zhi, zsh) & mask) + (uint32_t)zero_bias));
+}
+
+// NWARPS K-slices (warps) per CTA: the loop is a chain of dependent latencies, so what counts is warps per SM: 16 per CTA
+// when N / 32 CTAs do not give every SM at least two CTAs, 8 otherwise (three CTAs of 8 warps fit an SM, one of 16)
+template <int BITS, int MC, int NWARPS>
+__global__ void __launch_bounds__(NWARPS * 32)
 gemv_generic_kernel(const GemvArgs a, int m_base) {
-  __shared__ float red[kWarps][4][32];
+  __shared__ float red[NWARPS][4][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n = blockIdx.x * 32 + lane;
   const bool valid = n < a.N;
-  const int bits = a.bits;
-  const uint32_t mask = (1u << bits) - 1u;
+  constexpr uint32_t mask = (1u << BITS) - 1u;
   const int total_units = (a.K + 31) >> 5;
-  const int wq = (total_units + kWarps - 1) / kWarps;
+  const int wq = (total_units + NWARPS - 1) / NWARPS;
   const int my0 = min(warp * wq, total_units), my1 = min(my0 + wq, total_units);
-  const int mcount = min(4, a.M - m_base);
+  const int mcount = min(MC, a.M - m_base);
+  const int groups = (a.K + a.groupsize - 1) / a.groupsize;
 
-  float tot[4] = {0.f, 0.f, 0.f, 0.f};
-  float dsum[4] = {0.f, 0.f, 0.f, 0.f};   // sum a_k * w_k inside the current group
-  float asum[4] = {0.f, 0.f, 0.f, 0.f};   // sum a_k inside the current group
-  int cur_g = -1;
+  float tot[MC], dsum[MC], asum[MC];      // dsum / asum: sum a_k * w_k and sum a_k inside the current group
+#pragma unroll
+  for (int m = 0; m < MC; ++m) tot[m] = dsum[m] = asum[m] = 0.f;
   float s = 0.f, z = 0.f;
+  const bool vec_ok = (a.K % 8 == 0) && ((reinterpret_cast<uintptr_t>(a.a) & 15u) == 0);
   griddep_wait();
-  if (valid) {
+  if (valid && my0 < my1) {
+    auto load_unit = [&](int u, uint32_t (&w)[BITS]) {
+#pragma unroll
+      for (int j = 0; j < BITS; ++j) {
+        const int row = u * BITS + j;
+        w[j] = (u < my1 && row < a.qrows) ? __ldg(a.qweight + (size_t)row * a.N + n) : 0u;
+      }
+    };
+    int g = (my0 * 32) / a.groupsize;
+    int next_gk = (g + 1) * a.groupsize;
+    {
+      const float2 p = generic_group_params<BITS>(a.scales, a.qzeros, g, n, a.N, a.zwords, a.zero_bias);
+      s = p.x; z = p.y;
+    }
+    uint32_t wnext[BITS];
+    load_unit(my0, wnext);
     for (int u = my0; u < my1; ++u) {
-      unsigned long long buf = 0;
-      int avail = 0, next_word = u * bits;
-      for (int i = 0; i < 32; ++i) {
-        const int k = u * 32 + i;
-        if (k >= a.K) break;
-        if (avail < bits) {
-          const uint32_t wd = next_word < a.qrows ? __ldg(a.qweight + (size_t)next_word * a.N + n) : 0u;
-          buf |= (unsigned long long)wd << avail;
-          avail += 32;
-          ++next_word;
-        }
-        const float wv = (float)(uint32_t)(buf & mask);
-        buf >>= bits;
-        avail -= bits;
-        const int g = k / a.groupsize;
-        if (g != cur_g) {
-          if (cur_g >= 0) {
+      uint32_t w[BITS];
 #pragma unroll
-            for (int m = 0; m < 4; ++m) { tot[m] = fmaf(s, dsum[m] - z * asum[m], tot[m]); dsum[m] = 0.f; asum[m] = 0.f; }
+      for (int j = 0; j < BITS; ++j) w[j] = wnext[j];
+      load_unit(u + 1, wnext);
+#pragma unroll
+      for (int i8 = 0; i8 < 32; i8 += 8) {
+        const int kk = u * 32 + i8;
+        if (kk < a.K) {
+          // (activations beyond K read as 0: the fields there contribute nothing, whatever the packer left in them)
+          float av[MC][8];
+#pragma unroll
+          for (int m = 0; m < MC; ++m) {
+            const __half* arow = a.a + (size_t)(m_base + (m < mcount ? m : 0)) * a.K + kk;
+            if (vec_ok) {
+              const uint4 v = __ldg(reinterpret_cast<const uint4*>(arow));
+              const float2 f0 = __half22float2(u2h2(v.x)), f1 = __half22float2(u2h2(v.y));
+              const float2 f2 = __half22float2(u2h2(v.z)), f3 = __half22float2(u2h2(v.w));
+              av[m][0] = f0.x; av[m][1] = f0.y; av[m][2] = f1.x; av[m][3] = f1.y;
+              av[m][4] = f2.x; av[m][5] = f2.y; av[m][6] = f3.x; av[m][7] = f3.y;
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) av[m][j] = kk + j < a.K ? __half2float(arow[j]) : 0.f;
+            }
           }
-          cur_g = g;
-          s = __half2float(a.scales[(size_t)g * a.N + n]);
-          const int zpos = n * bits, zi = zpos >> 5, zsh = zpos & 31;
-          const uint32_t zlo = __ldg(a.qzeros + (size_t)g * a.zwords + zi);
-          const uint32_t zhi = (zsh + bits > 32 && zi + 1 < a.zwords) ? __ldg(a.qzeros + (size_t)g * a.zwords + zi + 1) : 0u;
-          z = (float)((__funnelshift_r(zlo, zhi, zsh) & mask) + (uint32_t)a.zero_bias);
-        }
 #pragma unroll
-        for (int m = 0; m < 4; ++m) {
-          if (m < mcount) {
-            const float av = __half2float(a.a[(size_t)(m_base + m) * a.K + k]);
-            dsum[m] = fmaf(av, wv, dsum[m]);
-            asum[m] += av;
+          for (int j = 0; j < 8; ++j) {
+            const int k = kk + j;
+            constexpr int dummy = 0; (void)dummy;
+            const int pos = (i8 + j) * BITS, wi = pos >> 5, sh = pos & 31;      // compile-time after unrolling
+            uint32_t f;
+            if (sh + BITS <= 32) f = (w[wi] >> sh) & mask;
+            else f = __funnelshift_r(w[wi], w[wi + 1 < BITS ? wi + 1 : wi], sh) & mask;
+            const float wv = (float)f;
+            if (k == next_gk) {
+#pragma unroll
+              for (int m = 0; m < MC; ++m) { tot[m] = fmaf(s, dsum[m] - z * asum[m], tot[m]); dsum[m] = 0.f; asum[m] = 0.f; }
+              g = min(g + 1, groups - 1);
+              next_gk += a.groupsize;
+              const float2 p = generic_group_params<BITS>(a.scales, a.qzeros, g, n, a.N, a.zwords, a.zero_bias);
+              s = p.x; z = p.y;
+            }
+#pragma unroll
+            for (int m = 0; m < MC; ++m) {
+              dsum[m] = fmaf(av[m][j], wv, dsum[m]);
+              asum[m] += av[m][j];
+            }
           }
         }
       }
     }
-    if (cur_g >= 0) {
 #pragma unroll
-      for (int m = 0; m < 4; ++m) tot[m] = fmaf(s, dsum[m] - z * asum[m], tot[m]);
-    }
+    for (int m = 0; m < MC; ++m) tot[m] = fmaf(s, dsum[m] - z * asum[m], tot[m]);
   }
 #pragma unroll
-  for (int m = 0; m < 4; ++m) red[warp][m][lane] = tot[m];
+  for (int m = 0; m < 4; ++m) red[warp][m][lane] = m < MC ? tot[m < MC ? m : 0] : 0.f;
   __syncthreads();
   if (warp < mcount && valid) {
     const int m = warp;
     float v = 0.f;
 #pragma unroll
-    for (int w = 0; w < kWarps; ++w) v += red[w][m][lane];
+    for (int w = 0; w < NWARPS; ++w) v += red[w][m][lane];
     const __half h = __float2half_rn(v);
     const size_t off = (size_t)(m_base + m) * a.ldo + a.col_offset + n;
     for (int p = 0; p < a.world; ++p) a.out[p][off] = h;
@@ -2009,7 +2056,19 @@ cudaError_t launch_gemv_w4_tc5(GemvArgs a, cudaStream_t stream) {
 cudaError_t launch_gemv_generic(GemvArgs a, cudaStream_t stream) {
   const unsigned grid = (unsigned)((a.N + 31) / 32);
   for (int m0 = 0; m0 < a.M; m0 += 4) {
-    gemv_generic_kernel<<<grid, kThreads, 0, stream>>>(a, m0);
+    const bool one = a.M - m0 == 1;
+    const bool wide = grid < 2u * (unsigned)device_sm_count();
+    switch (a.bits) {
+#define XBIT_GENERIC_CASE(B_) case B_:                                                              \
+      if (one && wide) gemv_generic_kernel<B_, 1, 16><<<grid, 512, 0, stream>>>(a, m0);              \
+      else if (one) gemv_generic_kernel<B_, 1, 8><<<grid, 256, 0, stream>>>(a, m0);                  \
+      else if (wide) gemv_generic_kernel<B_, 4, 16><<<grid, 512, 0, stream>>>(a, m0);                \
+      else gemv_generic_kernel<B_, 4, 8><<<grid, 256, 0, stream>>>(a, m0);                           \
+      break;
+      XBIT_GENERIC_CASE(2) XBIT_GENERIC_CASE(3) XBIT_GENERIC_CASE(4) XBIT_GENERIC_CASE(5) XBIT_GENERIC_CASE(6) XBIT_GENERIC_CASE(7) XBIT_GENERIC_CASE(8)
+#undef XBIT_GENERIC_CASE
+      default: return cudaErrorInvalidValue;
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
