@@ -47,6 +47,14 @@ def test_validation_errors_without_gpu():
     assert lib.xbit_gemv_f16(one, one, one, one, one, 1, 128, 64, 4, 128, 2, 64, None, 0, None) == -1
     assert lib.xbit_gemv_workspace_bytes(1, 4096, 4096, 4, 128) > 0       # optional stream-K scratch (W4 only)
     assert lib.xbit_gemv_workspace_bytes(1, 4096, 4096, 3, 128) == 0
+    assert lib.xbit_gemv_workspace_bytes(1, 4096, 4096, 8, 128) > 0       # 8- and 2-bit weights run the persistent kernel too
+    # bf16-native forms: same validation; the GEMV covers bits 2 / 4 / 8 at groupsize 128 only
+    assert lib.xbit_dequant_bf16(one, one, one, one, 128, 64, 9, 128, 0, None) == -1
+    assert lib.xbit_dequant_bf16(one, one, one, None, 128, 64, 4, 128, 0, None) == -1
+    assert lib.xbit_gemv_bf16(one, one, one, one, one, 1, 128, 64, 4, 64, 0, 64, None, 0, 0, None) == -1
+    assert "groupsize" in capi.last_error()
+    assert lib.xbit_gemv_bf16(one, one, one, one, one, 1, 128, 64, 3, 128, 0, 64, None, 0, 0, None) == -1
+    assert lib.xbit_gemv_bf16(one, one, one, one, one, 1, 128, 64, 4, 128, 0, 32, None, 0, 0, None) == -1
 
 
 def test_ops_reject_cpu_tensors():

@@ -1513,7 +1513,7 @@ Option g_options[] = {
     {"XBIT_GEMV_SPLITS", {0}, {false}},  {"XBIT_GEMV_RING", {0}, {false}},    {"XBIT_W4P_WARPS", {0}, {false}},
     {"XBIT_W4P_I8", {0}, {false}},       {"XBIT_W4P_FINE", {0}, {false}},     {"XBIT_W4P_GRID", {0}, {false}},
     {"XBIT_W4P_RING", {0}, {false}},     {"XBIT_W4P_ALLWAIT", {0}, {false}},
-    {"XBIT_W4P_DELAY", {0}, {false}},    {"XBIT_W4P_REDUX", {0}, {false}},    {"XBIT_DQ_SMEM_KB", {0}, {false}},
+    {"XBIT_W4P_DELAY", {0}, {false}},    {"XBIT_DQ_SMEM_KB", {0}, {false}},
     {"XBIT_GEMV_DEBUG_SKIP", {0}, {false}}, {"XBIT_LL_PERSIST", {0}, {false}},
 };
 std::once_flag g_options_once;

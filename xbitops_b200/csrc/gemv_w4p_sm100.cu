@@ -72,7 +72,6 @@ struct W4PArgsN {
   int ring;                 // slots per ring
   int static_weights;
   int all_wait;             // every consumer warp executes griddepcontrol.wait (comparison knob)
-  int stage_redux;          // group reductions of the activation staging with REDUX instead of shuffle trees (A/B knob)
   int prefetch_delay;       // SM clocks the producer waits before its first request (only when it starts ahead of the wait)
   // flag-in-data ("LL") form of the N-split exchange (xbit_gemv_f16_peers_ll, see gemv_sm100.cu): results leave as 8-byte
   // {two fp16 results, call number} stores into every rank's buffer; activations may arrive the same way
@@ -808,16 +807,9 @@ gemv_w4p_kernel(const __grid_constant__ W4PMapsN<(GEN ? kPMaxProblems : 1)> maps
           // (full-warp REDUX twice, one per half: a half-warp mask makes the compiler serialise the halves)
           const bool upper = (lane & 16) != 0;
           const uint32_t amax1 = max(am2 & 0xFFFFu, am2 >> 16);
-          uint32_t amax;
-          if (a.stage_redux) {
-            const uint32_t mlo = __reduce_max_sync(0xffffffffu, upper ? 0u : amax1);
-            const uint32_t mhi = __reduce_max_sync(0xffffffffu, upper ? amax1 : 0u);
-            amax = upper ? mhi : mlo;
-          } else {
-            amax = amax1;
-#pragma unroll
-            for (int o = 1; o < 16; o <<= 1) amax = max(amax, __shfl_xor_sync(0xffffffffu, amax, o));
-          }
+          const uint32_t mlo = __reduce_max_sync(0xffffffffu, upper ? 0u : amax1);
+          const uint32_t mhi = __reduce_max_sync(0xffffffffu, upper ? amax1 : 0u);
+          const uint32_t amax = upper ? mhi : mlo;
           // |a| < 2^E with E = exponent field - 14; q = a * 2^(22-E) (odd k: 2^(18-E)); inf / nan activations poison the group
           // (bf16: |a| < 2^E with E = exponent field - 126; fields below 22 -- |a| < 2^-104 -- share the scale of 22)
           const uint32_t eb = BF ? max(amax >> 7, 22u) : amax >> 10;
@@ -848,16 +840,9 @@ gemv_w4p_kernel(const __grid_constant__ W4PMapsN<(GEN ? kPMaxProblems : 1)> maps
             q1 = BITS == 8 ? (int)(((u0 + u2) + (u4 + u6)) + ((u1 + u3) + (u5 + u7)) - 8u * 0x4B400000u)
                            : (int)(((u0 + u2) + (u4 + u6)) + 16u * ((u1 + u3) + (u5 + u7)) - 68u * 0x4B400000u);
           }
-          int qsum;
-          if (a.stage_redux) {
-            const int slo = __reduce_add_sync(0xffffffffu, upper ? 0 : q1);
-            const int shi = __reduce_add_sync(0xffffffffu, upper ? q1 : 0);
-            qsum = upper ? shi : slo;
-          } else {
-            qsum = q1;
-#pragma unroll
-            for (int o = 1; o < 16; o <<= 1) qsum += __shfl_xor_sync(0xffffffffu, qsum, o);
-          }
+          const int slo = __reduce_add_sync(0xffffffffu, upper ? 0 : q1);
+          const int shi = __reduce_add_sync(0xffffffffu, upper ? q1 : 0);
+          const int qsum = upper ? shi : slo;
           const float sum = (float)qsum * gs;
           uint2 st0, st1, st2;
           if constexpr (BITS == 2) {
@@ -1365,7 +1350,6 @@ cudaError_t launch_gemv_w4p_multi(const GemvArgs* gs, int count, void* workspace
   a.static_weights = g0.static_weights;
   a.all_wait = env_int("XBIT_W4P_ALLWAIT", 0);
   a.prefetch_delay = env_int("XBIT_W4P_DELAY", 0);
-  a.stage_redux = env_int("XBIT_W4P_REDUX", 1);
   a.count = count;
   a.nb_shift = 31;
   while ((1ll << (a.nb_shift - 31)) < a.nb) ++a.nb_shift;          // 2^nb_shift > 2^30 * nb >= j * nb
