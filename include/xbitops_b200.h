@@ -68,7 +68,7 @@ enum {
   XBIT_GEMV_MMA = 2,      /* W4 tensor-core kernel: register-level unpack straight into mma.sync
                              m16n8k16 fragments, fp32 accumulation, M <= 16                          */
   XBIT_GEMV_GENERIC = 3,  /* any bits 2..8, any groupsize >= 16, any M: SIMT, fp32 accumulation      */
-  XBIT_GEMV_TCGEN05 = 4,  /* W4 g128, M <= 16: tcgen05.mma with the unpacked weights in TMEM          */
+  /* 4: the tcgen05 / TMEM family of round 1 -- removed (measured behind the mma.sync kernels at every M) */
   XBIT_GEMV_PERSIST = 5   /* W4, M <= 8: one persistent CTA per SM, per-warp TMA rings, block-granular
                              stream-K (same tensor-core block math as XBIT_GEMV_MMA); AUTO's choice
                              wherever it applies                                                       */

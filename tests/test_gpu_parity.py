@@ -142,7 +142,7 @@ def test_dequant_bf16_scales_and_full_size_properties(dev):
 # ------------------------------------------------------------------ gemv
 
 FAMILIES = [(capi.GEMV_SIMT, (1, 3)), (capi.GEMV_MMA, (1, 2, 7, 8, 9, 16)), (capi.GEMV_GENERIC, (1, 5)),
-            (capi.GEMV_TCGEN05, (1, 2, 5, 8, 11, 16)), (capi.GEMV_PERSIST, (1, 2, 3, 5, 8))]
+            (capi.GEMV_PERSIST, (1, 2, 3, 5, 8))]
 
 
 @pytest.mark.parametrize("family,Ms", FAMILIES)
@@ -153,8 +153,6 @@ def test_gemv_w4_families_vs_truth(family, Ms, dev, c_oracle):
             w = c_oracle.dequant(qw, s, qz, g, 4, K, bias)
             tq, ts, tz = ti(qw, dev), t16(s, dev), ti(qz, dev)
             for M in Ms:
-                if family == capi.GEMV_TCGEN05 and g != 128:
-                    continue                     # the tcgen05 family covers groupsize 128 (others: mma.sync family)
                 if family == capi.GEMV_PERSIST and M * K > 8 * 8192:
                     continue                     # M * K too large to stage in one SM's shared memory: AUTO uses the cluster kernel
                 y64 = a[:M].astype(np.float64) @ w.astype(np.float64)
@@ -319,7 +317,7 @@ def test_gemv_full_size_properties(K, N, dev):
     a = torch.randn((4, K), device=dev, generator=gen).to(torch.float16)
     w = X.dequant(qw, s, qz, g, bits, K, 1)
     truth = (a.double() @ w.double()).cpu().numpy()
-    for fam in (capi.GEMV_SIMT, capi.GEMV_MMA, capi.GEMV_TCGEN05, capi.GEMV_PERSIST):
+    for fam in (capi.GEMV_SIMT, capi.GEMV_MMA, capi.GEMV_PERSIST):
         y = X.gemv(a, qw, s, qz, g, bits, K, 1, family=fam)
         assert_gemv_close(y.cpu().numpy(), truth, f"{K}x{N} family {fam}", floor_of(fam))
         if fam == capi.GEMV_PERSIST:

@@ -15,19 +15,12 @@ lib = capi.load()
 PEAK = 6549.8
 K = N = 8192
 R, qw, sc, qz, a, out, nbytes1 = sweep.make(K, N)
-# correctness of the tcgen05 family at M = 12, 16 against a @ dequant
-import xbitops_b200 as X  # noqa: E402
-w = X.dequant(qw[0], sc[0], qz[0], 128, 4, K, 0)
-for M in (9, 12, 16):
-    y = X.gemv(a[:M], qw[0], sc[0], qz[0], 128, 4, K, 0, family=capi.GEMV_TCGEN05)
-    truth = a[:M].double() @ w.double()
-    print(f"tcgen05 M={M}: normalised err {float((y.double() - truth).abs().max() / truth.abs().max()):.3e}")
 print(f"== skinny GEMM {K}x{N}, bits 4, g128 (roofline {nbytes1/PEAK/1e3:.2f} us at M=1)")
 for M in (1, 2, 3, 4, 6, 8, 12, 16):
     nb = synth.gemv_bytes(K, N, 4, 128, M)
     row = f"   M={M:2d}:"
-    for fam, name in ((capi.GEMV_SIMT, "simt"), (capi.GEMV_MMA, "mma.sync"), (capi.GEMV_TCGEN05, "tcgen05")):
-        if fam == capi.GEMV_SIMT and M > 2:
+    for fam, name in ((capi.GEMV_SIMT, "simt"), (capi.GEMV_MMA, "mma.sync"), (capi.GEMV_PERSIST, "persist")):
+        if (fam == capi.GEMV_SIMT and M > 2) or (fam == capi.GEMV_PERSIST and M > 8):
             continue
 
         def fn(i):

@@ -1,6 +1,6 @@
 """Small invocations of every kernel family for compute-sanitizer (tools/sanitize.sh): dequant block / element kernels,
 the persistent W4 GEMV (integer and fp16 block math, tile-aligned and block-granular with the cross-CTA fix-up, several
-matrices per launch), the cluster split-K kernel (clustered and not), stream-K, tcgen05, the generic kernel, and the
+matrices per launch), the cluster split-K kernel (clustered and not), stream-K, the generic kernel, and the
 world = 1 forms of the peer / signal / flag-in-data entry points.  Results are checked against a @ dequant."""
 import ctypes
 import os
@@ -47,7 +47,6 @@ cases = [  # (K, N, M, g, family, env)
     (512, 4800, 9, 128, capi.GEMV_MMA, {"XBIT_GEMV_STREAMK": "0"}),          # no cluster, two MMA tiles
     (2048, 1024, 2, 128, capi.GEMV_MMA, {"XBIT_GEMV_STREAMK": "1"}),         # persistent stream-K of round 1
     (1024, 512, 1, 128, capi.GEMV_SIMT, {}),
-    (1024, 512, 4, 128, capi.GEMV_TCGEN05, {}),
     (300, 100, 3, 48, capi.GEMV_GENERIC, {}),
 ]
 for (K, N, M, g, fam, env) in cases:

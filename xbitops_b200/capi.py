@@ -9,7 +9,7 @@ from pathlib import Path
 from . import _build
 
 XBIT_OK = 0
-GEMV_AUTO, GEMV_SIMT, GEMV_MMA, GEMV_GENERIC, GEMV_TCGEN05, GEMV_PERSIST = 0, 1, 2, 3, 4, 5
+GEMV_AUTO, GEMV_SIMT, GEMV_MMA, GEMV_GENERIC, GEMV_PERSIST = 0, 1, 2, 3, 5
 GEMV_FLAG_STATIC_WEIGHTS = 0x100
 GEMV_FLAG_WAIT_PEERS = 0x200
 GEMV_FLAG_A_IS_LL = 0x400

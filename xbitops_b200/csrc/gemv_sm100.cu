@@ -28,8 +28,6 @@
 //       (xbit_gemv_f16_peers_ll) whose consumer is the next call's activation staging.
 //   gemv_w4_streamk_kernel<MT, UPG>    persistent stream-K schedule of the same block math: one CTA per SM on
 //       half an SM, contiguous unit ranges, fp32 partial tiles + flags in the caller's workspace.
-//   gemv_w4_tc5_kernel<MPAD>           tcgen05 / TMEM family (opt-in): converter warps -> TMEM A tiles ->
-//       tcgen05.mma -> tcgen05.ld epilogue.
 //   gemv_generic_kernel                any bits 2..8, any groupsize >= 16, any M, any N: one column per
 //       thread, bit-reader over the LSB-first stream, fp32 math with the zero point folded per
 //       group.  Correctness path for the combinations the reference aborts on (:152-155).
@@ -1012,343 +1010,9 @@ gemv_w4_streamk_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_co
   if (tid == 0) trace_stamp(a, 7);
 }
 
-// ------------------------------------------------------------------------------------------------
-// tcgen05 path: the Blackwell tensor core does the multiply-accumulate, from TMEM.
-//
-// Why: every register-level consumer above ends up bound by an SM math pipe, not by HBM -- legacy
-// mma.sync issues one m16n8k16 per 8 cycles per SM on B200 (16 B/clk of packed W4 when only one of
-// the 8 batch columns is used), FHFMA and HFMA2 are no faster per weight (profiles/);
-// with the math skipped the same TMA ring streams at 94-98 % of the measured HBM peak.
-// tcgen05.mma (M = 128 weight columns x N = 16 batch columns x K = 16) retires 2048 weights in 8
-// cycles, 5x more than the stream needs.
-//
-// CTA = 128 weight columns (= the 128 TMEM lanes).  Warps 0-7 convert, warp 8 = TMA producer (same ring
-// as gemv_w4_kernel), warp 9 = TMEM allocator + the single MMA-issuing thread.  A thread owns one weight column:
-//   convert : 8 x LDS.32 (its column's words of a 64-k half block; conflict-free under the swizzle),
-//             one IMAD.HI + four LOP3 per word -> fp16 subnormal pairs, tcgen05.st into the A buffer
-//             of the half block (128 lanes x 32 columns), tcgen05.wait::st, arrive "a_ready";
-//   mma     : 4 x tcgen05.mma.kind::f16 (A from TMEM, B = the permuted activation vector in shared
-//             memory through a K-major no-swizzle descriptor, D = 128 x 16 fp32 in TMEM),
-//             tcgen05.commit -> "a_free" (and "d_ready" after the second half);
-//   epilogue: tcgen05.ld of the M live columns of D, y[m] += s * (2^24 * d[m] - z * sum_k a_k), arrive "d_free".
-// One A buffer (a whole 128-k block, 64 columns) and two D buffers per group; TMEM use:
-// 2 x 64 (A) + 2 x 2 x 16 (D) = 192 -> 256 columns, so two CTAs fit per SM.
-constexpr int kTc5Threads = 10 * 32;
-constexpr int kTc5TmemCols = 256;
-
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&v)[16]) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
-                 "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
-}
-__device__ __forceinline__ void tc_ld8(uint32_t taddr, float (&d)[8]) {
-  uint32_t r[8];
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr) : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 8; ++i) d[i] = __uint_as_float(r[i]);
-}
-// D[tmem] (+)= A[tmem] * B[smem descriptor]; kind::f16, cta_group::1
-__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
-      " tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n}"
-      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
-}
-// K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1):
-// core matrix = 8 rows x 16 bytes with rows 16 bytes apart; LBO = distance between the two K chunks
-// of a K16 slice, SBO = distance between 8-row groups.
-__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
-         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
-}
-// kind::f16 instruction descriptor: D = f32, A = B = f16, both K-major, N = 16, M = 128
-constexpr uint32_t kTc5Idesc = (1u << 4) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
-
-// UPG = 4 only (groupsize 128); M <= 16.  MPAD = rows per activation chunk in shared memory (1, 2, 4, 8, 16).
-//
-// Warps 0-7 convert: thread (half = warp / 4, column n = tid % 128) owns words [8*half, 8*half+8) of its
-// column in every 128-k block and writes TMEM columns [32*half, 32*half+32) of the block's A buffer
-// (TMEM lane = n; a warp may only touch the lane quarter warp % 4).  A is triple buffered (3 x 64
-// columns), D double buffered (2 x 16): 224 -> 256 TMEM columns, two CTAs per SM.  Warps 0-3 also run
-// the epilogue of the previous block.  Warp 8 = TMA producer, warp 9 = TMEM allocator + MMA issuer.
-template <int MPAD>
-__global__ void __launch_bounds__(kTc5Threads, 2)
-gemv_w4_tc5_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap smap,
-                   const __grid_constant__ CUtensorMap zmap, const GemvArgs a) {
-  using Cfg = W4Cfg<4, 4>;                          // 128-column tile, 2 blocks (256 k) per stage
-  constexpr int WK = Cfg::WK, NT = Cfg::NT;
-  constexpr int kABufs = 3;
-  constexpr int YN = MPAD > 8 ? 16 : 8;               // batch columns read back from D
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int split = blockIdx.y;
-  const int n_cta = blockIdx.x * NT;
-  const int cw = min(NT, a.N - n_cta);
-  const int nblocks = a.K >> 7;
-  const int b0 = min(split * a.units_per_split, nblocks);
-  const int b1 = min(b0 + a.units_per_split, nblocks);
-  const int nblk_cta = b1 - b0;                     // 128-k blocks of this CTA
-  const int ntiles = (nblk_cta + WK - 1) / WK;
-  const int ring = a.ring;
-  const int nchunks = a.units_per_split * 16;       // 8-k activation chunks in this CTA's K range
-
-  unsigned char* stage_base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_base + ring * Cfg::kStageBytes);
-  uint64_t* full_bar = bars;                        // [8]  TMA stage landed
-  uint64_t* empty_bar = bars + 8;                   // [8]  stage converted by all 8 warps
-  uint64_t* a_ready = bars + 16;                    // [3]  A buffer written (8 warp arrivals)
-  uint64_t* mma_done = bars + 19;                   // [3]  tcgen05.commit: A buffer consumed, D complete
-  uint64_t* d_free = bars + 22;                     // [2]  D read back by the epilogue (4 warp arrivals)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
-  unsigned char* act_sm = stage_base + ring * Cfg::kStageBytes + 512;           // [nchunks + 32][MPAD][16 B]
-  float* asum_sm = reinterpret_cast<float*>(act_sm + (size_t)(nchunks + 32) * MPAD * 16);   // [blocks][YN]
-  float* red_sm = asum_sm + a.units_per_split * YN;                               // [M][NT]
-  float* clus_sm = red_sm + a.M * NT;                                            // [splits][M][NT]
-
-  const bool clustered = a.splits > 1;
-  if (clustered) asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
-  if (tid == 0) {
-    for (int s = 0; s < ring; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 8);
-    }
-    for (int i = 0; i < kABufs; ++i) {
-      mbar_init(&a_ready[i], 8);
-      mbar_init(&mma_done[i], 1);
-    }
-    mbar_init(&d_free[0], 4);
-    mbar_init(&d_free[1], 4);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 9) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)kTc5TmemCols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  griddep_launch_dependents();
-
-  // TMEM columns: A[buf] = 64 columns each at 0..191; D[buf] = 16 columns each at 192..223
-  auto a_col = [&](int buf) { return (uint32_t)(buf * 64); };
-  auto d_col = [&](int buf) { return (uint32_t)(192 + buf * 16); };
-
-  float y[YN];
-#pragma unroll
-  for (int m = 0; m < YN; ++m) y[m] = 0.f;
-
-  if (warp == 8) {
-    // =========================== TMA producer ===========================
-    if (!a.static_weights) griddep_wait();
-    if (lane == 0) {
-      uint64_t policy;
-      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&wmap) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&smap) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&zmap) : "memory");
-      int s = 0, ph = 0;                            // slot s has been filled (t / ring) times; ph = that count & 1
-      for (int t = 0; t < ntiles; ++t) {
-        if (t >= ring) mbar_wait(&empty_bar[s], ph ^ 1);
-        const int blk = b0 + t * WK;
-        unsigned char* st = stage_base + s * Cfg::kStageBytes;
-        mbar_arrive_expect_tx(&full_bar[s], Cfg::kTxBytes);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) tma_load_2d(st + c * Cfg::kBoxBytes, &wmap, n_cta + 32 * c, blk * 16, &full_bar[s], policy);
-        tma_load_2d(st + Cfg::kWeights, &smap, n_cta, blk, &full_bar[s], policy);
-        tma_load_2d(st + Cfg::kWeights + Cfg::kScales, &zmap, n_cta >> 3, blk, &full_bar[s], policy);
-        if (++s == ring) { s = 0; ph ^= 1; }
-      }
-    }
-    __syncwarp();
-  } else if (warp == 9) {
-    // =========================== MMA issuer ===========================
-    if (lane == 0) {
-      const uint32_t act_addr = smem_u32(act_sm);
-      int buf = 0, bph = 0;                         // A buffer and its phase parity
-      for (int bi = 0; bi < nblk_cta; ++bi) {
-        const int db = bi & 1;
-        mbar_wait(&a_ready[buf], bph);
-        if (bi >= 2) mbar_wait(&d_free[db], ((bi >> 1) - 1) & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const uint32_t chunk = (uint32_t)(bi * 16 + 2 * j);
-          const uint64_t bdesc = tc_smem_desc(act_addr + chunk * (MPAD * 16), MPAD * 16, 128);
-          tc_mma_ts(tmem_base + d_col(db), tmem_base + a_col(buf) + 8 * j, bdesc, kTc5Idesc, j ? 1u : 0u);
-        }
-        tc_commit(&mma_done[buf]);
-        if (++buf == kABufs) { buf = 0; bph ^= 1; }
-      }
-    }
-    __syncwarp();
-  } else {
-    // =========================== converters / epilogue ===========================
-    const int half = warp >> 2;                     // which 8 of the block's 16 word-rows this thread converts
-    const int quarter = warp & 3;                   // TMEM lane quarter of this warp
-    const int n = tid & 127;                        // weight column inside the tile = TMEM lane
-    const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    griddep_wait();
-    {
-      // activations of this CTA's K range as the MMA's B operand: [chunk of 8 k][MPAD rows][16 bytes],
-      // permuted / scaled like permute_act8<true>; plus sum_k a_k per 128-k block for the folded zero point
-      const int k0 = b0 * 128;
-      const int vecs = nblk_cta * 16;
-      for (int base = 0; base < MPAD * vecs; base += kConsumerThreads) {
-        const int idx = base + tid;
-        const bool ok = idx < MPAD * vecs;
-        const int m = ok ? idx / vecs : 0, v = ok ? idx - m * vecs : 0;
-        uint4 val = make_uint4(0, 0, 0, 0);
-        if (ok && m < a.M) val = __ldg(reinterpret_cast<const uint4*>(a.a + (size_t)m * a.K + k0) + v);
-        if (ok) *reinterpret_cast<uint4*>(act_sm + ((size_t)v * MPAD + m) * 16) = permute_act8<true>(val);
-        const float2 f0 = __half22float2(u2h2(val.x)), f1 = __half22float2(u2h2(val.y));
-        const float2 f2 = __half22float2(u2h2(val.z)), f3 = __half22float2(u2h2(val.w));
-        float sum = ((f0.x + f0.y) + (f1.x + f1.y)) + ((f2.x + f2.y) + (f3.x + f3.y));
-#pragma unroll
-        for (int o = 1; o < 16; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        if (ok && (lane & 15) == 0) asum_sm[(v >> 4) * YN + m] = sum;
-      }
-      // zero the padding chunks the MMA may touch as "other batch rows"
-      for (int idx = tid; idx < 32 * MPAD; idx += kConsumerThreads)
-        *reinterpret_cast<uint4*>(act_sm + ((size_t)vecs * MPAD + idx) * 16) = make_uint4(0, 0, 0, 0);
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> tensor-core (async proxy) reads
-    }
-    asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");
-
-    // this thread's column inside the swizzled stage: box = n / 32, 16-byte chunk = (n % 32) / 4, word = n % 4
-    const uint32_t w_base = (uint32_t)((n >> 5) * Cfg::kBoxBytes + half * 8 * 128 + (n & 3) * 4);
-    const int chunk = (n & 31) >> 2;
-    const uint32_t s_off = (uint32_t)(Cfg::kWeights + n * 2);
-    const uint32_t z_off = (uint32_t)(Cfg::kWeights + Cfg::kScales + (n >> 3) * 4);
-    const int zsh = 4 * (n & 7);
-    const float zbias = (float)a.zero_bias;
-    float prev_s24 = 0.f, prev_nsz = 0.f;
-    int buf = 0, bph = 0;                           // A buffer of the block being converted, its phase parity
-    int pbuf = 0, pph = 0;                          // the same for the previous block (epilogue)
-    int bi = 0;                                     // blocks converted so far
-
-    // block bj (A buffer pb, parity pp): wait for its MMAs, read D back, fold scale and zero point
-    auto epilogue = [&](int bj, int pb, int pp, float s24, float nsz) {
-      const int db = bj & 1;
-      mbar_wait(&mma_done[pb], pp);
-      tc_fence_after();
-      float d[YN];
-      {
-        float d0[8];
-        tc_ld8(lane_base + d_col(db), d0);
-#pragma unroll
-        for (int m = 0; m < 8; ++m) d[m] = d0[m];
-        if constexpr (YN == 16) {
-          tc_ld8(lane_base + d_col(db) + 8, d0);
-#pragma unroll
-          for (int m = 0; m < 8; ++m) d[8 + m] = d0[m];
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&d_free[db]);
-      const float* as = asum_sm + bj * YN;
-#pragma unroll
-      for (int m = 0; m < YN; ++m) y[m] = fmaf(nsz, as[m], fmaf(s24, d[m], y[m]));
-    };
-
-    int s = 0, ph = 0;
-    for (int t = 0; t < ntiles; ++t) {
-      mbar_wait(&full_bar[s], ph);
-      const unsigned char* st = stage_base + s * Cfg::kStageBytes;
-#pragma unroll
-      for (int g = 0; g < WK; ++g) {
-        if (t * WK + g < nblk_cta) {                // CTA-uniform
-          float cur_s24 = 0.f, cur_nsz = 0.f;
-          if (half == 0) {
-            const float sc = __half2float(*reinterpret_cast<const __half*>(st + s_off + g * (NT * 2)));
-            const uint32_t zw = *reinterpret_cast<const uint32_t*>(st + z_off + g * (NT / 2));
-            cur_s24 = sc * 16777216.f;
-            cur_nsz = -sc * ((float)((zw >> zsh) & 0xFu) + zbias);
-          }
-          uint32_t v[32];
-#pragma unroll
-          for (int r = 0; r < 8; ++r) {             // word-row 8*half + r of block g; swizzle phase = row & 7 = r
-            const uint32_t wd = *reinterpret_cast<const uint32_t*>(st + w_base + (g * 16 + r) * 128 + ((chunk ^ r) << 4));
-            uint32_t e[4];
-            unpack_w4_subnormal(wd, e);
-            v[4 * r + 0] = e[0]; v[4 * r + 1] = e[1]; v[4 * r + 2] = e[2]; v[4 * r + 3] = e[3];
-          }
-          // the A buffer is free once the MMAs of block bi - 3 have retired
-          if (bi >= kABufs) mbar_wait(&mma_done[buf], bph ^ 1);
-          tc_fence_after();
-          {
-            uint32_t lo[16], hi[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) { lo[i] = v[i]; hi[i] = v[16 + i]; }
-            tc_st16(lane_base + a_col(buf) + 32 * half, lo);
-            tc_st16(lane_base + a_col(buf) + 32 * half + 16, hi);
-          }
-          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&a_ready[buf]);
-          if (half == 0) {
-            if (bi >= 1) epilogue(bi - 1, pbuf, pph, prev_s24, prev_nsz);
-            prev_s24 = cur_s24; prev_nsz = cur_nsz;
-          }
-          pbuf = buf; pph = bph;
-          if (++buf == kABufs) { buf = 0; bph ^= 1; }
-          ++bi;
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty_bar[s]);    // the MMA never reads the stage: it can be refilled now
-      if (++s == ring) { s = 0; ph ^= 1; }
-    }
-    if (half == 0) {
-      if (bi >= 1) epilogue(bi - 1, pbuf, pph, prev_s24, prev_nsz);
-#pragma unroll
-      for (int m = 0; m < YN; ++m)
-        if (m < a.M) red_sm[m * NT + n] = y[m];
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 9) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kTc5TmemCols) : "memory");
-  }
-
-  const int nout = a.M * NT;
-  if (clustered) {
-    cg::cluster_group cluster = cg::this_cluster();
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-    float* leader = cluster.map_shared_rank(clus_sm, 0);
-    for (int o = tid; o < nout; o += kTc5Threads) leader[split * nout + o] = red_sm[o];
-    cluster.sync();
-    if (split != 0) return;
-  }
-  for (int o = tid; o < nout; o += kTc5Threads) {
-    const int m = o / NT, col = o - m * NT;
-    float v = 0.f;
-    if (clustered) {
-      for (int s = 0; s < a.splits; ++s) v += clus_sm[s * nout + o];
-    } else {
-      v = red_sm[o];
-    }
-    if (col < cw) {
-      const __half h = __float2half_rn(v);
-      const size_t off = (size_t)m * a.ldo + a.col_offset + n_cta + col;
-      a.out[0][off] = h;
-      for (int p = 1; p < a.world; ++p) a.out[p][off] = h;
-    }
-  }
-}
+// (A tcgen05 / TMEM family -- converter warps -> TMEM A tiles -> tcgen05.mma -> tcgen05.ld epilogue -- existed in round 1
+// and was removed in round 2: the converter warps pay the same unpack as the mma.sync kernels, and it measured behind them
+// at every M, profiles/r01_v4_*tcgen05*, profiles/r01_v6_skinny_m_crossover.log.)
 
 // ------------------------------------------------------------------------------------------------
 // generic: any bits / groupsize / M / N.  One column per thread, 32 columns x 8 K-slices per CTA.
@@ -1982,74 +1646,6 @@ cudaError_t launch_gemv_w4_streamk(GemvArgs a, int family, void* workspace, size
   attrs[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attrs;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kern, wmap, smap, zmap, a);
-}
-
-// ---- tcgen05 path launch (bits 4, groupsize 128, M <= 8)
-bool gemv_w4_tc5_supported(const GemvArgs& a) {
-  return gemv_w4_supported(a) && a.groupsize == 128 && a.M <= 16;
-}
-
-static size_t tc5_smem_bytes(int m, int mpad, int blocks_per_split, int splits, int ring) {
-  const size_t stage = W4Cfg<4, 4>::kStageBytes;
-  return 1024 + (size_t)ring * stage + 512 + (size_t)(blocks_per_split * 16 + 32) * mpad * 16 + (size_t)blocks_per_split * 16 * sizeof(float)
-         + (size_t)m * 128 * sizeof(float) + (size_t)(splits > 1 ? splits : 0) * m * 128 * sizeof(float);
-}
-
-cudaError_t launch_gemv_w4_tc5(GemvArgs a, cudaStream_t stream) {
-  if (!gemv_w4_tc5_supported(a)) return cudaErrorInvalidValue;
-  const int sms = device_sm_count();
-  const int nblocks = a.K / 128;
-  const int tiles = (a.N + 127) / 128;
-  const int mpad = a.M == 1 ? 1 : (a.M == 2 ? 2 : (a.M <= 4 ? 4 : (a.M <= 8 ? 8 : 16)));
-  int ring = env_int("XBIT_GEMV_RING", 0);
-  if (ring < 2 || ring > kMaxStages) ring = 4;
-  int splits = env_int("XBIT_GEMV_SPLITS", 0);
-  if (splits < 1 || splits > 8 || (splits & (splits - 1))) {
-    splits = 1;
-    while (splits < 8 && tiles * splits * 2 <= 2 * sms && nblocks / (splits * 2) >= 4) splits *= 2;
-  }
-  auto smem_of = [&](int sp) { return tc5_smem_bytes(a.M, mpad, (nblocks + sp - 1) / sp, sp, ring); };
-  while (splits < 8 && smem_of(splits) > kMaxDynSmem) splits *= 2;
-  if (smem_of(splits) > kMaxDynSmem) return cudaErrorInvalidValue;
-  a.splits = splits;
-  a.units_per_split = (nblocks + splits - 1) / splits;
-  a.ring = ring;
-  a.debug_skip = 0;
-  const size_t smem = smem_of(splits);
-  W4Kernel kern = mpad == 1 ? gemv_w4_tc5_kernel<1> : (mpad == 2 ? gemv_w4_tc5_kernel<2> : (mpad == 4 ? gemv_w4_tc5_kernel<4> : (mpad == 8 ? gemv_w4_tc5_kernel<8> : gemv_w4_tc5_kernel<16>)));
-
-  alignas(64) CUtensorMap wmap, smap, zmap;
-  cudaError_t e = encode_2d(&wmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, a.qweight, (uint64_t)a.N, (uint64_t)a.qrows,
-                            (uint64_t)a.N * 4, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
-  if (e != cudaSuccess) return e;
-  e = encode_2d(&smap, CU_TENSOR_MAP_DATA_TYPE_UINT16, a.scales, (uint64_t)a.N, (uint64_t)a.groups, (uint64_t)a.N * 2, 128, 2,
-                CU_TENSOR_MAP_SWIZZLE_NONE);
-  if (e != cudaSuccess) return e;
-  e = encode_2d(&zmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, a.qzeros, (uint64_t)a.zwords, (uint64_t)a.groups, (uint64_t)a.zwords * 4, 16, 2,
-                CU_TENSOR_MAP_SWIZZLE_NONE);
-  if (e != cudaSuccess) return e;
-  e = ensure_max_dyn_smem(reinterpret_cast<const void*>(kern));
-  if (e != cudaSuccess) return e;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)tiles, (unsigned)splits, 1);
-  cfg.blockDim = dim3(kTc5Threads, 1, 1);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = stream;
-  cudaLaunchAttribute attrs[2];
-  int na = 0;
-  attrs[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attrs[na].val.programmaticStreamSerializationAllowed = 1;
-  ++na;
-  if (splits > 1) {
-    attrs[na].id = cudaLaunchAttributeClusterDimension;
-    attrs[na].val.clusterDim.x = 1;
-    attrs[na].val.clusterDim.y = (unsigned)splits;
-    attrs[na].val.clusterDim.z = 1;
-    ++na;
-  }
-  cfg.attrs = attrs;
-  cfg.numAttrs = na;
   return cudaLaunchKernelEx(&cfg, kern, wmap, smap, zmap, a);
 }
 

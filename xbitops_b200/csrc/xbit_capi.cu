@@ -124,7 +124,6 @@ static int pick_family(const xbit::GemvArgs& a) {
   if (forced == XBIT_GEMV_SIMT && a.M == 1) return XBIT_GEMV_SIMT;
   if (forced == XBIT_GEMV_MMA) return XBIT_GEMV_MMA;
   if (forced == XBIT_GEMV_GENERIC) return XBIT_GEMV_GENERIC;
-  if (forced == XBIT_GEMV_TCGEN05 && xbit::gemv_w4_tc5_supported(a)) return XBIT_GEMV_TCGEN05;
   if (a.M <= 8 && xbit::gemv_w4p_preferred(a)) return XBIT_GEMV_PERSIST;
   return XBIT_GEMV_MMA;
 }
@@ -258,11 +257,6 @@ static int gemv_impl(const void* a_f16, const int32_t* qweight, const void* scal
           const bool has = workspace && workspace_bytes > off;
           e = xbit::launch_gemv_w4p(g, has ? static_cast<unsigned char*>(workspace) + off : nullptr, has ? workspace_bytes - off : 0, st);
         }
-        break;
-      case XBIT_GEMV_TCGEN05:
-        slab = g.M > 16 ? 16 : g.M; g.M = slab;
-        if (!xbit::gemv_w4_tc5_supported(g)) return fail(XBIT_EINVAL, "TCGEN05 family needs bits=4, groupsize=128, K%%128=0, N%%32=0, 16-byte aligned pointers");
-        e = xbit::launch_gemv_w4_tc5(g, st);
         break;
       case XBIT_GEMV_GENERIC:
         slab = g.M;

@@ -78,9 +78,6 @@ size_t gemv_w4p_workspace_bytes(int M);
 cudaError_t launch_gemv_w4p(const GemvArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 // `count` (<= 4) matrices sharing the activations in one launch; cudaErrorNotSupported = launch them one by one
 cudaError_t launch_gemv_w4p_multi(const GemvArgs* gs, int count, void* workspace, size_t workspace_bytes, cudaStream_t stream);
-// tcgen05 + TMEM path (bits 4, groupsize 128, M <= 8)
-bool gemv_w4_tc5_supported(const GemvArgs& a);
-cudaError_t launch_gemv_w4_tc5(GemvArgs a, cudaStream_t stream);
 // any bits / groupsize / M / N
 cudaError_t launch_gemv_generic(GemvArgs a, cudaStream_t stream);
 
