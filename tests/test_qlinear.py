@@ -38,7 +38,7 @@ def test_qlinear_forward_matches_dense(c_oracle):
     gen = torch.Generator(device=dev).manual_seed(3)
     K, N = 1024, 768
     lin = torch.nn.Linear(K, N, bias=True, device=dev, dtype=torch.float16)
-    for bits, g in ((4, 128), (3, 64), (8, 32)):
+    for bits, g in ((4, 128), (3, 64), (8, 32), (8, 128), (2, 128)):       # the last two: the fast 8- / 2-bit kernels
         q = Q.QLinear.from_linear(lin, bits, g)
         w = q.dequantized_weight()                                   # [K, N] fp16
         # the packed tensors restated by the C oracle give the same dense weight, bit for bit
@@ -54,7 +54,21 @@ def test_qlinear_forward_matches_dense(c_oracle):
         assert y3.shape == (2, 3, N)
     # bf16 layer: output dtype follows the scales (dq_torch_ops.cc:33-42)
     qb = Q.QLinear.from_linear(lin.to(torch.bfloat16), 4, 128)
-    assert qb(torch.randn((2, K), device=dev).to(torch.bfloat16)).dtype == torch.bfloat16
+    xb = torch.randn((2, K), device=dev, generator=gen).to(torch.bfloat16)
+    yb = qb(xb)
+    assert yb.dtype == torch.bfloat16
+    # ... and with the bf16-native kernels switched on the layer stays in bf16 end to end
+    from xbitops_b200 import ops
+    ops.set_native_bf16(True)
+    try:
+        yn = qb(xb)
+        wn = qb.dequantized_weight()
+    finally:
+        ops.set_native_bf16(False)
+    assert yn.dtype == torch.bfloat16 and wn.dtype == torch.bfloat16
+    refb = xb.double() @ wn.double() + qb.bias.double()
+    assert float((yn.double() - refb).abs().max() / refb.abs().max()) < 1e-2
+    assert float((yn.double() - yb.double()).abs().max() / refb.abs().max()) < 2e-2
 
 
 @pytest.mark.gpu
