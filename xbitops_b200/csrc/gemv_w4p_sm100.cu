@@ -25,6 +25,17 @@
 //     tile last, the others hold its later blocks and process them first, so a finisher normally finds the
 //     partials waiting.  Sums are taken in warp / CTA order: deterministic, no atomics on data.
 //     Without a workspace CTA boundaries are tile-aligned instead and nothing crosses CTAs.
+//
+// Round-2 additions, all compile-time forms of the one kernel template (gemv_w4p_kernel):
+//   I8    integer block math (groupsize 128, M <= 2): the packed words, masked, ARE the u8 operands of
+//         mma.sync.m16n8k32; the activations become 24-bit fixed point per scale group in three byte planes;
+//   BITS  4, 8 (a packed word is an A register as it is: no unpack instruction) or 2 (four byte masks per word, the
+//         activation planes scaled per k mod 4): A16W8 / A16W2 on the same schedule;
+//   BF    bf16-native: activations, scales and output bf16, one rounding of the fp32 result;
+//   GEN   0 = one matrix per launch (short parameter block, plain loads), 1 = several matrices sharing the activations
+//         (xbit_gemv_f16_multi), 2 = also the flag-in-data multi-GPU forms;
+//   MINB  2 = half an SM (the next launch co-resident, its share prefetched whole), 1 = a full SM (deeper rings).
+// No integer division in the kernel (host-supplied multipliers); single-tile CTAs finish through a named barrier.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
