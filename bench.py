@@ -678,6 +678,26 @@ def run_gpu_arm(args):
                 nb = synth.dq_bytes(Kd, Nd, b, g)
                 dq[f"b{b}_g{g}"] = {"us": round(us, 2), "GBps": round(nb / us / 1e3, 1), "frac_of_measured_peak": round(nb / us / 1e3 / peak, 4)}
                 del qw, qz, sc
+        # ... and the bf16-native form (scales and output bf16, one rounding) for three of them
+        dqb = {}
+        outb = outd.view(torch.bfloat16)
+        for b in (3, 4, 8):
+            g = 128
+            qw = torch.randint(-2**31, 2**31 - 1, (Rd, (Kd * b + 31) // 32, Nd), dtype=torch.int32, device=dev, generator=gen)
+            qz = torch.randint(-2**31, 2**31 - 1, (Rd, Kd // g, (Nd * b + 31) // 32), dtype=torch.int32, device=dev, generator=gen)
+            sc = (torch.rand((Rd, Kd // g, Nd), device=dev, generator=gen) * 0.018 + 0.002).to(torch.bfloat16)
+
+            def fn(i, b=b, g=g, qw=qw, qz=qz, sc=sc):
+                j = i % Rd
+                rc = lib.xbit_dequant_bf16(qw[j].data_ptr(), sc[j].data_ptr(), qz[j].data_ptr(), outb[j].data_ptr(), Kd, Nd, b, g, 1,
+                                           torch.cuda.current_stream().cuda_stream)
+                if rc != 0:
+                    raise RuntimeError(capi.last_error())
+            us = graph_us(fn, 2 * Rd)
+            nb = synth.dq_bytes(Kd, Nd, b, g)
+            dqb[f"b{b}_g{g}"] = {"us": round(us, 2), "GBps": round(nb / us / 1e3, 1), "frac_of_measured_peak": round(nb / us / 1e3 / peak, 4)}
+            del qw, qz, sc
+        line["dq_bf16_native"] = {"shape": "4096x11008", "by_bits_groupsize": dqb}
         line["dq"] = {"shape": "4096x11008", "by_bits_groupsize": dq,
                       "note": "algorithmic bytes = packed weights + scales + zeros + fp16 output (80 % of it is the output write)"}
         del outd
