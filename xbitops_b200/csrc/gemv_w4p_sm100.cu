@@ -1268,9 +1268,9 @@ static bool plan_w4p_nw(const GemvArgs& a, bool have_ws, W4PPlan& p, bool allow1
   //     (48 blocks, prefetched during the previous call) arrives at one SM's share of the bandwidth.
   const long long per_cta_fine = (total + g_fine - 1) / g_fine;
   const bool fine_is_aligned = total % g_fine == 0 && (total / g_fine) % nb == 0;
-  //   * with the fp16 block math (M > 2, or group sizes 32 / 64) every shared tile also moves M rows of partial sums:
-  //     8 blocks per row (4096 x 11008, M = 4: 8.9 us tile-aligned against 10.3 us; M = 8: 11.8 against 14.8)
-  const long long cost_fine = per_cta_fine + (fine_is_aligned ? 0 : (per_cta_fine < nb ? 42 : 20) + (a.M > 2 ? 8 * a.M : 0));
+  //   * with more than one activation row every shared tile also moves M rows of partial sums: 8 blocks per row
+  //     (4096 x 11008: M = 2 7.1 us tile-aligned against 7.3 us, M = 4 8.9 against 10.3, M = 8 11.8 against 14.8)
+  const long long cost_fine = per_cta_fine + (fine_is_aligned ? 0 : (per_cta_fine < nb ? 42 : 20) + (a.M > 1 ? 8 * a.M : 0));
   const long long cost_tile = (tiles + sms - 1) / sms * nb + ((tiles * 4 < sms * 3 && nb > 48) ? nb - 48 : 0);
   bool fine = have_ws && cost_fine < cost_tile;
   const int env_unit = env_int("XBIT_W4P_FINE", -1);
