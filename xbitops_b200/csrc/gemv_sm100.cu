@@ -1100,7 +1100,6 @@ gemv_generic_kernel(const GemvArgs a, int m_base) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int k = kk + j;
-            constexpr int dummy = 0; (void)dummy;
             const int pos = (i8 + j) * BITS, wi = pos >> 5, sh = pos & 31;      // compile-time after unrolling
             uint32_t f;
             if (sh + BITS <= 32) f = (w[wi] >> sh) & mask;
