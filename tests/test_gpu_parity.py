@@ -322,8 +322,19 @@ def test_gemv_full_size_properties(K, N, dev):
         assert_gemv_close(y.cpu().numpy(), truth, f"{K}x{N} family {fam}", floor_of(fam))
         if fam == capi.GEMV_PERSIST:
             # M <= 2 runs the integer block math, M >= 3 the fp16 exact-product math: rows agree bit for bit within each
-            y1 = X.gemv(a[1:2], qw, s, qz, g, bits, K, 1, family=fam)
-            assert torch.equal(y1[0], X.gemv(a[:2], qw, s, qz, g, bits, K, 1, family=fam)[1])
+            # -- under the same CTA-boundary mode (the planner may pick block-granular ranges for one row and tile-aligned
+            # ones for two: another fp32 summation order, i.e. fp16 rounding of the same sums)
+            for mode in (0, 1):
+                capi.set_option("XBIT_W4P_FINE", mode)
+                try:
+                    y1 = X.gemv(a[1:2], qw, s, qz, g, bits, K, 1, family=fam)
+                    y12 = X.gemv(a[:2], qw, s, qz, g, bits, K, 1, family=fam)
+                finally:
+                    capi.set_option("XBIT_W4P_FINE")
+                assert torch.equal(y1[0], y12[1]), f"{K}x{N} fine={mode}"
+            y1 = X.gemv(a[1:2], qw, s, qz, g, bits, K, 1, family=fam)[0].double()
+            y12 = X.gemv(a[:2], qw, s, qz, g, bits, K, 1, family=fam)[1].double()
+            assert float((y1 - y12).abs().max()) <= 2.0 ** -9 * float(y12.abs().max())
             # (3 and 4 rows may get different warp counts / rings, i.e. another fp32 summation order: fp16 rounding of the
             # same sums, not bit identity)
             y3 = X.gemv(a[1:4], qw, s, qz, g, bits, K, 1, family=fam)[1].double()
