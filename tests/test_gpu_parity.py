@@ -667,3 +667,13 @@ def test_gemv_w8_persistent_integer_math(wbits, dev, c_oracle):
             assert_gemv_close(y1.cpu().numpy(), y64, f"W{wbits} persist fine={fine} {K}x{N} M={M}")
         yg = X.gemv(ta, tq, ts, tz, 128, wbits, K, bias, family=capi.GEMV_GENERIC)
         assert float((yg.double() - y_auto.double()).abs().max()) <= 2e-3 * float(np.abs(y64).max())
+        # back-to-back launches (programmatic dependent launch, rings and workspace reused) reproduce the result bit for bit
+        X.set_static_weights(True)
+        try:
+            outs = torch.empty((30,) + tuple(y_auto.shape), dtype=torch.float16, device=dev)
+            for i in range(30):
+                X.gemv(ta, tq, ts, tz, 128, wbits, K, bias, out=outs[i])
+            torch.cuda.synchronize()
+        finally:
+            X.set_static_weights(False)
+        assert bool((outs == outs[0]).all()), f"W{wbits} {K}x{N} M={M}: repeated launches differ"
