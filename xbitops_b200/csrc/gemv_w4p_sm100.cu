@@ -1238,16 +1238,18 @@ static bool plan_w4p_nw(const GemvArgs& a, bool have_ws, W4PPlan& p, bool allow1
   //   half SM:  8 warps, rings of 2..3 two-block slots, two launches co-resident: a matrix whose per-CTA share fits the
   //             rings is prefetched whole while the previous call computes (4096 x 4096: 3.4 us against 4.3 us for the
   //             cluster kernel);
-  //   full SM:  rings of 4 slots (16 warps: 2), one CTA per SM and the register budget of one: larger matrices keep
+  //   full SM:  rings of 4..6 slots (16 warps: 2), one CTA per SM and the register budget of one: larger matrices keep
   //             streaming while they compute, and what counts is the compute rate and the bytes in flight
   //             (8192 x 28672: 22.3 against 26.0 us).
   const long long total_blocks = tiles * nb;
   const long long share = (total_blocks + sms - 1) / sms;           // blocks per CTA
   // (a launch of several matrices, xbit_gemv_f16_multi: the CTA streams the shares of all of them, share_all)
   const bool small = (share_all > 0 ? share_all : share) <= 8 * 2 * 3;   // fits 8 rings of 3 two-block slots
-  const bool large = share >= 100 && a.K <= 8192;                   // 16 warps pay off from about 35 MB (8192 x 8192: 8.6 vs 8.7 us, 8192 x 28672: 22.3 vs 23.0)
-  const int env_nw = env_int("XBIT_W4P_WARPS", 0);                  // 8 / 16: override (tools/ptime.py)
-  p.nw = w8 ? 8 : (env_nw == 16 ? 16 : (env_nw == 8 ? 8 : (large && allow16 ? 16 : 8)));
+  // (16 consumer warps -- rings of 2 slots -- paid off from about 35 MB while 8-warp rings stopped at 4 slots; with rings of
+  // 5..6 slots 8 warps are ahead everywhere: 8192 x 8192 8.0 against 8.3 us, 8192 x 28672 23.6 against 25.9,
+  // profiles/r02_ptime_8_vs_16_warps_deep_rings.log.  XBIT_W4P_WARPS=16 keeps the form reachable for tools/ptime.py.)
+  const int env_nw = env_int("XBIT_W4P_WARPS", 0);
+  p.nw = (!w8 && env_nw == 16 && allow16) ? 16 : 8;
   const int nr = p.nw;                               // rings
   // integer block math: groupsize 128, M <= 2 (XBIT_W4P_I8=0: the fp16 exact-product math everywhere)
   const bool i8 = w8 || (a.groupsize == 128 && a.M <= 2 && env_int("XBIT_W4P_I8", 1) != 0);
@@ -1263,14 +1265,14 @@ static bool plan_w4p_nw(const GemvArgs& a, bool have_ws, W4PPlan& p, bool allow1
   // Cost model in blocks per CTA (8 warps x 4 blocks ~ 1 us), fitted to profiles/r02_ptime_shard_shapes.log:
   //   * a tile shared between CTAs costs its finisher a round trip through the workspace: ~1.3 us (42 blocks) when the
   //     CTA ranges are shorter than a tile -- the contributor's piece is then its WHOLE range and lands when the finisher
-  //     is already waiting -- and ~0.6 us (20 blocks) when they are longer (the contributor does that piece first);
+  //     is already waiting -- and ~0.5 us (16 blocks) when they are longer (the contributor does that piece first);
   //   * tile-aligned with fewer tiles than SMs leaves the stream to few SMs: whatever exceeds the rings of a half-SM CTA
   //     (48 blocks, prefetched during the previous call) arrives at one SM's share of the bandwidth.
   const long long per_cta_fine = (total + g_fine - 1) / g_fine;
   const bool fine_is_aligned = total % g_fine == 0 && (total / g_fine) % nb == 0;
   //   * with more than one activation row every shared tile also moves M rows of partial sums: 8 blocks per row
   //     (4096 x 11008: M = 2 7.1 us tile-aligned against 7.3 us, M = 4 8.9 against 10.3, M = 8 11.8 against 14.8)
-  const long long cost_fine = per_cta_fine + (fine_is_aligned ? 0 : (per_cta_fine < nb ? 42 : 20) + (a.M > 1 ? 8 * a.M : 0));
+  const long long cost_fine = per_cta_fine + (fine_is_aligned ? 0 : (per_cta_fine < nb ? 42 : 16) + (a.M > 1 ? 8 * a.M : 0));
   const long long cost_tile = (tiles + sms - 1) / sms * nb + ((tiles * 4 < sms * 3 && nb > 48) ? nb - 48 : 0);
   bool fine = have_ws && cost_fine < cost_tile;
   const int env_unit = env_int("XBIT_W4P_FINE", -1);
@@ -1287,7 +1289,9 @@ static bool plan_w4p_nw(const GemvArgs& a, bool have_ws, W4PPlan& p, bool allow1
   if (small && nr == 8 && a.bits != 8)
     for (int r = 3; r >= 2 && !ring; --r)
       if (w4p_smem_bytes(upg, nr, a.M, a.K, r, i8, 2, count, a.bits) <= half) ring = r;
-  for (int r = (nr == 16 ? 2 : 4); r >= 2 && !ring; --r)      // (16 rings: 3 slots measured no better than 2)
+  // (8 rings: as deep as fits, up to 6 slots -- 5 against 4: 8.05 / 8.7 us on 8192 x 8192, 6.18 / 6.27 on 4096 x 11008,
+  // profiles/r02_ptime_ring_5_6.log; 16 rings: 3 slots measured no better than 2)
+  for (int r = (nr == 16 ? 2 : 6); r >= 2 && !ring; --r)
     if (w4p_smem_bytes(upg, nr, a.M, a.K, r, i8, 2, count, a.bits) <= kMaxDynSmem) ring = r;
   if (!ring) return false;
   const int env_ring = env_int("XBIT_W4P_RING", 0);
