@@ -79,3 +79,18 @@ def test_product_never_imports_the_oracle():
                 assert "xbit_oracle" not in text and "libxbit_refcpu" not in text, f
     hdr = open(os.path.join(ROOT, "include", "xbitops_b200.h")).read()
     assert "oracle" not in hdr
+
+
+def test_auto_family_policy_without_gpu():
+    """xbit_gemv_pick_family is pure host logic (148 SMs assumed without a device): the measured policy of DESIGN.md 4.2
+    -- persistent kernel (5) on the Llama shapes, for 8- / 2-bit weights at groupsize 128 and for whole-tile batches of a
+    short K; cluster split-K (2) for few tiles of a long K, K > 16384 and batches beyond 8 rows; the generic kernel (3)
+    for odd widths, other group sizes and ragged N."""
+    from xbitops_b200 import capi
+    lib = capi.load()
+    want = {(1, 4096, 4096, 4, 128): 5, (1, 4096, 11008, 4, 128): 5, (1, 11008, 4096, 4, 128): 5, (1, 8192, 28672, 4, 128): 5,
+            (1, 8192, 1024, 4, 128): 2, (1, 28672, 8192, 4, 128): 2, (8, 4096, 11008, 4, 128): 5, (4, 8192, 8192, 4, 128): 2,
+            (16, 8192, 8192, 4, 128): 2, (1, 4096, 4096, 8, 128): 5, (2, 4096, 4096, 2, 128): 5, (1, 4096, 4096, 3, 128): 3,
+            (1, 4096, 4096, 4, 100): 3, (1, 4096, 4096, 8, 64): 3, (1, 4096, 4100, 4, 128): 3}
+    for args, fam in want.items():
+        assert lib.xbit_gemv_pick_family(*args) == fam, args
