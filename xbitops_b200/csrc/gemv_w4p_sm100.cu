@@ -1244,7 +1244,9 @@ static bool plan_w4p_nw(const GemvArgs& a, bool have_ws, W4PPlan& p, bool allow1
   const long long total_blocks = tiles * nb;
   const long long share = (total_blocks + sms - 1) / sms;           // blocks per CTA
   // (a launch of several matrices, xbit_gemv_f16_multi: the CTA streams the shares of all of them, share_all)
-  const bool small = (share_all > 0 ? share_all : share) <= 8 * 2 * 3;   // fits 8 rings of 3 two-block slots
+  // half SM: the share fits 8 rings of 3 two-block slots AND no CTA gets more than one tile (4096 x 5504, 172 tiles: 4.55 us
+  // on a full SM with rings of 6 against 5.1 us on half an SM, profiles/r02_ptime_half_vs_full_sm_mid_shapes.log)
+  const bool small = (share_all > 0 ? share_all : share) <= 8 * 2 * 3 && (share_all > 0 || tiles <= sms);
   // (16 consumer warps -- rings of 2 slots -- paid off from about 35 MB while 8-warp rings stopped at 4 slots; with rings of
   // 5..6 slots 8 warps are ahead everywhere: 8192 x 8192 8.0 against 8.3 us, 8192 x 28672 23.6 against 25.9,
   // profiles/r02_ptime_8_vs_16_warps_deep_rings.log.  XBIT_W4P_WARPS=16 keeps the form reachable for tools/ptime.py.)
