@@ -1738,8 +1738,19 @@ cudaError_t launch_ll_unpack(const void* ll_in, void* out_f16, long long n_pairs
 // front of the GEMV costs ~10 us of copy-engine latency per call; measured in bench.py's e2e leg)
 __global__ void pull_rows_kernel(const uint4* __restrict__ src_host, uint4* __restrict__ dst, size_t nvec) {
   griddep_launch_dependents();                      // the GEMV behind may start streaming its weights
+  // The host rows do not depend on the kernel in front (the caller wrote them before enqueueing the call): the PCIe reads
+  // -- about 1.5 us of latency -- are issued BEFORE the wait and only the stores into dst, which the previous GEMV may still
+  // be reading, come after it.  Four vectors per thread cover 1 MiB of activations; a longer tail is read after the wait.
+  const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  uint4 pre[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (i0 + j * stride < nvec) pre[j] = src_host[i0 + j * stride];
   griddep_wait();                                   // the previous GEMV has finished reading dst
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) dst[i] = src_host[i];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (i0 + j * stride < nvec) dst[i0 + j * stride] = pre[j];
+  for (size_t i = i0 + 4 * stride; i < nvec; i += stride) dst[i] = src_host[i];
 }
 
 cudaError_t launch_pull_rows(const void* src_host_devptr, void* dst, size_t bytes, cudaStream_t stream) {
