@@ -97,4 +97,22 @@ capi.check(lib.xbit_ll_unpack_f16(ll[1].data_ptr(), out.data_ptr(), M * N, state
 torch.cuda.synchronize()
 y1 = X.gemv(a, qw, s, qz, 128, 4, K, 1)
 check(out, y1, w, "flag-in-data chain world=1")
+# 8- and 2-bit weights on the persistent kernel (integer block math), both CTA-boundary modes
+for bits in (8, 2):
+    for fine in (0, 1):
+        capi.set_option("XBIT_W4P_FINE", fine)
+        q8, s8, z8 = rand(1024, 512, bits, 128)
+        a8 = torch.randn((2, 1024), device=dev, generator=gen).to(torch.float16)
+        check(X.gemv(a8, q8, s8, z8, 128, bits, 1024, 1), a8, X.dequant(q8, s8, z8, 128, bits, 1024, 1), f"gemv bits={bits} fine={fine}")
+    capi.set_option("XBIT_W4P_FINE")
+# bf16-native forms
+X.set_native_bf16(True)
+try:
+    q4, s4, z4 = rand(1024, 512, 4, 128)
+    sb = s4.to(torch.bfloat16)
+    ab = torch.randn((2, 1024), device=dev, generator=gen).to(torch.bfloat16)
+    wb = X.dequant(q4, sb, z4, 128, 4, 1024, 1)
+    check(X.gemv(ab, q4, sb, z4, 128, 4, 1024, 1), ab, wb, "bf16-native gemv / dequant")
+finally:
+    X.set_native_bf16(False)
 print("all sanitizer cases ran", flush=True)
